@@ -1,0 +1,110 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference (dev container only).
+
+    python -m oracle.make_golden            # rewrites tests/golden/
+
+Every expected value in the fixtures is an output of /root/reference's own code
+(HierarchicalGraph.search, GraphEnvironment.*, AHRAGGymEnv.*) executed through ``oracle/stubs.py``;
+inputs are ``ah_rag_b200.synth.make_graph`` graphs and hash embeddings.  The similarity seam inside
+the reference run is the stub's exact cosine (parity there is unpinned, see oracle/__init__.py).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from ah_rag_b200 import synth  # noqa: E402
+from oracle import ref_runner, stubs  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+GRAPHS = [
+    dict(name="g_small_s3", kw=dict(seed=3)),
+    dict(name="g_dense_s11", kw=dict(seed=11, n_entities=120, n_l1=6, n_l2=3, n_hyperedges=60, related_density=0.5)),
+    dict(name="g_flat_s5", kw=dict(seed=5, n_entities=40, n_l1=3, n_l2=0, n_hyperedges=5)),
+    dict(name="g_filter_s7", kw=dict(seed=7, n_entities=50, n_l1=10, n_l2=2, n_hyperedges=20,
+                                     search_params={"judge_overall_min": 3.0, "member_top_m": 3,
+                                                    "type_filter": ["summary", "entity"],
+                                                    "alpha": 0.5, "beta": 0.3, "gamma": 0.15, "delta": 0.05})),
+]
+
+SEARCH_CASES = [
+    dict(top_k=5), dict(top_k=3, member_top_m=2), dict(top_k=1), dict(top_k=10, type_filter=["summary"]),
+    dict(top_k=8, judge_overall_min=4.0), dict(top_k=8, confidence_min=3.0, alpha=0.3, beta=0.4),
+    dict(top_k=50, member_top_m=5), dict(top_k=200, member_top_m=50),
+]
+
+GYM_ACTION_SEQS = [[1, 0, 2, 2, 3, 4, 5], [0, 0, 0, 0, 0, 0], [2, 1, 3, 3, 1, 2], [3, 4, 1, 5], [5]]
+
+
+def main() -> None:
+    assert ref_runner.reference_available(), "needs /root/reference"
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for spec in GRAPHS:
+        stubs.reset_store()
+        g = synth.make_graph(**spec["kw"])
+        rs = ref_runner.ReferenceSession(g)
+        queries = [f"golden query {i}" for i in range(6)]
+        qvecs = np.stack([stubs.hash_embed(q) for q in queries])
+        fixture = {"name": spec["name"], "make_graph_kwargs": spec["kw"], "node_link": g,
+                   "index_ids": rs.index_ids, "queries": queries, "search": [], "env": [], "gym": []}
+        for qi, q in enumerate(queries):
+            for case in SEARCH_CASES:
+                out = ref_runner.strip_search(rs.search(q, **case))
+                fixture["search"].append({"query": qi, "kwargs": case, "out": out})
+        # environment traces: reset then every expand op on several id slices, then commit
+        for qi in (0, 3):
+            env = rs.make_env()
+            trace = []
+            obs, info = env.reset(seed_query=queries[qi], top_k=5)
+            info = {k: v for k, v in info.items() if k != "time_s"}
+            trace.append({"call": "reset", "args": {"query": qi, "top_k": 5}, "obs": obs, "info": info})
+            ids = [n["node_id"] for n in obs["selection"]]
+            for op in ("expand_parents", "expand_children", "expand_related"):
+                for sl in (ids[:1], ids[:2], ids[1:4], ids, ["not-a-node"] + ids[:1]):
+                    for limit in (10, 3):
+                        o, i = getattr(env, op)(list(sl), limit=limit)
+                        trace.append({"call": op, "args": {"node_ids": list(sl), "limit": limit}, "obs": o, "info": i})
+            o, i = env.commit_selection(ids[:3])
+            trace.append({"call": "commit_selection", "args": {"node_ids": ids[:3]}, "obs": o, "info": i})
+            o, i = env.expand_related(ids[:2])
+            trace.append({"call": "expand_related", "args": {"node_ids": ids[:2], "limit": 10}, "obs": o, "info": i})
+            fixture["env"].append(trace)
+        for si, seq in enumerate(GYM_ACTION_SEQS):
+            gym = rs.make_gym(max_steps=6)
+            qi = si % len(queries)
+            vec, info = gym.reset(queries[qi])
+            steps = [{"vec": [float(x) for x in vec], "mask": info.get("action_mask")}]
+            for a in seq:
+                v, r, d, inf = gym.step(a)
+                steps.append({"action": a, "vec": [float(x) for x in v], "reward": r, "done": d,
+                              "mask": inf.get("action_mask")})
+                if d:
+                    break
+            fixture["gym"].append({"query": qi, "steps": steps})
+        with open(os.path.join(GOLDEN_DIR, spec["name"] + ".json"), "w", encoding="utf-8") as f:
+            json.dump(fixture, f, ensure_ascii=False)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, spec["name"] + ".npz"),
+                            index_rows=rs.index_rows.astype(np.float32), query_vecs=qvecs.astype(np.float32))
+        print(spec["name"], "nodes", rs.hg.G.number_of_nodes(), "edges", rs.hg.G.number_of_edges(),
+              "index", len(rs.index_ids), "search cases", len(fixture["search"]))
+
+    # known answers held by the reference's own tests / shipped data
+    HG = rs.HG
+    known = {
+        "make_entity_id": {"Tim Burton": HG.make_entity_id("Tim Burton")},  # test/test_answer_generator.py:9
+        "empty_graph_hash": HG()._graph_snapshot_hash(),  # graph_datasets/hotpotqa_distractor/meta.json:17
+        "default_search_params": HG().G.graph["search_params"],  # hierarchical_graph.py:37-47
+    }
+    with open(os.path.join(GOLDEN_DIR, "known_answers.json"), "w", encoding="utf-8") as f:
+        json.dump(known, f, indent=1)
+    print(known["make_entity_id"], known["empty_graph_hash"])
+
+
+if __name__ == "__main__":
+    main()
