@@ -1,0 +1,96 @@
+"""ctypes binding of libahrag_b200.so (the C ABI declared in include/ahrag_b200.h).
+
+There is no CPU fallback: if the shared library is missing and cannot be built, importing this module
+raises.  The library itself refuses to run on anything but an sm_100 device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_void_p
+
+from . import _build
+
+AHR_DTYPE_F32, AHR_DTYPE_BF16 = 0, 1
+AHR_MODE_BF16, AHR_MODE_EXACT = 0, 1
+AHR_N_CSR = 6
+CSR_PART_OUT, CSR_PART_IN, CSR_BEL_OUT, CSR_BEL_IN, CSR_REL_OUT, CSR_REL_IN = range(6)
+NT_ENTITY, NT_SUMMARY, NT_HYPEREDGE, NT_OTHER = 0, 1, 2, 3
+EK_SEED, EK_PARENT, EK_MEMBER = 1, 2, 3
+OP_PARENTS, OP_CHILDREN, OP_RELATED = 0, 1, 2
+
+# every symbol include/ahrag_b200.h declares (tests/test_abi.py checks the header against this list)
+EXPORTS = [
+    "ahr_last_error", "ahr_version", "ahr_launch_count", "ahr_index_create", "ahr_index_destroy", "ahr_topk",
+    "ahr_topk_host", "ahr_merge_topk", "ahr_graph_create", "ahr_graph_destroy", "ahr_anchor_rerank", "ahr_expand",
+    "ahr_debug_tc_scores", "ahr_rescore", "ahr_debug_round4", "ahr_exact_stats",
+]
+
+
+class RerankParams(ctypes.Structure):
+    """Mirror of ``struct ahr_rerank_params``."""
+    _fields_ = [
+        ("alpha", c_double), ("beta", c_double), ("gamma", c_double), ("delta", c_double),
+        ("boost", c_double * 4),
+        ("judge_min", c_double), ("conf_min", c_double),
+        ("has_judge_min", c_int32), ("has_conf_min", c_int32),
+        ("type_mask", c_int32), ("member_top_m", c_int32), ("parent_cap", c_int32), ("reserved", c_int32),
+    ]
+
+
+def _declare(lib: ctypes.CDLL) -> None:
+    vp = c_void_p
+    lib.ahr_last_error.restype = c_char_p
+    lib.ahr_last_error.argtypes = []
+    lib.ahr_version.restype = c_int
+    lib.ahr_launch_count.restype = c_int64
+    lib.ahr_index_create.argtypes = [POINTER(vp), c_int, c_int64, c_int32, c_int, vp, c_int64]
+    lib.ahr_index_destroy.argtypes = [vp]
+    lib.ahr_topk.argtypes = [vp, vp, c_int32, c_int32, c_int, vp, vp, vp]
+    lib.ahr_topk_host.argtypes = [vp, vp, c_int32, c_int32, c_int, vp, vp, vp]
+    lib.ahr_merge_topk.argtypes = [c_int, vp, vp, c_int32, c_int32, c_int32, vp, vp, vp]
+    lib.ahr_graph_create.argtypes = [POINTER(vp), c_int, c_int64, POINTER(vp), POINTER(vp), vp, vp, vp, vp, vp]
+    lib.ahr_graph_destroy.argtypes = [vp]
+    lib.ahr_anchor_rerank.argtypes = [vp, c_int32, c_int32, vp, vp, POINTER(RerankParams), c_int32,
+                                      vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ahr_expand.argtypes = [vp, c_int32, vp, vp, vp, c_int32, vp, vp, vp]
+    lib.ahr_debug_tc_scores.argtypes = [vp, vp, c_int32, vp, vp]
+    lib.ahr_rescore.argtypes = [vp, vp, c_int32, c_int32, vp, vp, vp]
+    lib.ahr_debug_round4.argtypes = [c_int, vp, c_int64, vp, vp]
+    lib.ahr_exact_stats.argtypes = [vp, POINTER(c_int64), POINTER(c_int64)]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("ahr_last_error", "ahr_launch_count"):
+            fn.restype = c_int
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load (building first if sources are newer and nvcc is present) the CUDA library.  Fails loudly."""
+    global _lib
+    if _lib is None:
+        if _build.needs_build():
+            try:
+                _build.build()
+            except Exception as e:  # no nvcc on this machine: only fatal if there is no prebuilt library
+                if not os.path.exists(_build.LIB_PATH):
+                    raise ImportError(
+                        "ah_rag_b200: libahrag_b200.so is missing and could not be built "
+                        f"({e}); run `python -c 'import __graft_entry__ as g; g.build()'` on a machine with nvcc. "
+                        "There is no CPU fallback.") from e
+        lib = ctypes.CDLL(_build.LIB_PATH)
+        _declare(lib)
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().ahr_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libahrag_b200 {what} failed (code {rc}): {msg}")

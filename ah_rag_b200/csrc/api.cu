@@ -1,0 +1,387 @@
+// api.cu -- the C ABI of libahrag_b200 (include/ahrag_b200.h): handles, workspaces, orchestration.
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ahr {
+
+static thread_local std::string g_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+
+// grow-only device buffer
+struct DevBuf {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need) {
+    if (need <= bytes) return AHR_OK;
+    if (ptr) AHR_CUDA_CHECK(cudaFree(ptr));
+    ptr = nullptr;
+    bytes = 0;
+    need = (need + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&ptr, need);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+      return AHR_E_NOMEM;
+    }
+    bytes = need;
+    return AHR_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+};
+
+}  // namespace ahr
+
+using namespace ahr;
+
+struct ahr_index {
+  int device = 0;
+  int sm_count = 148;
+  int64_t n_rows = 0;
+  int32_t dim = 0;
+  int dtype = 0;
+  const void *rows = nullptr;
+  int64_t id_base = 0;
+  bool has_map = false;
+  CUtensorMap map_x;
+  DevBuf ws;        // partial lists / score chunks
+  DevBuf ws2;       // exact-mode scratch
+  DevBuf hq, hs, hi;  // device staging of the *_host entry point
+  float *d_max_norm = nullptr;
+  int64_t n_certified = 0, n_fallback = 0;
+};
+
+struct ahr_graph {
+  int device = 0;
+  GraphView view;
+  DevBuf ws;
+};
+
+extern "C" {
+
+const char *ahr_last_error(void) { return g_error.c_str(); }
+int ahr_version(void) { return AHR_VERSION; }
+int64_t ahr_launch_count(void) { return g_launches.load(); }
+
+// ---------------------------------------------------------------------------------------------
+int ahr_index_create(ahr_index **out, int device, int64_t n_rows, int32_t dim, int dtype, const void *dev_rows,
+                     int64_t id_base) {
+  AHR_REQUIRE(out != nullptr, "ahr_index_create: out is NULL");
+  AHR_REQUIRE(n_rows >= 0 && dim >= 1, "ahr_index_create: bad shape [%lld, %d]", (long long)n_rows, dim);
+  AHR_REQUIRE(dtype == AHR_DTYPE_F32 || dtype == AHR_DTYPE_BF16, "ahr_index_create: unknown dtype %d", dtype);
+  AHR_REQUIRE(n_rows == 0 || dev_rows != nullptr, "ahr_index_create: dev_rows is NULL");
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    set_error("ahr_index_create: cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+    return AHR_E_CUDA;
+  }
+  cudaDeviceProp prop;
+  AHR_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("libahrag_b200 is built for sm_100a (Blackwell B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+    return AHR_E_UNSUPPORTED;
+  }
+  ahr_index *idx = new ahr_index();
+  idx->device = device;
+  idx->sm_count = prop.multiProcessorCount;
+  idx->n_rows = n_rows;
+  idx->dim = dim;
+  idx->dtype = dtype;
+  idx->rows = dev_rows;
+  idx->id_base = id_base;
+  if (dtype == AHR_DTYPE_BF16 && n_rows > 0 && dim % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(dev_rows) & 15) == 0) {
+    int rc = tc_make_corpus_map(&idx->map_x, dev_rows, n_rows, dim);
+    if (rc != AHR_OK) { delete idx; return rc; }
+    idx->has_map = true;
+  }
+  cudaError_t e = cudaMalloc(&idx->d_max_norm, sizeof(float));
+  if (e != cudaSuccess) { delete idx; set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return AHR_E_NOMEM; }
+  int rc = row_norms_max(dev_rows, dtype, n_rows, dim, idx->d_max_norm, 0);
+  if (rc != AHR_OK) { cudaFree(idx->d_max_norm); delete idx; return rc; }
+  AHR_CUDA_CHECK(cudaStreamSynchronize(0));
+  *out = idx;
+  return AHR_OK;
+}
+
+int ahr_index_destroy(ahr_index *idx) {
+  if (!idx) return AHR_OK;
+  DeviceGuard guard(idx->device);
+  idx->ws.release(); idx->ws2.release(); idx->hq.release(); idx->hs.release(); idx->hi.release();
+  if (idx->d_max_norm) cudaFree(idx->d_max_norm);
+  delete idx;
+  return AHR_OK;
+}
+
+// brute-force exact scan for a subset of queries (q_sel == nullptr: all), results into out_* [nq_sel, k]
+static int exact_bruteforce(ahr_index *idx, const void *dev_q, const int32_t *q_sel, int32_t nq_sel, int32_t k,
+                            float *out_scores, int64_t *out_ids, DevBuf &scratch, cudaStream_t st) {
+  if (nq_sel <= 0) return AHR_OK;
+  int64_t chunk = (int64_t)(64ll << 20) / nq_sel;  // <= 256 MB of scores
+  chunk = std::max<int64_t>(64, std::min<int64_t>(chunk, std::max<int64_t>(idx->n_rows, 1)));
+  int rc = scratch.reserve((size_t)nq_sel * chunk * sizeof(float));
+  if (rc != AHR_OK) return rc;
+  float *sc = reinterpret_cast<float *>(scratch.ptr);
+  bool first = true;
+  if (idx->n_rows == 0) return select_topk(sc, nullptr, nullptr, 0, 0, nq_sel, k, 0, false, out_scores, out_ids, st);
+  for (int64_t r0 = 0; r0 < idx->n_rows; r0 += chunk) {
+    const int64_t n = std::min(chunk, idx->n_rows - r0);
+    rc = exact_scores(idx->rows, dev_q, idx->dtype, idx->dim, r0, n, q_sel, nq_sel, sc, st);
+    if (rc != AHR_OK) return rc;
+    rc = select_topk(sc, nullptr, nullptr, n, n, nq_sel, k, idx->id_base + r0, !first, out_scores, out_ids, st);
+    if (rc != AHR_OK) return rc;
+    first = false;
+  }
+  return AHR_OK;
+}
+
+// tensor-core path: per-slab partial lists (K1) + per-query reduction, results [nq, k] with global ids
+static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, float *out_scores, int64_t *out_ids,
+                   float *dbg_scores, cudaStream_t st) {
+  AHR_REQUIRE(idx->dtype == AHR_DTYPE_BF16, "the tensor-core path needs a bf16 index");
+  AHR_REQUIRE(idx->has_map, "bf16 index is not TMA-addressable (dim %% 8 != 0 or rows not 16-byte aligned)");
+  AHR_REQUIRE((reinterpret_cast<uintptr_t>(dev_q) & 15) == 0, "queries must be 16-byte aligned");
+  const int64_t n_ctiles = (idx->n_rows + 255) / 256;
+  const int32_t n_qtiles = (nq + 127) / 128;
+  const int S = tc_choose_slabs(n_qtiles, n_ctiles, idx->sm_count);
+  const size_t n_part = (size_t)nq * S * k;
+  int rc = idx->ws.reserve(n_part * 8);
+  if (rc != AHR_OK) return rc;
+  float *ps = reinterpret_cast<float *>(idx->ws.ptr);
+  int32_t *pi = reinterpret_cast<int32_t *>(ps + n_part);
+  rc = tc_topk_partials(idx->map_x, dev_q, idx->n_rows, idx->dim, nq, k, S, idx->sm_count, ps, pi, dbg_scores, st);
+  if (rc != AHR_OK) return rc;
+  return select_topk(ps, pi, nullptr, (int64_t)S * k, (int64_t)S * k, nq, k, idx->id_base, false, out_scores, out_ids, st);
+}
+
+int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode, float *dev_scores, int64_t *dev_ids,
+             void *stream) {
+  AHR_REQUIRE(idx != nullptr, "ahr_topk: index is NULL");
+  AHR_REQUIRE(nq >= 0 && k >= 1, "ahr_topk: bad sizes nq=%d k=%d", nq, k);
+  AHR_REQUIRE(k <= SELECT_MAX_K, "ahr_topk: k must be <= %d (got %d)", SELECT_MAX_K, k);
+  AHR_REQUIRE(mode == AHR_MODE_BF16 || mode == AHR_MODE_EXACT, "ahr_topk: unknown mode %d", mode);
+  if (nq == 0) return AHR_OK;
+  AHR_REQUIRE(dev_q && dev_scores && dev_ids, "ahr_topk: NULL buffer");
+  DeviceGuard guard(idx->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  if (mode == AHR_MODE_BF16) {
+    AHR_REQUIRE(k <= 128, "AHR_MODE_BF16 supports k <= 128 (got %d); use AHR_MODE_EXACT", k);
+    if (idx->n_rows == 0) return select_topk(dev_scores, nullptr, nullptr, 0, 0, nq, k, 0, false, dev_scores, dev_ids, st);
+    return tc_topk(idx, dev_q, nq, k, dev_scores, dev_ids, nullptr, st);
+  }
+
+  // ---- exact mode ----
+  idx->n_certified = 0;
+  idx->n_fallback = 0;
+  const bool use_tc = idx->dtype == AHR_DTYPE_BF16 && idx->has_map && k <= 96 && idx->n_rows > 4096 &&
+                      (reinterpret_cast<uintptr_t>(dev_q) & 15) == 0;
+  if (!use_tc) {
+    idx->n_fallback = nq;
+    return exact_bruteforce(idx, dev_q, nullptr, nq, k, dev_scores, dev_ids, idx->ws, st);
+  }
+  const int32_t kc = k <= 40 ? 64 : 128;  // candidates per query: k plus slack for the tensor-core rounding error
+  // scratch: cand scores/ids [nq,kc], exact scores [nq,kc], eps [nq], flags [nq], list [nq], count
+  const size_t nc = (size_t)nq * kc;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_cs = carve(nc * 4), o_ci = carve(nc * 8), o_ex = carve(nc * 4), o_eps = carve((size_t)nq * 4),
+               o_flag = carve((size_t)nq * 4), o_list = carve((size_t)nq * 4), o_cnt = carve(4),
+               o_fs = carve((size_t)nq * k * 4), o_fi = carve((size_t)nq * k * 8);
+  int rc = idx->ws2.reserve(off);
+  if (rc != AHR_OK) return rc;
+  uint8_t *w = reinterpret_cast<uint8_t *>(idx->ws2.ptr);
+  float *cs = reinterpret_cast<float *>(w + o_cs);
+  int64_t *ci = reinterpret_cast<int64_t *>(w + o_ci);
+  float *ex = reinterpret_cast<float *>(w + o_ex);
+  float *eps = reinterpret_cast<float *>(w + o_eps);
+  int32_t *flags = reinterpret_cast<int32_t *>(w + o_flag);
+  int32_t *flist = reinterpret_cast<int32_t *>(w + o_list);
+  int32_t *fcnt = reinterpret_cast<int32_t *>(w + o_cnt);
+  float *fs = reinterpret_cast<float *>(w + o_fs);
+  int64_t *fi = reinterpret_cast<int64_t *>(w + o_fi);
+
+  rc = tc_topk(idx, dev_q, nq, kc, cs, ci, nullptr, st);
+  if (rc != AHR_OK) return rc;
+  rc = exact_rescore(idx->rows, dev_q, idx->dtype, idx->dim, nq, kc, ci, idx->id_base, ex, st);
+  if (rc != AHR_OK) return rc;
+  // |tensor - canonical| <= eps_rel * ||q|| * ||x||: fp32 accumulation over dim/16 MMA steps plus the in-step
+  // alignment of 16 exact products; 2^-23 per accumulation step with generous headroom
+  const float eps_rel = (float)((idx->dim / 8 + 32) * std::ldexp(1.0, -23));
+  rc = query_eps(dev_q, idx->dtype, nq, idx->dim, idx->d_max_norm, eps_rel, eps, st);
+  if (rc != AHR_OK) return rc;
+  AHR_CUDA_CHECK(cudaMemsetAsync(fcnt, 0, 4, st));
+  rc = exact_certify(cs, ci, ex, nq, kc, k, eps, dev_scores, dev_ids, flags, fcnt, flist, st);
+  if (rc != AHR_OK) return rc;
+  int32_t n_fail = 0;
+  AHR_CUDA_CHECK(cudaMemcpyAsync(&n_fail, fcnt, 4, cudaMemcpyDeviceToHost, st));
+  AHR_CUDA_CHECK(cudaStreamSynchronize(st));
+  idx->n_certified = nq - n_fail;
+  idx->n_fallback = n_fail;
+  if (n_fail > 0) {
+    rc = exact_bruteforce(idx, dev_q, flist, n_fail, k, fs, fi, idx->ws, st);
+    if (rc != AHR_OK) return rc;
+    rc = gather_rows_i64(fs, fi, flist, n_fail, k, dev_scores, dev_ids, /*scatter=*/true, st);
+    if (rc != AHR_OK) return rc;
+  }
+  return AHR_OK;
+}
+
+int ahr_topk_host(ahr_index *idx, const void *host_q, int32_t nq, int32_t k, int mode, float *host_scores,
+                  int64_t *host_ids, void *stream) {
+  AHR_REQUIRE(idx != nullptr, "ahr_topk_host: index is NULL");
+  AHR_REQUIRE(nq >= 0 && k >= 1, "ahr_topk_host: bad sizes nq=%d k=%d", nq, k);
+  if (nq == 0) return AHR_OK;
+  AHR_REQUIRE(host_q && host_scores && host_ids, "ahr_topk_host: NULL buffer");
+  DeviceGuard guard(idx->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t esz = idx->dtype == AHR_DTYPE_F32 ? 4 : 2;
+  const size_t qb = (size_t)nq * idx->dim * esz, sb = (size_t)nq * k * 4, ib = (size_t)nq * k * 8;
+  int rc;
+  if ((rc = idx->hq.reserve(qb)) != AHR_OK) return rc;
+  if ((rc = idx->hs.reserve(sb)) != AHR_OK) return rc;
+  if ((rc = idx->hi.reserve(ib)) != AHR_OK) return rc;
+  AHR_CUDA_CHECK(cudaMemcpyAsync(idx->hq.ptr, host_q, qb, cudaMemcpyHostToDevice, st));
+  rc = ahr_topk(idx, idx->hq.ptr, nq, k, mode, reinterpret_cast<float *>(idx->hs.ptr),
+                reinterpret_cast<int64_t *>(idx->hi.ptr), stream);
+  if (rc != AHR_OK) return rc;
+  AHR_CUDA_CHECK(cudaMemcpyAsync(host_scores, idx->hs.ptr, sb, cudaMemcpyDeviceToHost, st));
+  AHR_CUDA_CHECK(cudaMemcpyAsync(host_ids, idx->hi.ptr, ib, cudaMemcpyDeviceToHost, st));
+  AHR_CUDA_CHECK(cudaStreamSynchronize(st));
+  return AHR_OK;
+}
+
+int ahr_merge_topk(int device, const float *dev_scores, const int64_t *dev_ids, int32_t parts, int32_t nq, int32_t k,
+                   float *dev_out_scores, int64_t *dev_out_ids, void *stream) {
+  AHR_REQUIRE(parts >= 1 && nq >= 0 && k >= 1, "ahr_merge_topk: bad sizes parts=%d nq=%d k=%d", parts, nq, k);
+  if (nq == 0) return AHR_OK;
+  AHR_REQUIRE(dev_scores && dev_ids && dev_out_scores && dev_out_ids, "ahr_merge_topk: NULL buffer");
+  DeviceGuard guard(device);
+  // [parts, nq, k]: candidate i = (part, j) of query q at q * k + part * (nq * k) + j
+  return select_topk_strided(dev_scores, nullptr, dev_ids, k, (int64_t)parts * k, k, (int64_t)nq * k, nq, k, 0, false,
+                             dev_out_scores, dev_out_ids, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ahr_debug_tc_scores(ahr_index *idx, const void *dev_q, int32_t nq, float *dev_out, void *stream) {
+  AHR_REQUIRE(idx && dev_q && dev_out && nq >= 1, "ahr_debug_tc_scores: bad arguments");
+  AHR_REQUIRE(idx->n_rows >= 1, "ahr_debug_tc_scores: empty index");
+  DeviceGuard guard(idx->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int k = 8;
+  const size_t ids_off = (((size_t)nq * k * 4) + 255) & ~(size_t)255;
+  int rc = idx->ws2.reserve(ids_off + (size_t)nq * k * 8);
+  if (rc != AHR_OK) return rc;
+  float *s = reinterpret_cast<float *>(idx->ws2.ptr);
+  int64_t *i = reinterpret_cast<int64_t *>(reinterpret_cast<uint8_t *>(idx->ws2.ptr) + ids_off);
+  return tc_topk(idx, dev_q, nq, k, s, i, dev_out, st);
+}
+
+int ahr_rescore(ahr_index *idx, const void *dev_q, int32_t nq, int32_t m, const int64_t *dev_cand_ids,
+                float *dev_out_scores, void *stream) {
+  AHR_REQUIRE(idx && dev_q && dev_cand_ids && dev_out_scores, "ahr_rescore: NULL argument");
+  DeviceGuard guard(idx->device);
+  return exact_rescore(idx->rows, dev_q, idx->dtype, idx->dim, nq, m, dev_cand_ids, idx->id_base, dev_out_scores,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ahr_exact_stats(ahr_index *idx, int64_t *n_certified, int64_t *n_fallback) {
+  AHR_REQUIRE(idx != nullptr, "ahr_exact_stats: index is NULL");
+  if (n_certified) *n_certified = idx->n_certified;
+  if (n_fallback) *n_fallback = idx->n_fallback;
+  return AHR_OK;
+}
+
+int ahr_debug_round4(int device, const double *dev_x, int64_t n, double *dev_out, void *stream) {
+  AHR_REQUIRE(dev_x && dev_out, "ahr_debug_round4: NULL buffer");
+  DeviceGuard guard(device);
+  return debug_round4(dev_x, n, dev_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+int ahr_graph_create(ahr_graph **out, int device, int64_t n_nodes, const int64_t *const dev_row_ptr[AHR_N_CSR],
+                     const int32_t *const dev_col_idx[AHR_N_CSR], const uint8_t *dev_node_type,
+                     const uint8_t *dev_level, const double *dev_judge, const double *dev_judge_term,
+                     const double *dev_conf) {
+  AHR_REQUIRE(out != nullptr, "ahr_graph_create: out is NULL");
+  AHR_REQUIRE(n_nodes >= 0 && n_nodes < (int64_t)INT32_MAX, "ahr_graph_create: n_nodes %lld out of range", (long long)n_nodes);
+  AHR_REQUIRE(dev_row_ptr && dev_col_idx, "ahr_graph_create: NULL CSR tables");
+  for (int s = 0; s < AHR_N_CSR; ++s) AHR_REQUIRE(dev_row_ptr[s] != nullptr, "ahr_graph_create: row_ptr[%d] is NULL", s);
+  AHR_REQUIRE(n_nodes == 0 || (dev_node_type && dev_level && dev_judge && dev_judge_term && dev_conf),
+              "ahr_graph_create: NULL attribute array");
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    set_error("ahr_graph_create: cannot select CUDA device %d", device);
+    return AHR_E_CUDA;
+  }
+  ahr_graph *g = new ahr_graph();
+  g->device = device;
+  g->view.n_nodes = n_nodes;
+  for (int s = 0; s < AHR_N_CSR; ++s) {
+    g->view.row_ptr[s] = dev_row_ptr[s];
+    g->view.col_idx[s] = dev_col_idx[s];
+  }
+  g->view.node_type = dev_node_type;
+  g->view.level = dev_level;
+  g->view.judge = dev_judge;
+  g->view.judge_term = dev_judge_term;
+  g->view.conf = dev_conf;
+  *out = g;
+  return AHR_OK;
+}
+
+int ahr_graph_destroy(ahr_graph *g) {
+  if (!g) return AHR_OK;
+  DeviceGuard guard(g->device);
+  g->ws.release();
+  delete g;
+  return AHR_OK;
+}
+
+int ahr_anchor_rerank(ahr_graph *g, int32_t nq, int32_t n_seeds, const int32_t *dev_seed_nodes,
+                      const float *dev_seed_scores, const ahr_rerank_params *params, int32_t top_k,
+                      int32_t *dev_out_nodes, double *dev_out_semantic, double *dev_out_score, int32_t *dev_out_count,
+                      int32_t *dev_exp_nodes, double *dev_exp_semantic, uint8_t *dev_exp_kind, int32_t *dev_exp_count,
+                      double *dev_seed_semantic, void *stream) {
+  AHR_REQUIRE(g && params, "ahr_anchor_rerank: NULL handle or params");
+  if (nq == 0) return AHR_OK;
+  AHR_REQUIRE(dev_seed_nodes && dev_seed_scores && dev_out_nodes && dev_out_semantic && dev_out_score && dev_out_count,
+              "ahr_anchor_rerank: NULL buffer");
+  AHR_REQUIRE(!dev_exp_nodes || dev_exp_semantic, "ahr_anchor_rerank: exp_nodes needs exp_semantic");
+  DeviceGuard guard(g->device);
+  const size_t need = graph_anchor_workspace_bytes(nq, n_seeds, *params);
+  if (need) {
+    int rc = g->ws.reserve(need);
+    if (rc != AHR_OK) return rc;
+  }
+  return graph_anchor_rerank(g->view, nq, n_seeds, dev_seed_nodes, dev_seed_scores, *params, top_k, dev_out_nodes,
+                             dev_out_semantic, dev_out_score, dev_out_count, dev_exp_nodes, dev_exp_semantic,
+                             dev_exp_kind, dev_exp_count, dev_seed_semantic, g->ws.ptr, g->ws.bytes,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ahr_expand(ahr_graph *g, int32_t n_env, const int32_t *dev_ops, const int32_t *dev_in_ids,
+               const int32_t *dev_in_offsets, int32_t limit, int32_t *dev_out_ids, int32_t *dev_out_counts,
+               void *stream) {
+  AHR_REQUIRE(g != nullptr, "ahr_expand: graph is NULL");
+  if (n_env == 0) return AHR_OK;
+  AHR_REQUIRE(dev_ops && dev_in_offsets && dev_out_ids && dev_out_counts, "ahr_expand: NULL buffer");
+  DeviceGuard guard(g->device);
+  return graph_expand(g->view, n_env, dev_ops, dev_in_ids, dev_in_offsets, limit, dev_out_ids, dev_out_counts,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// kernels.h -- internal host-side entry points of the kernel translation units (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "../../include/ahrag_b200.h"
+
+namespace ahr {
+
+// ---- topk_tc.cu (K1) ----
+int tc_make_corpus_map(CUtensorMap *map, const void *dev_rows, int64_t n_rows, int32_t dim);
+int tc_choose_slabs(int32_t n_qtiles, int64_t n_ctiles, int grid);
+int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows, int32_t dim, int32_t nq, int32_t k,
+                     int32_t n_slabs, int grid, float *part_scores, int32_t *part_ids, float *dbg_scores,
+                     cudaStream_t stream);
+
+// ---- select.cu ----
+// Per query: reduce n_cand candidates to the top k by (score desc, id asc).
+//   cand_scores[q * stride + i];  ids: cand_ids32 / cand_ids64 (one may be given) or implicit = i;
+//   final id = id + id_offset (entries with raw id < 0 are skipped).
+//   carry_in: the current contents of out_* (k entries, id < 0 = empty) take part in the selection.
+int select_topk(const float *cand_scores, const int32_t *cand_ids32, const int64_t *cand_ids64, int64_t stride,
+                int64_t n_cand, int32_t nq, int32_t k, int64_t id_offset, bool carry_in, float *out_scores,
+                int64_t *out_ids, cudaStream_t stream);
+// general addressing: candidate i of query q at q * stride + (i / inner) * stride_outer + (i % inner)
+int select_topk_strided(const float *cand_scores, const int32_t *cand_ids32, const int64_t *cand_ids64, int64_t stride,
+                        int64_t n_cand, int64_t inner, int64_t stride_outer, int32_t nq, int32_t k, int64_t id_offset,
+                        bool carry_in, float *out_scores, int64_t *out_ids, cudaStream_t stream);
+constexpr int SELECT_MAX_K = 1024;
+
+// ---- topk_exact.cu (K1x) ----
+// canonical scores of rows [row0, row0 + n_chunk) for the queries listed in q_sel (or all nq when q_sel == nullptr):
+// out[qi * n_chunk + r]
+int exact_scores(const void *dev_rows, const void *dev_q, int dtype, int32_t dim, int64_t row0, int64_t n_chunk,
+                 const int32_t *q_sel, int32_t nq_sel, float *out, cudaStream_t stream);
+int exact_rescore(const void *dev_rows, const void *dev_q, int dtype, int32_t dim, int32_t nq, int32_t m,
+                  const int64_t *cand_ids, int64_t id_base, float *out_scores, cudaStream_t stream);
+// certification of tensor-core candidate sets (see api.cu)
+int exact_certify(const float *tc_scores, const int64_t *tc_ids, const float *ex_scores, int32_t nq, int32_t kc,
+                  int32_t k, const float *eps_per_query, float *out_scores, int64_t *out_ids, int32_t *fail_flags,
+                  int32_t *fail_count, int32_t *fail_list, cudaStream_t stream);
+int row_norms_max(const void *dev_rows, int dtype, int64_t n_rows, int32_t dim, float *dev_out_max, cudaStream_t stream);
+int query_eps(const void *dev_q, int dtype, int32_t nq, int32_t dim, const float *dev_max_row_norm, float eps_rel,
+              float *dev_eps, cudaStream_t stream);
+int gather_rows_i64(const float *src_s, const int64_t *src_i, const int32_t *sel, int32_t n_sel, int32_t k,
+                    float *dst_s, int64_t *dst_i, bool scatter, cudaStream_t stream);
+
+// ---- graph.cu (K2) ----
+struct GraphView {
+  int64_t n_nodes;
+  const int64_t *row_ptr[AHR_N_CSR];
+  const int32_t *col_idx[AHR_N_CSR];
+  const uint8_t *node_type;
+  const uint8_t *level;
+  const double *judge;
+  const double *judge_term;
+  const double *conf;
+};
+int graph_anchor_rerank(const GraphView &g, int32_t nq, int32_t n_seeds, const int32_t *seed_nodes,
+                        const float *seed_scores, const ahr_rerank_params &prm, int32_t top_k, int32_t *out_nodes,
+                        double *out_sem, double *out_score, int32_t *out_count, int32_t *exp_nodes, double *exp_sem,
+                        uint8_t *exp_kind, int32_t *exp_count, double *seed_sem, void *workspace, size_t workspace_bytes,
+                        cudaStream_t stream);
+size_t graph_anchor_workspace_bytes(int32_t nq, int32_t n_seeds, const ahr_rerank_params &prm);
+int graph_expand(const GraphView &g, int32_t n_env, const int32_t *ops, const int32_t *in_ids,
+                 const int32_t *in_offsets, int32_t limit, int32_t *out_ids, int32_t *out_counts, cudaStream_t stream);
+int debug_round4(const double *x, int64_t n, double *out, cudaStream_t stream);
+
+}  // namespace ahr

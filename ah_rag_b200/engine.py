@@ -1,0 +1,287 @@
+"""Host-side handles over the C ABI: device memory, streams and lifetimes come from PyTorch; every
+computation is a call into libahrag_b200.so with raw device pointers.  No CPU fallback anywhere.
+
+  VectorIndex  -- device-resident embedding matrix + batched top-k          (replaces the Chroma collection,
+                                                                               hierarchical_graph.py:605-611, :714)
+  GraphCSR     -- device-resident typed CSR + node attributes               (replaces the NetworkX adjacency
+                                                                               reads, hierarchical_graph.py:441-462)
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Any, Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RerankParams, check
+
+_NT_BITS = {"entity": 1 << 0, "summary": 1 << 1, "hyperedge": 1 << 2}
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the engine has no CPU path")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    """CUDA kernels launched by the library so far in this process (bench.py's ``gpu_launches``)."""
+    return int(_lib.load().ahr_launch_count())
+
+
+class VectorIndex:
+    """Embedding index over rows already resident on one GPU.  ``rows``: [n, dim] float32 or bfloat16."""
+
+    def __init__(self, rows: torch.Tensor, id_base: int = 0) -> None:
+        self.lib = _lib.load()
+        _require_cuda(rows, "rows")
+        if rows.dim() != 2 or rows.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("rows must be a [n, dim] float32 or bfloat16 tensor")
+        self.rows = rows  # keep alive: the library borrows the pointer
+        self.device = rows.device
+        self.n, self.dim = int(rows.shape[0]), int(rows.shape[1])
+        self.dtype = rows.dtype
+        self.id_base = int(id_base)
+        self._h = ctypes.c_void_p()
+        code = _lib.AHR_DTYPE_F32 if rows.dtype == torch.float32 else _lib.AHR_DTYPE_BF16
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_index_create(ctypes.byref(self._h), self.device.index or 0, self.n, self.dim, code,
+                                            rows.data_ptr() if self.n else None, self.id_base), "ahr_index_create")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.ahr_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _mode(self, mode: str) -> int:
+        if mode == "bf16":
+            return _lib.AHR_MODE_BF16
+        if mode in ("exact", "fp32"):
+            return _lib.AHR_MODE_EXACT
+        raise ValueError(f"unknown mode {mode!r} (bf16 | exact)")
+
+    def topk(self, q: torch.Tensor, k: int, mode: str = "bf16") -> Tuple[torch.Tensor, torch.Tensor]:
+        """scores [nq, k] float32 and ids [nq, k] int64 on the device, sorted by (score desc, id asc)."""
+        _require_cuda(q, "q")
+        if q.dim() != 2 or q.shape[1] != self.dim or q.dtype != self.dtype:
+            raise ValueError(f"q must be [nq, {self.dim}] {self.dtype}")
+        nq = int(q.shape[0])
+        scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_topk(self._h, q.data_ptr(), nq, int(k), self._mode(mode), scores.data_ptr(),
+                                    ids.data_ptr(), _stream_ptr(self.device)), "ahr_topk")
+        return scores, ids
+
+    def topk_host(self, q_host: torch.Tensor, k: int, mode: str = "bf16",
+                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """End-to-end call with HOST buffers (H2D copy of the queries, top-k, D2H copy of the results)."""
+        if q_host.is_cuda or not q_host.is_contiguous() or q_host.dtype != self.dtype:
+            raise ValueError("q_host must be a contiguous host tensor of the index dtype")
+        nq = int(q_host.shape[0])
+        if out is None:
+            out = (torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                   torch.empty((nq, k), dtype=torch.int64).pin_memory())
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_topk_host(self._h, q_host.data_ptr(), nq, int(k), self._mode(mode), out[0].data_ptr(),
+                                         out[1].data_ptr(), _stream_ptr(self.device)), "ahr_topk_host")
+        return out
+
+    def exact_stats(self) -> Tuple[int, int]:
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        check(self.lib.ahr_exact_stats(self._h, ctypes.byref(a), ctypes.byref(b)), "ahr_exact_stats")
+        return int(a.value), int(b.value)
+
+    def rescore(self, q: torch.Tensor, cand_ids: torch.Tensor) -> torch.Tensor:
+        _require_cuda(q, "q")
+        _require_cuda(cand_ids, "cand_ids")
+        out = torch.empty(cand_ids.shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_rescore(self._h, q.data_ptr(), int(q.shape[0]), int(cand_ids.shape[1]),
+                                       cand_ids.data_ptr(), out.data_ptr(), _stream_ptr(self.device)), "ahr_rescore")
+        return out
+
+    def debug_tc_scores(self, q: torch.Tensor) -> torch.Tensor:
+        """Raw tensor-core accumulators for every (query, row) pair -- tests only, small inputs."""
+        _require_cuda(q, "q")
+        out = torch.full((int(q.shape[0]), self.n), float("nan"), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_debug_tc_scores(self._h, q.data_ptr(), int(q.shape[0]), out.data_ptr(),
+                                               _stream_ptr(self.device)), "ahr_debug_tc_scores")
+        return out
+
+
+def merge_topk(scores: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Device k-way merge of [parts, nq, k] candidate lists (the step after the NCCL all-gather)."""
+    _require_cuda(scores, "scores")
+    _require_cuda(ids, "ids")
+    parts, nq, k = (int(x) for x in scores.shape)
+    if scores.dtype != torch.float32 or ids.dtype != torch.int64 or tuple(ids.shape) != (parts, nq, k):
+        raise ValueError("scores must be float32 [parts, nq, k] and ids int64 of the same shape")
+    lib = _lib.load()
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        check(lib.ahr_merge_topk(scores.device.index or 0, scores.data_ptr(), ids.data_ptr(), parts, nq, k,
+                                 out_s.data_ptr(), out_i.data_ptr(), _stream_ptr(scores.device)), "ahr_merge_topk")
+    return out_s, out_i
+
+
+def round4_device(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, "x")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().ahr_debug_round4(x.device.index or 0, x.data_ptr(), x.numel(), out.data_ptr(),
+                                           _stream_ptr(x.device)), "ahr_debug_round4")
+    return out
+
+
+@dataclass
+class SearchParams:
+    """Resolved knobs of HierarchicalGraph.search (hierarchical_graph.py:681-699)."""
+    alpha: float = 0.6
+    beta: float = 0.2
+    gamma: float = 0.1
+    delta: float = 0.1
+    judge_overall_min: Optional[float] = None
+    confidence_min: Optional[float] = None
+    type_filter: Optional[Sequence[str]] = None
+    member_top_m: int = 5
+    layer_boost: Optional[Dict[str, float]] = None
+    parent_cap: int = 2
+
+    def to_c(self) -> RerankParams:
+        p = RerankParams()
+        p.alpha, p.beta, p.gamma, p.delta = float(self.alpha), float(self.beta), float(self.gamma), float(self.delta)
+        lb = self.layer_boost if self.layer_boost is not None else {"entity": 0.0, "summary": 1.0, "hyperedge": 0.0}
+        # float(layer_boost_map.get(node_type, 0.0)): a node without node_type looks up the key None
+        p.boost[0] = float(lb.get("entity", 0.0))
+        p.boost[1] = float(lb.get("summary", 0.0))
+        p.boost[2] = float(lb.get("hyperedge", 0.0))
+        p.boost[3] = float(lb.get(None, 0.0))
+        p.has_judge_min = 0 if self.judge_overall_min is None else 1
+        p.judge_min = 0.0 if self.judge_overall_min is None else float(self.judge_overall_min)
+        p.has_conf_min = 0 if self.confidence_min is None else 1
+        p.conf_min = 0.0 if self.confidence_min is None else float(self.confidence_min)
+        mask = 0
+        if self.type_filter:  # `if type_filter and node_type not in type_filter` -- empty list == no filter
+            for t in self.type_filter:
+                mask |= _NT_BITS.get(t, 0)
+            mask |= 1 << 30  # keep the mask non-zero even when no known type is listed (everything filtered)
+        p.type_mask = mask
+        p.member_top_m = max(0, int(self.member_top_m))
+        p.parent_cap = int(self.parent_cap)
+        return p
+
+
+class GraphCSR:
+    """Device-resident typed CSR + node attributes built from ``csr.csr_from_networkx`` / ``csr_from_edges``."""
+
+    def __init__(self, arrays: Dict[str, Any], device: torch.device | str = "cuda") -> None:
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GraphCSR needs a CUDA device: the engine has no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n_nodes = int(arrays["n_nodes"])
+        dev = self.device
+        self.row_ptr = [torch.as_tensor(np.ascontiguousarray(a, dtype=np.int64)).to(dev) for a in arrays["row_ptr"]]
+        self.col_idx = [torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev) for a in arrays["col_idx"]]
+        self.node_type = torch.as_tensor(np.ascontiguousarray(arrays["node_type"], dtype=np.uint8)).to(dev)
+        self.level = torch.as_tensor(np.ascontiguousarray(arrays["level"], dtype=np.uint8)).to(dev)
+        self.judge = torch.as_tensor(np.ascontiguousarray(arrays["judge"], dtype=np.float64)).to(dev)
+        self.judge_term = torch.as_tensor(np.ascontiguousarray(arrays["judge_term"], dtype=np.float64)).to(dev)
+        self.conf = torch.as_tensor(np.ascontiguousarray(arrays["conf"], dtype=np.float64)).to(dev)
+        rp = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in self.row_ptr])
+        ci = (ctypes.c_void_p * 6)(*[t.data_ptr() if t.numel() else None for t in self.col_idx])
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            check(self.lib.ahr_graph_create(ctypes.byref(self._h), dev.index, self.n_nodes, rp, ci,
+                                            self.node_type.data_ptr(), self.level.data_ptr(), self.judge.data_ptr(),
+                                            self.judge_term.data_ptr(), self.conf.data_ptr()), "ahr_graph_create")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.ahr_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def nbytes(self) -> int:
+        ts = self.row_ptr + self.col_idx + [self.node_type, self.level, self.judge, self.judge_term, self.conf]
+        return sum(t.numel() * t.element_size() for t in ts)
+
+    def anchor_rerank(self, seed_nodes: torch.Tensor, seed_scores: torch.Tensor, params: SearchParams, top_k: int,
+                      want_cluster: bool = True) -> Dict[str, torch.Tensor]:
+        """Batched hierarchical_graph.py:719-789.  seed_nodes int32 [nq, n_seeds] (-1 = none), seed_scores fp32."""
+        _require_cuda(seed_nodes, "seed_nodes")
+        _require_cuda(seed_scores, "seed_scores")
+        if seed_nodes.dtype != torch.int32 or seed_scores.dtype != torch.float32 or seed_nodes.shape != seed_scores.shape:
+            raise ValueError("seed_nodes must be int32 and seed_scores float32 of the same [nq, n_seeds] shape")
+        nq, ns = int(seed_nodes.shape[0]), int(seed_nodes.shape[1])
+        dev = self.device
+        cp = params.to_c()
+        cap = ns * (1 + max(cp.parent_cap, cp.member_top_m))
+        out = {
+            "nodes": torch.empty((nq, top_k), dtype=torch.int32, device=dev),
+            "semantic": torch.empty((nq, top_k), dtype=torch.float64, device=dev),
+            "score": torch.empty((nq, top_k), dtype=torch.float64, device=dev),
+            "count": torch.empty((nq,), dtype=torch.int32, device=dev),
+        }
+        null = None
+        if want_cluster:
+            out["exp_nodes"] = torch.empty((nq, cap), dtype=torch.int32, device=dev)
+            out["exp_semantic"] = torch.empty((nq, cap), dtype=torch.float64, device=dev)
+            out["exp_kind"] = torch.empty((nq, cap), dtype=torch.uint8, device=dev)
+            out["exp_count"] = torch.empty((nq,), dtype=torch.int32, device=dev)
+            out["seed_semantic"] = torch.empty((nq, ns), dtype=torch.float64, device=dev)
+        if nq == 0:
+            return out
+        with torch.cuda.device(dev):
+            check(self.lib.ahr_anchor_rerank(
+                self._h, nq, ns, seed_nodes.data_ptr(), seed_scores.data_ptr(), ctypes.byref(cp), int(top_k),
+                out["nodes"].data_ptr(), out["semantic"].data_ptr(), out["score"].data_ptr(), out["count"].data_ptr(),
+                out["exp_nodes"].data_ptr() if want_cluster else null,
+                out["exp_semantic"].data_ptr() if want_cluster else null,
+                out["exp_kind"].data_ptr() if want_cluster else null,
+                out["exp_count"].data_ptr() if want_cluster else null,
+                out["seed_semantic"].data_ptr() if want_cluster else null,
+                _stream_ptr(dev)), "ahr_anchor_rerank")
+        return out
+
+    def expand(self, ops: torch.Tensor, in_ids: torch.Tensor, in_offsets: torch.Tensor, limit: int = 10
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Batched environment.py:393-480.  ops int32 [n_env]; in_ids int32 (CSR by in_offsets int32 [n_env+1])."""
+        for t, name in ((ops, "ops"), (in_ids, "in_ids"), (in_offsets, "in_offsets")):
+            _require_cuda(t, name)
+            if t.dtype != torch.int32:
+                raise ValueError(f"{name} must be int32")
+        n_env = int(ops.shape[0])
+        out_ids = torch.empty((n_env, limit), dtype=torch.int32, device=self.device)
+        out_cnt = torch.empty((n_env,), dtype=torch.int32, device=self.device)
+        if n_env == 0:
+            return out_ids, out_cnt
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_expand(self._h, n_env, ops.data_ptr(), in_ids.data_ptr() if in_ids.numel() else None,
+                                      in_offsets.data_ptr(), int(limit), out_ids.data_ptr(), out_cnt.data_ptr(),
+                                      _stream_ptr(self.device)), "ahr_expand")
+        return out_ids, out_cnt

@@ -1,0 +1,467 @@
+"""Drop-in for ``ah_rag.graph.hierarchical_graph.HierarchicalGraph`` on the retrieval hot path.
+
+Same public surface the reference's callers use (hierarchical_graph.py: ``load`` :191, ``save`` :175,
+``build_vector_index`` :602, ``search`` :675, ``.G``, ``name_to_entity_id``, ``topic_to_summary_id``, the id
+helpers :56-69 and the edge-type aware neighbour helpers :441-470), with the two things underneath
+replaced by the B200 engine:
+
+  * the Chroma / HNSW collection  -> ``engine.VectorIndex`` (device-resident rows, batched fused top-k)
+  * the NetworkX adjacency walks + Python rerank loop -> ``engine.GraphCSR.anchor_rerank`` (one kernel)
+
+``search`` keeps its signature and result schema; ``search_batch`` is the additive batched entry point the
+single-query call delegates to.  The graph itself stays a ``networkx.DiGraph`` on the host (it is the
+on-disk / in-memory contract other reference modules read directly); the CSR is exported from it in the
+LOADED adjacency order.  Ingest (``build_from_artifacts``: LLM extraction + BERTopic) and embedding-model
+inference are out of scope: embeddings come from a pluggable ``embedder`` callable.
+
+There is no CPU fallback: ``search`` raises if CUDA or the compiled library is unavailable.
+"""
+from __future__ import annotations
+
+import datetime
+import hashlib
+import json
+import os
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import networkx as nx
+import numpy as np
+
+GRAPH_DIR = "graph"
+
+_DEFAULT_SEARCH_PARAMS = {
+    "alpha": 0.6, "beta": 0.2, "gamma": 0.1, "delta": 0.1,
+    "judge_overall_min": None, "confidence_min": None, "member_top_m": 5, "type_filter": None,
+    "layer_boost": {"entity": 0.0, "summary": 1.0, "hyperedge": 0.0},
+}
+
+Embedder = Callable[[List[str]], np.ndarray]
+
+
+class HierarchicalGraph:
+    def __init__(self) -> None:
+        self.G: nx.DiGraph = nx.DiGraph()
+        self.name_to_entity_id: Dict[str, str] = {}
+        self.topic_to_summary_id: Dict[int, str] = {}
+        self.G.graph.setdefault("search_params", json.loads(json.dumps(_DEFAULT_SEARCH_PARAMS)))
+        self.G.graph.setdefault("dirty", False)
+        self.G.graph.setdefault("vector_index", {"db_path": "vector_db", "model": "all-MiniLM-L6-v2",
+                                                 "indexed_nodes": 0, "indexed_meta": {}})
+        # engine-side state
+        self.embedder: Optional[Embedder] = None  # texts -> [n, d] float32, L2-normalised
+        self.index_dtype: str = "fp32"            # "fp32": exact mode (faithful) | "bf16": tensor-core mode
+        self.device: str = "cuda"
+        self._dev_graph: Optional[Dict[str, Any]] = None
+        self._dev_index: Optional[Dict[str, Any]] = None
+        self._st_model = None
+        self._st_name: Optional[str] = None
+
+    # ------------------------------------------------------------------ ids (hierarchical_graph.py:56-69)
+    @staticmethod
+    def _hash(text: str, length: int = 10) -> str:
+        return hashlib.sha1(text.encode("utf-8")).hexdigest()[:length]
+
+    @staticmethod
+    def make_entity_id(name: str) -> str:
+        return "ent:" + HierarchicalGraph._hash(name)
+
+    @staticmethod
+    def make_hyperedge_id(uid: str) -> str:
+        return f"hedge:{uid}"
+
+    @staticmethod
+    def make_summary_id(topic_id: int) -> str:
+        return f"sum:{int(topic_id)}"
+
+    # ------------------------------------------------------------------ construction (:74-168, host only)
+    def _touch(self) -> None:
+        self.G.graph["dirty"] = True
+        self._dev_graph = None
+
+    def add_entity(self, name: str, description: Optional[str] = None, entity_type: Optional[str] = None,
+                   embedding_ref: Optional[Tuple[str, int]] = None,
+                   l1_parents: Optional[Dict[str, float]] = None) -> str:
+        nid = self.name_to_entity_id.get(name)
+        if nid is None:
+            nid = self.make_entity_id(name)
+            self.G.add_node(nid, node_type="entity", name=name, description=description, entity_type=entity_type,
+                            embedding_ref=embedding_ref, l1_parents=json.dumps(l1_parents) if l1_parents else None)
+            self.name_to_entity_id[name] = nid
+        else:
+            d = self.G.nodes[nid]
+            if description is not None and not d.get("description"):
+                d["description"] = description
+            if entity_type is not None and not d.get("entity_type"):
+                d["entity_type"] = entity_type
+            if embedding_ref is not None:
+                d["embedding_ref"] = embedding_ref
+            if l1_parents is not None:
+                d["l1_parents"] = json.dumps(l1_parents)
+        self._touch()
+        return nid
+
+    def add_hyperedge(self, uid: str, description: str, relation_type: str,
+                      confidence_score: Optional[float] = None, source_text_ref: Optional[str] = None) -> str:
+        nid = self.make_hyperedge_id(uid)
+        if not self.G.has_node(nid):
+            self.G.add_node(nid, node_type="hyperedge", description=description, relation_type=relation_type,
+                            confidence_score=confidence_score, source_text_ref=source_text_ref)
+        self._touch()
+        return nid
+
+    def add_summary(self, topic_id: int, title: Optional[str] = None, summary_text: Optional[str] = None,
+                    confidence: Optional[float] = None, top_words: Optional[List[str]] = None,
+                    members: Optional[List[str]] = None, judge_scores: Optional[Dict[str, Any]] = None,
+                    centroid: Optional[List[float]] = None) -> str:
+        fields = {"title": title, "summary_text": summary_text, "confidence": confidence,
+                  "top_words": json.dumps(top_words) if top_words else None,
+                  "members": json.dumps(members) if members else None,
+                  "judge_scores": json.dumps(judge_scores) if judge_scores else None,
+                  "centroid": json.dumps(centroid) if centroid is not None else None}
+        nid = self.topic_to_summary_id.get(int(topic_id))
+        if nid is None:
+            nid = self.make_summary_id(topic_id)
+            self.G.add_node(nid, node_type="summary", topic_id=int(topic_id), **fields)
+            self.topic_to_summary_id[int(topic_id)] = nid
+        else:
+            d = self.G.nodes[nid]
+            given = {"title": title, "summary_text": summary_text, "confidence": confidence, "top_words": top_words,
+                     "members": members, "judge_scores": judge_scores, "centroid": centroid}
+            for key, val in given.items():
+                if val is not None:
+                    d[key] = fields[key] if key in ("top_words", "members", "judge_scores", "centroid") else val
+        self._touch()
+        return nid
+
+    def add_participation(self, entity_id: str, hyperedge_id: str, role: Optional[str] = None) -> None:
+        self.G.add_edge(entity_id, hyperedge_id, edge_type="participates_in", role=role)
+        self._touch()
+
+    def add_belongs_to(self, entity_id: str, summary_id: str, prob: Optional[float] = None) -> None:
+        self.G.add_edge(entity_id, summary_id, edge_type="belongs_to", prob=prob)
+        self._touch()
+
+    def add_related(self, summary_a: str, summary_b: str, weight: Optional[float] = None,
+                    jaccard: Optional[float] = None, cosine: Optional[float] = None, overlap: Optional[int] = None,
+                    confidence: Optional[float] = None) -> None:
+        self.G.add_edge(summary_a, summary_b, edge_type="related_to", weight=weight, jaccard=jaccard, cosine=cosine,
+                        overlap=overlap, confidence=confidence)
+        self._touch()
+
+    def build_from_artifacts(self, *a: Any, **k: Any) -> None:
+        raise NotImplementedError("offline ingest (LLM extraction + BERTopic, hierarchical_graph.py:241-421) is out of "
+                                  "scope of the B200 engine; build the graph with the reference and load() it here")
+
+    # ------------------------------------------------------------------ persistence (:175-236)
+    def save(self, directory: str = GRAPH_DIR, meta: Optional[Dict[str, Any]] = None) -> None:
+        """Node-link JSON with the ``"links"`` key ``load`` reads (the reference's own save() writes ``"edges"``
+        under networkx >= 3.6 and can no longer be loaded -- SURVEY.md section 0-7)."""
+        os.makedirs(directory, exist_ok=True)
+        data = nx.node_link_data(self.G, edges="links")
+        with open(os.path.join(directory, "structure.json"), "w", encoding="utf-8") as f:
+            json.dump(data, f, ensure_ascii=False, indent=2)
+        merged = dict(meta) if meta else {}
+        merged["search_params"] = self.G.graph.get("search_params", {})
+        merged["graph_hash"] = self._graph_snapshot_hash()
+        merged["dirty"] = self.G.graph.get("dirty", False)
+        merged["vector_index"] = self.G.graph.get("vector_index", {})
+        with open(os.path.join(directory, "meta.json"), "w", encoding="utf-8") as f:
+            json.dump(merged, f, ensure_ascii=False, indent=2)
+
+    @classmethod
+    def load(cls, directory: str = GRAPH_DIR) -> "HierarchicalGraph":
+        with open(os.path.join(directory, "structure.json"), "r", encoding="utf-8") as f:
+            data = json.load(f)
+        hg = cls()
+        key = "links" if "links" in data else "edges"
+        hg.G = nx.node_link_graph(data, directed=True, edges=key)
+        for nid, attr in hg.G.nodes(data=True):
+            if attr.get("node_type") == "entity" and attr.get("name"):
+                hg.name_to_entity_id[attr["name"]] = nid
+            if attr.get("node_type") == "summary" and attr.get("topic_id") is not None:
+                hg.topic_to_summary_id[int(attr["topic_id"])] = nid
+        meta_path = os.path.join(directory, "meta.json")
+        if os.path.exists(meta_path):
+            try:
+                with open(meta_path, "r", encoding="utf-8") as f:
+                    meta = json.load(f)
+                if isinstance(meta.get("search_params"), dict):
+                    hg.G.graph["search_params"] = {**hg.G.graph.get("search_params", {}), **meta["search_params"]}
+                if isinstance(meta.get("vector_index"), dict):
+                    hg.G.graph["vector_index"] = meta["vector_index"]
+                if isinstance(meta.get("dirty"), bool):
+                    hg.G.graph["dirty"] = meta["dirty"]
+            except Exception:
+                pass
+        return hg
+
+    def _graph_snapshot_hash(self) -> str:
+        items = [(nid, d.get("node_type"), d.get("name"), d.get("title"), d.get("summary_text"), d.get("description"))
+                 for nid, d in self.G.nodes(data=True)]
+        items.sort(key=lambda x: x[0])
+        return hashlib.sha1(json.dumps(items, ensure_ascii=False).encode("utf-8")).hexdigest()
+
+    # ------------------------------------------------------------------ host neighbour helpers (:426-470)
+    def get_parents(self, node_id: str) -> List[str]:
+        return list(self.G.successors(node_id))
+
+    def get_children(self, node_id: str) -> List[str]:
+        return list(self.G.predecessors(node_id))
+
+    def find_entity(self, name: str) -> Optional[str]:
+        return self.name_to_entity_id.get(name)
+
+    def find_summary(self, topic_id: int) -> Optional[str]:
+        return self.topic_to_summary_id.get(int(topic_id))
+
+    def _neighbors_by_edge_type(self, node_id: str, direction: str, edge_type: str) -> List[str]:
+        if direction == "out":
+            return [v for _, v, d in self.G.out_edges(node_id, data=True) if d.get("edge_type") == edge_type]
+        return [u for u, _, d in self.G.in_edges(node_id, data=True) if d.get("edge_type") == edge_type]
+
+    def get_belongs_to(self, node_id: str) -> List[str]:
+        return self._neighbors_by_edge_type(node_id, "out", "belongs_to")
+
+    def get_summary_members(self, summary_id: str) -> List[str]:
+        return self._neighbors_by_edge_type(summary_id, "in", "belongs_to")
+
+    def get_hyperedge_participants(self, hyperedge_id: str) -> List[str]:
+        return self._neighbors_by_edge_type(hyperedge_id, "in", "participates_in")
+
+    def get_entity_hyperedges(self, entity_id: str) -> List[str]:
+        return self._neighbors_by_edge_type(entity_id, "out", "participates_in")
+
+    # ------------------------------------------------------------------ embeddings (out of scope: pluggable)
+    def set_embedder(self, fn: Optional[Embedder]) -> None:
+        self.embedder = fn
+
+    def _embed(self, texts: List[str], model_name: str) -> np.ndarray:
+        if self.embedder is not None:
+            out = np.asarray(self.embedder(list(texts)), dtype=np.float32)
+        else:
+            try:
+                from sentence_transformers import SentenceTransformer  # the reference's embedder (:8, :655, :709)
+            except Exception as e:
+                raise RuntimeError("embedding-model inference is out of scope of the B200 engine and "
+                                   "sentence_transformers is not installed: set HierarchicalGraph.embedder to a "
+                                   "callable texts -> [n, d] float32 (L2-normalised)") from e
+            if self._st_model is None or self._st_name != model_name:
+                self._st_model, self._st_name = SentenceTransformer(model_name), model_name
+            out = np.asarray(self._st_model.encode(list(texts), normalize_embeddings=True), dtype=np.float32)
+        return out.reshape(len(texts), -1)
+
+    def _embedding_text(self, node_id: str) -> Tuple[str, Dict[str, Any]]:
+        """Text + metadata a node is indexed under (hierarchical_graph.py:558-600)."""
+        from ..csr import judge_overall
+        d = self.G.nodes[node_id]
+        nt = d.get("node_type")
+        if nt == "entity":
+            text = f"Entity: {d.get('name') or ''}. {d.get('description') or ''}"
+        elif nt == "summary":
+            words: List[str] = []
+            if d.get("top_words"):
+                try:
+                    words = json.loads(d["top_words"]) if isinstance(d["top_words"], str) else d["top_words"]
+                except Exception:
+                    words = []
+            kw = ", ".join(words[:10]) if words else ""
+            text = f"Summary: {d.get('title') or ''}. {d.get('summary_text') or d.get('summary') or ''}. Keywords: {kw}"
+        else:
+            text = f"Relation: {d.get('relation_type') or ''}. {d.get('description') or ''}"
+        meta = {"node_id": node_id, "node_type": nt, "layer": 1 if nt == "summary" else 0,
+                "judge_overall": judge_overall(d), "confidence": d.get("confidence"),
+                "updated_at": datetime.datetime.now(datetime.timezone.utc).replace(tzinfo=None).isoformat() + "Z"}
+        return text, meta
+
+    # ------------------------------------------------------------------ vector index (:602-673)
+    @staticmethod
+    def _index_key(d: Dict[str, Any]) -> str:
+        blob = "|".join([str(d.get("node_type")), str(d.get("name") or d.get("title") or ""),
+                         str(d.get("summary_text") or ""), str(d.get("description") or "")])
+        return hashlib.sha1(blob.encode("utf-8")).hexdigest()
+
+    def build_vector_index(self, db_path: str = "vector_db", layers: set = {0, 1}, include_hyperedges: bool = False,
+                           model_name: str = "all-MiniLM-L6-v2", upsert_only: bool = True, reset: bool = False,
+                           embeddings: Optional[Dict[str, np.ndarray]] = None) -> None:
+        """Same selection / incremental-upsert rules as the reference; the store is ``<db_path>/nodes.npz``
+        (ids + fp32 rows + metadata) instead of a Chroma directory.  ``embeddings`` may supply precomputed
+        rows by node id (synthetic inputs), bypassing the embedder."""
+        from . import vector_store
+        os.makedirs(db_path, exist_ok=True)
+        store = vector_store.VectorStore.open(db_path, reset=reset)
+        vi = self.G.graph.get("vector_index", {})
+        prev = vi.get("indexed_meta") if isinstance(vi.get("indexed_meta"), dict) else {}
+        ids, docs, metas = [], [], []
+        for nid, d in self.G.nodes(data=True):
+            nt = d.get("node_type")
+            wanted = (nt == "entity" and 0 in layers) or (nt == "summary" and 1 in layers) or \
+                     (nt == "hyperedge" and include_hyperedges)
+            if not wanted:
+                continue
+            if upsert_only and prev.get(nid) == self._index_key(d):
+                continue
+            text, meta = self._embedding_text(nid)
+            ids.append(nid); docs.append(text); metas.append(meta)
+        if not ids:
+            return
+        if embeddings is not None:
+            rows = np.stack([np.asarray(embeddings[n], dtype=np.float32) for n in ids])
+        else:
+            rows = self._embed(docs, model_name)
+        store.upsert(ids, docs, rows, metas)
+        store.save()
+        new_meta = dict(prev)
+        for nid in ids:
+            new_meta[nid] = self._index_key(self.G.nodes[nid])
+        self.G.graph["vector_index"] = {"db_path": db_path, "model": model_name, "indexed_nodes": len(new_meta),
+                                        "indexed_meta": new_meta}
+        self.G.graph["dirty"] = False
+        self._dev_index = None
+
+    # ------------------------------------------------------------------ device residency
+    def _device_graph(self) -> Dict[str, Any]:
+        sig = (id(self.G), self.G.number_of_nodes(), self.G.number_of_edges())
+        if self._dev_graph is None or self._dev_graph["sig"] != sig:
+            from .. import csr as csr_mod
+            from .. import engine
+            arrays = csr_mod.csr_from_networkx(self.G)
+            self._dev_graph = {"sig": sig, "arrays": arrays, "csr": engine.GraphCSR(arrays, self.device)}
+            self._dev_index = None  # row -> node map depends on dense ids
+        return self._dev_graph
+
+    def _device_index(self, db_path: str) -> Dict[str, Any]:
+        import torch
+        from . import vector_store
+        from .. import engine
+        dg = self._device_graph()
+        stamp = vector_store.VectorStore.stamp(db_path)
+        cur = self._dev_index
+        if cur is None or cur["db_path"] != db_path or cur["stamp"] != stamp or cur["dtype"] != self.index_dtype:
+            store = vector_store.VectorStore.open(db_path)
+            rows = torch.from_numpy(np.ascontiguousarray(store.rows, dtype=np.float32))
+            dev = dg["csr"].device
+            if self.index_dtype == "bf16":
+                rows_dev = rows.to(dev).to(torch.bfloat16).contiguous()
+            else:
+                rows_dev = rows.to(dev).contiguous()
+            dense = dg["arrays"]["dense"]
+            row_to_node = torch.tensor([dense.get(n, -1) for n in store.ids], dtype=torch.int32, device=dev)
+            index = engine.VectorIndex(rows_dev) if len(store.ids) else None
+            cur = {"db_path": db_path, "stamp": stamp, "dtype": self.index_dtype, "store": store, "index": index,
+                   "row_to_node": row_to_node}
+            self._dev_index = cur
+        return cur
+
+    def invalidate_device_cache(self) -> None:
+        self._dev_graph = None
+        self._dev_index = None
+
+    # ------------------------------------------------------------------ search (:675-789)
+    def _resolve(self, member_top_m, alpha, beta, gamma, delta, judge_overall_min, confidence_min, type_filter):
+        from ..engine import SearchParams
+        sp = self.G.graph.get("search_params", {})
+        if type_filter is None:
+            tf = sp.get("type_filter")
+            type_filter = list(tf) if isinstance(tf, (set, tuple)) else tf
+        return SearchParams(
+            alpha=alpha if alpha is not None else sp.get("alpha", 0.6),
+            beta=beta if beta is not None else sp.get("beta", 0.2),
+            gamma=gamma if gamma is not None else sp.get("gamma", 0.1),
+            delta=delta if delta is not None else sp.get("delta", 0.1),
+            judge_overall_min=judge_overall_min if judge_overall_min is not None else sp.get("judge_overall_min"),
+            confidence_min=confidence_min if confidence_min is not None else sp.get("confidence_min"),
+            type_filter=type_filter,
+            member_top_m=member_top_m if member_top_m is not None else sp.get("member_top_m", 5),
+            layer_boost=sp.get("layer_boost", {"entity": 0.0, "summary": 1.0, "hyperedge": 0.0}))
+
+    def search(self, query: str, top_k: int = 5, member_top_m: int = 5,
+               alpha: Optional[float] = None, beta: Optional[float] = None, gamma: Optional[float] = None,
+               delta: Optional[float] = None, judge_overall_min: Optional[float] = None,
+               confidence_min: Optional[float] = None, type_filter: Optional[List[str]] = None,
+               return_cluster: bool = False, db_path: Optional[str] = None,
+               model_name: Optional[str] = None) -> Union[List[Dict[str, Any]], Dict[str, Any]]:
+        """Single-query API of the reference; one-row batch through :meth:`search_batch`."""
+        db_path, model_name = self._resolve_index(db_path, model_name)
+        q = self._embed([query], model_name)
+        return self.search_batch(q, top_k=top_k, member_top_m=member_top_m, alpha=alpha, beta=beta, gamma=gamma,
+                                 delta=delta, judge_overall_min=judge_overall_min, confidence_min=confidence_min,
+                                 type_filter=type_filter, return_cluster=return_cluster, db_path=db_path)[0]
+
+    def _resolve_index(self, db_path: Optional[str], model_name: Optional[str]) -> Tuple[str, str]:
+        if not db_path or not model_name:
+            vi = self.G.graph.get("vector_index", {}) if isinstance(self.G.graph.get("vector_index"), dict) else {}
+            db_path = db_path or vi.get("db_path", "vector_db")
+            model_name = model_name or vi.get("model", "all-MiniLM-L6-v2")
+        return db_path, model_name
+
+    def search_batch(self, query_embeddings, top_k: int = 5, member_top_m: int = 5,
+                     alpha: Optional[float] = None, beta: Optional[float] = None, gamma: Optional[float] = None,
+                     delta: Optional[float] = None, judge_overall_min: Optional[float] = None,
+                     confidence_min: Optional[float] = None, type_filter: Optional[List[str]] = None,
+                     return_cluster: bool = False, db_path: Optional[str] = None) -> List[Any]:
+        """Batched search: ``query_embeddings`` [B, d] (numpy or torch, host or device).  Per item the result
+        equals ``search`` on that query.  One fused top-k launch + one expansion/rerank launch for the batch."""
+        import torch
+        params = self._resolve(member_top_m, alpha, beta, gamma, delta, judge_overall_min, confidence_min, type_filter)
+        db_path, _ = self._resolve_index(db_path, "unused")
+        dg = self._device_graph()
+        di = self._device_index(db_path)
+        csr, arrays, store = dg["csr"], dg["arrays"], di["store"]
+        dev = csr.device
+        q = query_embeddings if isinstance(query_embeddings, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(query_embeddings, dtype=np.float32))
+        B = int(q.shape[0])
+        n_index = len(store.ids)
+        if B == 0:
+            return []
+        if n_index == 0 or top_k <= 0:
+            empty = {"seeds": [], "expanded": [], "reranked": []}
+            return [dict(empty) if return_cluster else [] for _ in range(B)]
+        k_eff = min(int(top_k), n_index)  # Chroma returns at most the collection size
+        if self.index_dtype == "bf16":
+            qd = q.to(dev).to(torch.bfloat16).contiguous()
+            scores, rows = di["index"].topk(qd, k_eff, mode="bf16")
+        else:
+            qd = q.to(dev).to(torch.float32).contiguous()
+            scores, rows = di["index"].topk(qd, k_eff, mode="exact")
+        seed_nodes = torch.where(rows >= 0, di["row_to_node"][rows.clamp(min=0)], torch.full_like(rows, -1, dtype=torch.int32))
+        out = csr.anchor_rerank(seed_nodes.to(torch.int32).contiguous(), scores, params, int(top_k),
+                                want_cluster=return_cluster)
+        host = {k: v.cpu().numpy() for k, v in out.items()}
+        rows_h = rows.cpu().numpy() if return_cluster else None
+        node_ids, G = arrays["node_ids"], self.G
+        from ..csr import judge_overall
+        results: List[Any] = []
+        for b in range(B):
+            reranked = []
+            for j in range(int(host["count"][b])):
+                nid = node_ids[int(host["nodes"][b, j])]
+                d = G.nodes.get(nid, {})
+                nt = d.get("node_type")
+                reranked.append({"node_id": nid, "node_type": nt, "layer": 1 if nt == "summary" else 0,
+                                 "semantic": float(host["semantic"][b, j]), "judge_overall": judge_overall(d),
+                                 "confidence": d.get("confidence"), "score": float(host["score"][b, j]),
+                                 "name": d.get("name"), "title": d.get("title")})
+            if not return_cluster:
+                results.append(reranked)
+                continue
+            seeds, seed_meta = [], {}
+            for r in range(k_eff):
+                row = int(rows_h[b, r])
+                if row < 0:
+                    continue
+                nid = store.ids[row]
+                seeds.append({"node_id": nid, "semantic": float(host["seed_semantic"][b, r]), "meta": store.metas[row]})
+                seed_meta[nid] = store.metas[row]
+            expanded = []
+            for j in range(int(host["exp_count"][b])):
+                nid = node_ids[int(host["exp_nodes"][b, j])]
+                kind = int(host["exp_kind"][b, j])
+                if kind == 1:
+                    expanded.append({"node_id": nid, "semantic": float(host["exp_semantic"][b, j]),
+                                     "meta": seed_meta.get(nid), "node_type": G.nodes.get(nid, {}).get("node_type")})
+                else:
+                    expanded.append({"node_id": nid, "semantic": float(host["exp_semantic"][b, j]),
+                                     "meta": {"expanded": True}, "node_type": "summary" if kind == 2 else "entity"})
+            results.append({"seeds": seeds, "expanded": expanded, "reranked": reranked})
+        return results

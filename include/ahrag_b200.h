@@ -1,0 +1,193 @@
+/*
+ * ahrag_b200.h -- C ABI of the B200-native retrieval engine for AH-RAG's hot path.
+ *
+ * The reference (Yaron9/AH-RAG) is pure Python and exposes no FFI; the seams this library replaces are
+ * Python call sites.  Each entry point below names the reference interface it stands in for
+ * (paths relative to the reference tree).  See INTEGRATION.md for the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; every function returns 0 on success and a negative
+ *     AHR_E_* code otherwise; the message is available from ahr_last_error() (thread-local).
+ *   - "dev_" pointers are CUDA device pointers on the handle's device, owned by the caller; the library
+ *     never frees them.  Inputs of *_create must stay alive until *_destroy.
+ *   - work is enqueued on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = default
+ *     stream) and is asynchronous unless the function name ends in _host or the doc says otherwise.
+ *   - a handle is not thread-safe; distinct handles are independent.  One process per GPU.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with AHR_E_CUDA.
+ */
+#ifndef AHRAG_B200_H_
+#define AHRAG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AHR_VERSION 100
+
+/* error codes */
+#define AHR_OK 0
+#define AHR_E_INVALID (-1)  /* bad argument */
+#define AHR_E_CUDA (-2)     /* CUDA runtime / driver failure (message has the CUDA error string) */
+#define AHR_E_UNSUPPORTED (-3)
+#define AHR_E_NOMEM (-4)
+
+/* row dtypes of an embedding index */
+#define AHR_DTYPE_F32 0
+#define AHR_DTYPE_BF16 1
+
+/* top-k modes */
+#define AHR_MODE_BF16 0   /* tcgen05 bf16 GEMM, fp32 accumulate, fused top-k epilogue (needs a bf16 index) */
+#define AHR_MODE_EXACT 1  /* canonical fp32 score (fp64 ordered accumulation), ties -> lower id */
+
+/* edge CSR slots: 3 edge types x 2 directions, adjacency in the LOADED NetworkX iteration order */
+#define AHR_CSR_PART_OUT 0 /* participates_in, G.out_edges order  (entity -> hyperedge) */
+#define AHR_CSR_PART_IN 1  /* participates_in, G.in_edges order */
+#define AHR_CSR_BEL_OUT 2  /* belongs_to out  (child -> parent) */
+#define AHR_CSR_BEL_IN 3   /* belongs_to in   (parent <- members) */
+#define AHR_CSR_REL_OUT 4  /* related_to out */
+#define AHR_CSR_REL_IN 5   /* related_to in */
+#define AHR_N_CSR 6
+
+/* node types (uint8 attribute array) */
+#define AHR_NT_ENTITY 0
+#define AHR_NT_SUMMARY 1
+#define AHR_NT_HYPEREDGE 2
+#define AHR_NT_OTHER 3 /* node_type missing / unknown (d.get("node_type") is None) */
+
+/* how an entry of the expanded map was inserted (ahr_anchor_rerank, exp_kind) */
+#define AHR_EK_SEED 1
+#define AHR_EK_PARENT 2
+#define AHR_EK_MEMBER 3
+
+/* expand ops */
+#define AHR_OP_PARENTS 0  /* GraphEnvironment.expand_parents   src/ah_rag/agent/environment.py:417-438 */
+#define AHR_OP_CHILDREN 1 /* GraphEnvironment.expand_children  src/ah_rag/agent/environment.py:393-415 */
+#define AHR_OP_RELATED 2  /* GraphEnvironment.expand_related   src/ah_rag/agent/environment.py:440-480 */
+
+typedef struct ahr_index ahr_index;
+typedef struct ahr_graph ahr_graph;
+
+const char *ahr_last_error(void);
+int ahr_version(void);
+/* number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t ahr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Embedding index.  Replaces the Chroma collection built at
+ *   src/ah_rag/graph/hierarchical_graph.py:605-611,660  (PersistentClient / get_or_create_collection
+ *   {"hnsw:space": "cosine"} / Collection.upsert)
+ * by a device-resident row-major [n_rows, dim] matrix the caller already holds.  Rows are expected
+ * L2-normalised by the producer, as the reference does (:655-656); ids are id_base + row.
+ * dim must be a multiple of 8 for bf16 indexes (16-byte TMA row pitch).
+ * ---------------------------------------------------------------------------------------------- */
+int ahr_index_create(ahr_index **out, int device, int64_t n_rows, int32_t dim, int dtype,
+                     const void *dev_rows, int64_t id_base);
+int ahr_index_destroy(ahr_index *idx);
+
+/*
+ * Batched nearest-neighbour query.  Replaces, for nq queries at once,
+ *   src/ah_rag/graph/hierarchical_graph.py:714   coll.query(query_embeddings=[q], n_results=k)
+ * dev_q: [nq, dim] in the index dtype.  Outputs [nq, k]: scores = <q, x> (the reference's
+ * `semantic` is 1 - fl32(1 - score), :723) and ids, sorted by (score desc, id asc); lists shorter than k
+ * (n_rows < k) are padded with (-inf, -1).
+ *   AHR_MODE_BF16 : k <= 128.  scores are the tensor-core fp32 accumulations.
+ *   AHR_MODE_EXACT: canonical scores, bit-reproducible; ids bit-identical to the CPU oracle.
+ *                   May synchronise the stream internally (certification of the candidate set).
+ */
+int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode, float *dev_scores,
+             int64_t *dev_ids, void *stream);
+
+/* Same query through HOST buffers: copies host_q to the device, runs ahr_topk, copies results back and
+ * synchronises the stream.  This is the call bench.py times for the end-to-end ("e2e") figure. */
+int ahr_topk_host(ahr_index *idx, const void *host_q, int32_t nq, int32_t k, int mode, float *host_scores,
+                  int64_t *host_ids, void *stream);
+
+/*
+ * k-way merge of `parts` candidate lists per query (multi-GPU: the lists all-gathered from the
+ * node-range shards).  dev_scores/dev_ids: [parts, nq, k]; entries with id < 0 are ignored.
+ * Output [nq, k] sorted by (score desc, id asc) -- identical for every sharding of the same corpus.
+ */
+int ahr_merge_topk(int device, const float *dev_scores, const int64_t *dev_ids, int32_t parts, int32_t nq,
+                   int32_t k, float *dev_out_scores, int64_t *dev_out_ids, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Knowledge-graph CSR.  Replaces the NetworkX adjacency reads of
+ *   src/ah_rag/graph/hierarchical_graph.py:441-462 (_neighbors_by_edge_type, get_belongs_to,
+ *   get_summary_members) and src/ah_rag/agent/environment.py:401-402,424-425,448-467.
+ * Dense node id = position in G.nodes order of the loaded graph.  For each of the AHR_N_CSR slots:
+ * row_ptr[n_nodes + 1] (int64) and col_idx (int32), neighbours in adjacency iteration order.
+ * Attributes (per node): node_type (AHR_NT_*), level (0 if absent), and fp64 arrays
+ *   judge       overall judge score, NaN when absent (judge is None)       hierarchical_graph.py:746-752
+ *   judge_term  1/(1+exp(-judge/10)) evaluated by the host exactly as :766 does, 0.0 when absent
+ *   conf        confidence, NaN when absent                                :753
+ * ---------------------------------------------------------------------------------------------- */
+int ahr_graph_create(ahr_graph **out, int device, int64_t n_nodes, const int64_t *const dev_row_ptr[AHR_N_CSR],
+                     const int32_t *const dev_col_idx[AHR_N_CSR], const uint8_t *dev_node_type,
+                     const uint8_t *dev_level, const double *dev_judge, const double *dev_judge_term,
+                     const double *dev_conf);
+int ahr_graph_destroy(ahr_graph *g);
+
+typedef struct ahr_rerank_params {
+  double alpha, beta, gamma, delta; /* hierarchical_graph.py:683-686 */
+  double boost[4];                  /* layer_boost per AHR_NT_* (index 3 = unknown type -> 0.0)  :699 */
+  double judge_min, conf_min;       /* thresholds, used when the has_* flag is set              :759-762 */
+  int32_t has_judge_min, has_conf_min;
+  int32_t type_mask;                /* bit t set = node type t passes; 0 = no type filter        :756-757 */
+  int32_t member_top_m;             /* summary -> first m members                                :737 */
+  int32_t parent_cap;               /* entity -> first 2 parents                                 :734 */
+  int32_t reserved;
+} ahr_rerank_params;
+
+/*
+ * Anchor expansion + rerank for nq queries.  Replaces, per query,
+ *   src/ah_rag/graph/hierarchical_graph.py:719-789  (seeds -> expanded -> reranked)
+ * Inputs: seed_nodes [nq, n_seeds] dense node ids in rank order (-1 = no seed), seed_scores [nq, n_seeds]
+ * fp32 similarity scores.  cap = n_seeds * (1 + max(parent_cap, member_top_m)) bounds the expanded map.
+ * Outputs (any of the exp_* / seed_sem pointers may be NULL):
+ *   out_nodes/out_semantic/out_score [nq, top_k], out_count [nq]: the reranked list; semantic and score
+ *     are already rounded to 4 decimals exactly as Python's round() does (:769-776), order = stable sort
+ *     on the rounded score descending (:781);
+ *   exp_nodes/exp_semantic/exp_kind [nq, cap], exp_count [nq]: the `expanded` map in insertion order with
+ *     the unrounded fp64 semantic (return_cluster=True, :783-788); kind = AHR_EK_SEED / AHR_EK_PARENT
+ *     (inserted by the entity rule, node_type reported as "summary", :736) / AHR_EK_MEMBER (summary rule,
+ *     reported as "entity", :740);
+ *   seed_semantic [nq, n_seeds]: 1.0 - (double)fl32(1 - score)  (:723).
+ */
+int ahr_anchor_rerank(ahr_graph *g, int32_t nq, int32_t n_seeds, const int32_t *dev_seed_nodes,
+                      const float *dev_seed_scores, const ahr_rerank_params *params, int32_t top_k,
+                      int32_t *dev_out_nodes, double *dev_out_semantic, double *dev_out_score,
+                      int32_t *dev_out_count, int32_t *dev_exp_nodes, double *dev_exp_semantic,
+                      uint8_t *dev_exp_kind, int32_t *dev_exp_count, double *dev_seed_semantic, void *stream);
+
+/*
+ * Batched frontier expansion.  Replaces, for n_env environments at once,
+ *   GraphEnvironment.expand_parents / expand_children / expand_related
+ *   (src/ah_rag/agent/environment.py:393-480): ordered concatenation of typed neighbour lists of the input
+ *   nodes, stop after the input node at which the un-deduplicated length reaches `limit`,
+ *   order-preserving dedup, cut to `limit`.
+ * dev_ops[n_env] (AHR_OP_*), inputs in CSR form: dev_in_ids[dev_in_offsets[e] .. dev_in_offsets[e+1])
+ * (-1 = id not in the graph, skipped like environment.py:398).  Outputs: dev_out_ids [n_env, limit]
+ * (padded with -1) and dev_out_counts [n_env].
+ */
+int ahr_expand(ahr_graph *g, int32_t n_env, const int32_t *dev_ops, const int32_t *dev_in_ids,
+               const int32_t *dev_in_offsets, int32_t limit, int32_t *dev_out_ids, int32_t *dev_out_counts,
+               void *stream);
+
+/* ---- diagnostics used by the parity tests (not part of the reference seam) ---------------------- */
+/* full [nq, n_rows] score matrix of the tensor-core path (small inputs only) */
+int ahr_debug_tc_scores(ahr_index *idx, const void *dev_q, int32_t nq, float *dev_out, void *stream);
+/* canonical scores of given candidate rows: cand [nq, m] row ids (-1 -> -inf) */
+int ahr_rescore(ahr_index *idx, const void *dev_q, int32_t nq, int32_t m, const int64_t *dev_cand_ids,
+                float *dev_out_scores, void *stream);
+/* Python round(x, 4) on the device, elementwise (the rerank kernel's rounding routine) */
+int ahr_debug_round4(int device, const double *dev_x, int64_t n, double *dev_out, void *stream);
+/* statistics of the last AHR_MODE_EXACT call on this index: queries certified by the tensor-core
+ * candidate path vs. re-run through the brute-force exact scan */
+int ahr_exact_stats(ahr_index *idx, int64_t *n_certified, int64_t *n_fallback);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AHRAG_B200_H_ */

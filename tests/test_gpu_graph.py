@@ -1,0 +1,136 @@
+"""GPU parity tests of hop expansion + rerank (K2) through the C ABI, against the oracle / reference goldens."""
+import copy
+
+import networkx as nx
+import numpy as np
+import pytest
+import torch
+
+from ah_rag_b200 import csr as csr_mod
+from ah_rag_b200 import synth
+from oracle import exact, ref_search
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from ah_rag_b200 import engine as e
+    return e
+
+
+def _setup(engine, node_link):
+    og = ref_search.OracleGraph(copy.deepcopy(node_link))
+    arrays = csr_mod.csr_from_networkx(og.G)
+    return og, arrays, engine.GraphCSR(arrays)
+
+
+def _params(engine, p):
+    return engine.SearchParams(alpha=p["alpha"], beta=p["beta"], gamma=p["gamma"], delta=p["delta"],
+                               judge_overall_min=p["judge_overall_min"], confidence_min=p["confidence_min"],
+                               type_filter=p["type_filter"], member_top_m=p["member_top_m"],
+                               layer_boost=p["layer_boost"])
+
+
+@pytest.mark.parametrize("name", gu.fixture_names())
+def test_anchor_rerank_matches_reference_golden(engine, name):
+    """Seeds taken from the golden file (outputs of the real reference); expansion/rerank on the GPU."""
+    fx = gu.load(name)
+    og, arrays, g = _setup(engine, fx["node_link"])
+    dense = arrays["dense"]
+    row_of = {nid: r for r, nid in enumerate(fx["index_ids"])}
+    S = exact.canonical_scores(fx["index_rows"], fx["query_vecs"])
+    for case in fx["search"]:
+        kw = dict(case["kwargs"])
+        top_k = kw.pop("top_k")
+        prm = ref_search.resolve_params(og, **{"member_top_m": 5, **kw})
+        seeds = case["out"]["seeds"]
+        ns = max(1, len(seeds))
+        sn = np.full((1, ns), -1, np.int32)
+        ss = np.zeros((1, ns), np.float32)
+        for r, s in enumerate(seeds):
+            sn[0, r] = dense[s["node_id"]]
+            ss[0, r] = S[case["query"], row_of[s["node_id"]]]
+        out = g.anchor_rerank(torch.from_numpy(sn).cuda(), torch.from_numpy(ss).cuda(), _params(engine, prm), top_k)
+        out = {k: v.cpu().numpy() for k, v in out.items()}
+        want = case["out"]
+        # seeds: semantic = 1 - fl32(1 - score)
+        assert [float(x) for x in out["seed_semantic"][0][:len(seeds)]] == [s["semantic"] for s in seeds]
+        # expanded map: order, unrounded semantic, node_type as the reference reports it
+        ne = int(out["exp_count"][0])
+        got_exp = []
+        for j in range(ne):
+            nid = arrays["node_ids"][out["exp_nodes"][0, j]]
+            kind = int(out["exp_kind"][0, j])
+            nt = og.G.nodes[nid].get("node_type") if kind == 1 else ("summary" if kind == 2 else "entity")
+            got_exp.append({"node_id": nid, "semantic": float(out["exp_semantic"][0, j]), "node_type": nt})
+        assert got_exp == want["expanded"], (name, case["query"], case["kwargs"])
+        nr = int(out["count"][0])
+        got = [(arrays["node_ids"][out["nodes"][0, j]], float(out["semantic"][0, j]), float(out["score"][0, j]))
+               for j in range(nr)]
+        ref = [(r["node_id"], r["semantic"], r["score"]) for r in want["reranked"]]
+        assert got == ref, (name, case["query"], case["kwargs"])
+
+
+@pytest.mark.parametrize("name", gu.fixture_names())
+def test_expand_ops_match_reference_golden(engine, name):
+    fx = gu.load(name)
+    og, arrays, g = _setup(engine, fx["node_link"])
+    dense = arrays["dense"]
+    opcode = {"expand_parents": 0, "expand_children": 1, "expand_related": 2}
+    calls = [st for tr in fx["env"] for st in tr if st["call"] in opcode]
+    for limit in (10, 3):
+        sel = [c for c in calls if c["args"]["limit"] == limit]
+        ops = torch.tensor([opcode[c["call"]] for c in sel], dtype=torch.int32).cuda()
+        ids, offs = [], [0]
+        for c in sel:
+            ids += [dense.get(n, -1) for n in c["args"]["node_ids"]]
+            offs.append(len(ids))
+        out_ids, out_cnt = g.expand(ops, torch.tensor(ids, dtype=torch.int32).cuda(),
+                                    torch.tensor(offs, dtype=torch.int32).cuda(), limit)
+        out_ids, out_cnt = out_ids.cpu().numpy(), out_cnt.cpu().numpy()
+        for e, c in enumerate(sel):
+            got = [arrays["node_ids"][i] for i in out_ids[e, :out_cnt[e]]]
+            want = [n["node_id"] for n in c["obs"]["selection"]]
+            assert got == want, (name, c["call"], c["args"])
+            assert (out_ids[e, out_cnt[e]:] == -1).all()
+
+
+@pytest.mark.parametrize("seed", [101, 102])
+def test_batched_random_graph_vs_oracle(engine, seed):
+    """Bigger random graphs, many queries / envs per launch, large fan-out and limits."""
+    rng = np.random.default_rng(seed)
+    nl = synth.make_graph(seed=seed, n_entities=600, n_l1=12, n_l2=3, n_hyperedges=300, related_density=0.4)
+    og, arrays, g = _setup(engine, nl)
+    nodes = arrays["node_ids"]
+    n = len(nodes)
+    # anchor + rerank: 64 queries x 50 random seeds with random scores
+    nq, ns, top_k, m = 64, 50, 50, 7
+    sn = np.stack([rng.permutation(n)[:ns] for _ in range(nq)]).astype(np.int32)
+    ss = np.sort(rng.uniform(0.05, 0.95, size=(nq, ns)).astype(np.float32), axis=1)[:, ::-1].copy()
+    prm = ref_search.resolve_params(og, member_top_m=m)
+    out = g.anchor_rerank(torch.from_numpy(sn).cuda(), torch.from_numpy(ss).cuda(), _params(engine, prm), top_k)
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    for q in range(nq):
+        seeds = ref_search.seeds_from_topk([nodes[i] for i in sn[q]], ss[q])
+        want = ref_search.anchor_rerank(og, seeds, top_k, prm)
+        got = [(nodes[out["nodes"][q, j]], float(out["semantic"][q, j]), float(out["score"][q, j]))
+               for j in range(out["count"][q])]
+        assert got == [(r["node_id"], r["semantic"], r["score"]) for r in want["reranked"]]
+        assert [nodes[i] for i in out["exp_nodes"][q, :out["exp_count"][q]]] == [e["node_id"] for e in want["expanded"]]
+    # expansions: 1024 envs, 1-3 inputs, mixed ops, limits 10 and 200
+    for limit in (10, 200):
+        n_env = 1024
+        ops = rng.integers(0, 3, size=n_env).astype(np.int32)
+        ids, offs = [], [0]
+        for e in range(n_env):
+            ids += list(rng.integers(0, n, size=int(rng.integers(0, 4))))
+            offs.append(len(ids))
+        out_ids, out_cnt = g.expand(torch.from_numpy(ops).cuda(), torch.tensor(ids, dtype=torch.int32).cuda(),
+                                    torch.tensor(offs, dtype=torch.int32).cuda(), limit)
+        out_ids, out_cnt = out_ids.cpu().numpy(), out_cnt.cpu().numpy()
+        names = ["parents", "children", "related"]
+        for e in range(n_env):
+            want = ref_search.expand(og, names[ops[e]], [nodes[i] for i in ids[offs[e]:offs[e + 1]]], limit)
+            assert [nodes[i] for i in out_ids[e, :out_cnt[e]]] == want

@@ -1,0 +1,149 @@
+"""GPU parity tests of the similarity + top-k path, through the C ABI (ctypes), against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from ah_rag_b200 import synth
+from oracle import exact
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(x):
+    return torch.from_numpy(x).cuda().to(torch.bfloat16).contiguous()
+
+
+def _bits(t):
+    return t.view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from ah_rag_b200 import engine as e
+    return e
+
+
+@pytest.mark.parametrize("n,dim,nq", [(1000, 64, 5), (4096, 128, 128), (5000, 1024, 130), (777, 384, 1), (300, 72, 17)])
+def test_tensor_core_scores_match_canonical(engine, n, dim, nq):
+    """Every accumulator the tcgen05 GEMM produces (descriptor / swizzle / TMEM addressing check)."""
+    X, Q = _bf16(synth.unit_rows(n, dim, 1)), _bf16(synth.unit_rows(nq, dim, 2))
+    idx = engine.VectorIndex(X)
+    got = idx.debug_tc_scores(Q).cpu().numpy()
+    want = exact.canonical_scores(_bits(X), _bits(Q))
+    assert not np.isnan(got).any()
+    err = np.abs(got - want).max()
+    # fp32 accumulation of exact bf16 products: far below the certification bound (dim/8+32) * 2^-23
+    assert err <= (dim / 8 + 32) * 2.0 ** -23 / 4, err
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [(1000, 64, 5, 10), (20000, 128, 300, 50), (5000, 1024, 130, 50),
+                                        (40, 64, 3, 50), (257, 64, 129, 1), (9000, 384, 64, 100)])
+def test_bf16_mode_topk(engine, n, dim, nq, k):
+    X, Q = _bf16(synth.unit_rows(n, dim, 3, clustered=16)), _bf16(synth.unit_rows(nq, dim, 4, clustered=16))
+    idx = engine.VectorIndex(X)
+    s, i = idx.topk(Q, k, mode="bf16")
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    rs, ri = exact.exact_topk(_bits(X), _bits(Q), k)
+    kk = min(k, n)
+    assert (i[:, kk:] == -1).all() and np.isneginf(s[:, kk:]).all()
+    # scores within 1e-2 relative of the fp32 reference (north-star tolerance); recall@k >= 0.999
+    assert np.allclose(s[:, :kk], rs[:, :kk], rtol=1e-2, atol=1e-4)
+    hits = sum(len(set(i[q, :kk]) & set(ri[q, :kk])) for q in range(nq))
+    assert hits / (nq * kk) >= 0.999
+    # sorted by (score desc, id asc)
+    assert (np.diff(s[:, :kk], axis=1) <= 0).all()
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+@pytest.mark.parametrize("n,dim,nq,k", [(1000, 64, 5, 10), (6000, 128, 70, 50), (50, 32, 4, 64), (5000, 384, 9, 5)])
+def test_exact_mode_ids_bit_exact(engine, dtype, n, dim, nq, k):
+    Xn, Qn = synth.unit_rows(n, dim, 5, clustered=8), synth.unit_rows(nq, dim, 6, clustered=8)
+    Xn[n // 2] = Xn[7]  # exact duplicates: tie -> lower id
+    Xn[n - 1] = Xn[7]
+    Qn[0] = Xn[7]
+    if dtype == "bf16":
+        X, Q = _bf16(Xn), _bf16(Qn)
+        rs, ri = exact.exact_topk(_bits(X), _bits(Q), k)
+    else:
+        X, Q = torch.from_numpy(Xn).cuda(), torch.from_numpy(Qn).cuda()
+        rs, ri = exact.exact_topk(Xn, Qn, k)
+    idx = engine.VectorIndex(X)
+    s, i = idx.topk(Q, k, mode="exact")
+    assert np.array_equal(i.cpu().numpy(), ri)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), rs.view(np.uint32))
+
+
+def test_exact_mode_uses_tensor_core_candidates_and_certifies(engine):
+    n, dim, nq, k = 60000, 256, 200, 50
+    X, Q = _bf16(synth.unit_rows(n, dim, 7)), _bf16(synth.unit_rows(nq, dim, 8))
+    idx = engine.VectorIndex(X)
+    s, i = idx.topk(Q, k, mode="exact")
+    cert, fb = idx.exact_stats()
+    assert cert + fb == nq and cert >= nq * 0.9  # random data: nearly every query certifies
+    rs, ri = exact.exact_topk(_bits(X), _bits(Q), k)
+    assert np.array_equal(i.cpu().numpy(), ri)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), rs.view(np.uint32))
+
+
+def test_exact_mode_fallback_on_near_ties(engine):
+    """Rows that differ by less than the tensor-core error bound cannot be certified -> brute-force fallback."""
+    n, dim, nq, k = 8192, 128, 6, 10
+    Xn = synth.unit_rows(n, dim, 9)
+    Xn[1000:1200] = Xn[999]  # 201 identical rows: the k-th / kc-th gap is zero
+    Qn = synth.unit_rows(nq, dim, 10)
+    Qn[0] = Xn[999]
+    X, Q = _bf16(Xn), _bf16(Qn)
+    idx = engine.VectorIndex(X)
+    s, i = idx.topk(Q, k, mode="exact")
+    cert, fb = idx.exact_stats()
+    assert fb >= 1
+    rs, ri = exact.exact_topk(_bits(X), _bits(Q), k)
+    assert np.array_equal(i.cpu().numpy(), ri)
+    assert list(i[0].cpu().numpy()) == list(range(999, 999 + k))
+
+
+def test_topk_host_entry_point(engine):
+    n, dim, nq, k = 3000, 128, 33, 20
+    X = _bf16(synth.unit_rows(n, dim, 11))
+    Qh = torch.from_numpy(synth.unit_rows(nq, dim, 12)).to(torch.bfloat16).pin_memory()
+    idx = engine.VectorIndex(X, id_base=1_000_000)
+    s, i = idx.topk_host(Qh, k, mode="exact")
+    rs, ri = exact.exact_topk(_bits(X), _bits(Qh), k, id_base=1_000_000)
+    assert np.array_equal(i.numpy(), ri) and np.array_equal(s.numpy().view(np.uint32), rs.view(np.uint32))
+
+
+def test_sharded_merge_equals_single_index(engine):
+    """Node-range shards + device k-way merge == one index (what the NCCL path computes), fp32-exact."""
+    n, dim, nq, k = 10000, 64, 40, 50
+    Xn, Qn = synth.unit_rows(n, dim, 13, clustered=4), synth.unit_rows(nq, dim, 14, clustered=4)
+    X, Q = _bf16(Xn), _bf16(Qn)
+    full_s, full_i = engine.VectorIndex(X).topk(Q, k, mode="exact")
+    for shards in (2, 4, 8):
+        bounds = [n * g // shards for g in range(shards + 1)]
+        parts = [engine.VectorIndex(X[bounds[g]:bounds[g + 1]].contiguous(), id_base=bounds[g]).topk(Q, k, mode="exact")
+                 for g in range(shards)]
+        ms, mi = engine.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+        assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+
+
+def test_empty_and_degenerate_inputs(engine):
+    dim = 64
+    X = _bf16(synth.unit_rows(10, dim, 15))
+    idx = engine.VectorIndex(X)
+    s, i = idx.topk(_bf16(synth.unit_rows(0, dim, 1).reshape(0, dim)), 5, mode="bf16")
+    assert s.shape == (0, 5)
+    with pytest.raises(RuntimeError):
+        idx.topk(torch.zeros((2, dim), dtype=torch.bfloat16), 5)  # host tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        idx.topk(_bf16(synth.unit_rows(2, dim, 1)), 5000, mode="exact")  # k too large -> library error
+
+
+def test_round4_device_matches_cpython(engine):
+    import random
+    random.seed(3)
+    xs = [random.random() * 2 for _ in range(20000)]
+    xs += [round(random.random(), 4) + 0.00005 for _ in range(20000)]
+    xs += [0.0, 0.00035, 5e-05, 1.00005, 2.5e-5, -0.00035, 123456.78905]
+    got = engine.round4_device(torch.tensor(xs, dtype=torch.float64).cuda()).cpu().numpy()
+    want = np.array([round(x, 4) for x in xs])
+    assert np.array_equal(got, want)
