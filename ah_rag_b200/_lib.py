@@ -23,7 +23,8 @@ OP_PARENTS, OP_CHILDREN, OP_RELATED = 0, 1, 2
 EXPORTS = [
     "ahr_last_error", "ahr_version", "ahr_launch_count", "ahr_index_create", "ahr_index_destroy", "ahr_topk",
     "ahr_topk_host", "ahr_merge_topk", "ahr_graph_create", "ahr_graph_destroy", "ahr_anchor_rerank", "ahr_expand",
-    "ahr_debug_tc_scores", "ahr_rescore", "ahr_debug_round4", "ahr_exact_stats",
+    "ahr_debug_tc_scores", "ahr_rescore", "ahr_debug_round4", "ahr_exact_stats", "ahr_set_profiling",
+    "ahr_get_profile",
 ]
 
 
@@ -58,6 +59,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.ahr_rescore.argtypes = [vp, vp, c_int32, c_int32, vp, vp, vp]
     lib.ahr_debug_round4.argtypes = [c_int, vp, c_int64, vp, vp]
     lib.ahr_exact_stats.argtypes = [vp, POINTER(c_int64), POINTER(c_int64)]
+    lib.ahr_set_profiling.argtypes = [vp, c_int]
+    lib.ahr_get_profile.argtypes = [vp, POINTER(c_double), POINTER(c_int64), POINTER(c_int32)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("ahr_last_error", "ahr_launch_count"):

@@ -63,6 +63,9 @@ struct ahr_index {
   DevBuf hq, hs, hi;  // device staging of the *_host entry point
   float *d_max_norm = nullptr;
   int64_t n_certified = 0, n_fallback = 0;
+  bool profile = false;  // CUDA-event timing of the dominant kernel (K1) on its launch stream
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  int last_slabs = 0;
 };
 
 struct ahr_graph {
@@ -163,8 +166,19 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
   if (rc != AHR_OK) return rc;
   float *ps = reinterpret_cast<float *>(idx->ws.ptr);
   int32_t *pi = reinterpret_cast<int32_t *>(ps + n_part);
+  idx->last_slabs = S;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (idx->profile) {
+    AHR_CUDA_CHECK(cudaEventCreate(&e0));
+    AHR_CUDA_CHECK(cudaEventCreate(&e1));
+    AHR_CUDA_CHECK(cudaEventRecord(e0, st));
+  }
   rc = tc_topk_partials(idx->map_x, dev_q, idx->n_rows, idx->dim, nq, k, S, idx->sm_count, ps, pi, dbg_scores, st);
   if (rc != AHR_OK) return rc;
+  if (idx->profile) {
+    AHR_CUDA_CHECK(cudaEventRecord(e1, st));
+    idx->prof_events.emplace_back(e0, e1);
+  }
   return select_topk(ps, pi, nullptr, (int64_t)S * k, (int64_t)S * k, nq, k, idx->id_base, false, out_scores, out_ids, st);
 }
 
@@ -302,6 +316,31 @@ int ahr_exact_stats(ahr_index *idx, int64_t *n_certified, int64_t *n_fallback) {
   AHR_REQUIRE(idx != nullptr, "ahr_exact_stats: index is NULL");
   if (n_certified) *n_certified = idx->n_certified;
   if (n_fallback) *n_fallback = idx->n_fallback;
+  return AHR_OK;
+}
+
+int ahr_set_profiling(ahr_index *idx, int enable) {
+  AHR_REQUIRE(idx != nullptr, "ahr_set_profiling: index is NULL");
+  idx->profile = enable != 0;
+  return AHR_OK;
+}
+
+int ahr_get_profile(ahr_index *idx, double *k1_ms_total, int64_t *k1_launches, int32_t *n_slabs) {
+  AHR_REQUIRE(idx != nullptr, "ahr_get_profile: index is NULL");
+  DeviceGuard guard(idx->device);
+  double total = 0.0;
+  for (auto &pr : idx->prof_events) {
+    AHR_CUDA_CHECK(cudaEventSynchronize(pr.second));
+    float ms = 0.f;
+    AHR_CUDA_CHECK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    total += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  if (k1_ms_total) *k1_ms_total = total;
+  if (k1_launches) *k1_launches = (int64_t)idx->prof_events.size();
+  if (n_slabs) *n_slabs = idx->last_slabs;
+  idx->prof_events.clear();
   return AHR_OK;
 }
 

@@ -1,0 +1,67 @@
+"""Node-range sharding of the embedding index across the GPUs of one box (one process per GPU).
+
+Each rank holds rows [lo, hi) of the corpus, computes its local top-k with the fused kernel, and the
+candidate lists meet through ONE all-gather (NCCL over NVLink; gloo in the CPU tests) followed by a
+device-side k-way merge with the total order (score desc, id asc) -- so fp32-exact results are identical
+for every shard count.  Queries are replicated (every rank receives the same batch).
+
+The reference has no distributed path at all; this is the B200-native scaling of
+the ``Collection.query`` seam (hierarchical_graph.py:714).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous node-id range of ``rank``: [n*rank/world, n*(rank+1)/world)."""
+    return (n_rows * rank) // world, (n_rows * (rank + 1)) // world
+
+
+def pack_candidates(scores: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """[nq, k] fp32 scores + [nq, k] int64 ids -> one flat byte buffer (a single collective moves both)."""
+    return torch.cat([scores.contiguous().view(torch.uint8).reshape(-1), ids.contiguous().view(torch.uint8).reshape(-1)])
+
+
+def unpack_candidates(buf: torch.Tensor, world: int, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[world, bytes] gathered buffer -> scores [world, nq, k] fp32, ids [world, nq, k] int64."""
+    sb = nq * k * 4
+    buf = buf.reshape(world, -1)
+    scores = buf[:, :sb].contiguous().view(torch.float32).reshape(world, nq, k)
+    ids = buf[:, sb:].contiguous().view(torch.int64).reshape(world, nq, k)
+    return scores, ids
+
+
+class ShardedIndex:
+    """Top-k over a corpus sharded by node range.  ``local_topk(q, k, mode) -> (scores, ids)`` with GLOBAL ids
+    and ``merge(scores[G,nq,k], ids[G,nq,k]) -> (scores, ids)`` are injectable so the plumbing can be tested
+    on CPU with gloo; in production they are ``VectorIndex.topk`` and ``engine.merge_topk``."""
+
+    def __init__(self, local_topk: Callable, merge: Callable, group: Optional[dist.ProcessGroup] = None) -> None:
+        self.local_topk = local_topk
+        self.merge = merge
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    @classmethod
+    def from_rows(cls, rows_local: torch.Tensor, id_base: int, group: Optional[dist.ProcessGroup] = None) -> "ShardedIndex":
+        from . import engine
+        index = engine.VectorIndex(rows_local, id_base=id_base)
+        obj = cls(index.topk, engine.merge_topk, group)
+        obj.index = index
+        return obj
+
+    def topk(self, q: torch.Tensor, k: int, mode: str = "bf16") -> Tuple[torch.Tensor, torch.Tensor]:
+        scores, ids = self.local_topk(q, k, mode)
+        if self.world == 1:
+            return scores, ids
+        nq = int(scores.shape[0])
+        mine = pack_candidates(scores, ids)
+        gathered = torch.empty((self.world, mine.numel()), dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)  # the single exchange of the path
+        all_s, all_i = unpack_candidates(gathered, self.world, nq, k)
+        return self.merge(all_s, all_i)

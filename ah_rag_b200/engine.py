@@ -101,6 +101,15 @@ class VectorIndex:
                                          out[1].data_ptr(), _stream_ptr(self.device)), "ahr_topk_host")
         return out
 
+    def set_profiling(self, enable: bool) -> None:
+        check(self.lib.ahr_set_profiling(self._h, 1 if enable else 0), "ahr_set_profiling")
+
+    def get_profile(self) -> Dict[str, Any]:
+        """Summed CUDA-event duration of the K1 launches since the last call (device time on the launch stream)."""
+        ms, n, s = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int32()
+        check(self.lib.ahr_get_profile(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(s)), "ahr_get_profile")
+        return {"k1_ms_total": float(ms.value), "k1_launches": int(n.value), "n_slabs": int(s.value)}
+
     def exact_stats(self) -> Tuple[int, int]:
         a, b = ctypes.c_int64(), ctypes.c_int64()
         check(self.lib.ahr_exact_stats(self._h, ctypes.byref(a), ctypes.byref(b)), "ahr_exact_stats")

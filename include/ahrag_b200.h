@@ -187,6 +187,12 @@ int ahr_debug_round4(int device, const double *dev_x, int64_t n, double *dev_out
  * candidate path vs. re-run through the brute-force exact scan */
 int ahr_exact_stats(ahr_index *idx, int64_t *n_certified, int64_t *n_fallback);
 
+/* CUDA-event timing of the dominant kernel (the fused GEMM + top-k, K1) on the stream it is launched on.
+ * ahr_get_profile waits for the recorded events, returns the summed duration (ms), the number of K1
+ * launches since the last call and the slab count of the last launch, and resets the record. */
+int ahr_set_profiling(ahr_index *idx, int enable);
+int ahr_get_profile(ahr_index *idx, double *k1_ms_total, int64_t *k1_launches, int32_t *n_slabs);
+
 #ifdef __cplusplus
 }
 #endif
