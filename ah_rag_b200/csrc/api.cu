@@ -57,7 +57,13 @@ struct ahr_index {
   const void *rows = nullptr;
   int64_t id_base = 0;
   bool has_map = false;
-  CUtensorMap map_x;
+  CUtensorMap map_x;   // box 64 x 256 rows (single-CTA K1)
+  CUtensorMap map_x2;  // box 64 x 128 rows (CTA-pair K1: each CTA stages half a corpus tile)
+  int variant = 2;     // AHR_TC_VARIANT: 2 = CTA pairs (default), 1 = single CTA
+  int prefetch_tiles = 0;  // AHR_TC_PREFETCH: L2 prefetch distance in corpus tiles (0 = off, the default: measured slower)
+  int force_slabs = 0;     // AHR_TC_SLABS: override the slab heuristic (experiments)
+  bool tc_stats = false;   // AHR_TC_STATS=1: per-role wait-cycle counters of K1, printed to stderr (debug)
+  DevBuf stats_buf;
   DevBuf ws;        // partial lists / score chunks
   DevBuf ws2;       // exact-mode scratch
   DevBuf hq, hs, hi;  // device staging of the *_host entry point
@@ -109,9 +115,14 @@ int ahr_index_create(ahr_index **out, int device, int64_t n_rows, int32_t dim, i
   if (dtype == AHR_DTYPE_BF16 && n_rows > 0 && dim % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(dev_rows) & 15) == 0) {
     int rc = tc_make_corpus_map(&idx->map_x, dev_rows, n_rows, dim);
+    if (rc == AHR_OK) rc = tc2_make_corpus_map(&idx->map_x2, dev_rows, n_rows, dim);
     if (rc != AHR_OK) { delete idx; return rc; }
     idx->has_map = true;
   }
+  if (const char *e = getenv("AHR_TC_VARIANT")) idx->variant = atoi(e) == 1 ? 1 : 2;
+  if (const char *e = getenv("AHR_TC_PREFETCH")) idx->prefetch_tiles = std::max(0, atoi(e));
+  if (const char *e = getenv("AHR_TC_SLABS")) idx->force_slabs = std::max(0, atoi(e));
+  if (const char *e = getenv("AHR_TC_STATS")) idx->tc_stats = atoi(e) != 0;
   cudaError_t e = cudaMalloc(&idx->d_max_norm, sizeof(float));
   if (e != cudaSuccess) { delete idx; set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return AHR_E_NOMEM; }
   int rc = row_norms_max(dev_rows, dtype, n_rows, dim, idx->d_max_norm, 0);
@@ -124,7 +135,7 @@ int ahr_index_create(ahr_index **out, int device, int64_t n_rows, int32_t dim, i
 int ahr_index_destroy(ahr_index *idx) {
   if (!idx) return AHR_OK;
   DeviceGuard guard(idx->device);
-  idx->ws.release(); idx->ws2.release(); idx->hq.release(); idx->hs.release(); idx->hi.release();
+  idx->stats_buf.release(); idx->ws.release(); idx->ws2.release(); idx->hq.release(); idx->hs.release(); idx->hi.release();
   if (idx->d_max_norm) cudaFree(idx->d_max_norm);
   delete idx;
   return AHR_OK;
@@ -159,8 +170,11 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
   AHR_REQUIRE(idx->has_map, "bf16 index is not TMA-addressable (dim %% 8 != 0 or rows not 16-byte aligned)");
   AHR_REQUIRE((reinterpret_cast<uintptr_t>(dev_q) & 15) == 0, "queries must be 16-byte aligned");
   const int64_t n_ctiles = (idx->n_rows + 255) / 256;
-  const int32_t n_qtiles = (nq + 127) / 128;
-  const int S = tc_choose_slabs(n_qtiles, n_ctiles, idx->sm_count);
+  const bool pairs = idx->variant == 2;
+  const int32_t n_qtiles = pairs ? (nq + 255) / 256 : (nq + 127) / 128;
+  const int n_units = pairs ? std::max(1, idx->sm_count / 2) : idx->sm_count;  // CTA pairs or CTAs
+  int S = tc_choose_slabs(n_qtiles, n_ctiles, n_units);
+  if (idx->force_slabs > 0) S = (int)std::min<int64_t>(idx->force_slabs, n_ctiles);
   const size_t n_part = (size_t)nq * S * k;
   int rc = idx->ws.reserve(n_part * 8);
   if (rc != AHR_OK) return rc;
@@ -173,11 +187,37 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
     AHR_CUDA_CHECK(cudaEventCreate(&e1));
     AHR_CUDA_CHECK(cudaEventRecord(e0, st));
   }
-  rc = tc_topk_partials(idx->map_x, dev_q, idx->n_rows, idx->dim, nq, k, S, idx->sm_count, ps, pi, dbg_scores, st);
+  unsigned long long *stats = nullptr;
+  if (idx->tc_stats && pairs) {
+    rc = idx->stats_buf.reserve((size_t)idx->sm_count * 8 * 8);
+    if (rc != AHR_OK) return rc;
+    stats = reinterpret_cast<unsigned long long *>(idx->stats_buf.ptr);
+    AHR_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)idx->sm_count * 64, st));
+  }
+  if (pairs)
+    rc = tc2_topk_partials(idx->map_x2, dev_q, idx->n_rows, idx->dim, nq, k, S, n_units, idx->prefetch_tiles, ps, pi,
+                           dbg_scores, stats, st);
+  else
+    rc = tc_topk_partials(idx->map_x, dev_q, idx->n_rows, idx->dim, nq, k, S, idx->sm_count, ps, pi, dbg_scores, st);
   if (rc != AHR_OK) return rc;
   if (idx->profile) {
     AHR_CUDA_CHECK(cudaEventRecord(e1, st));
     idx->prof_events.emplace_back(e0, e1);
+  }
+  if (stats) {
+    std::vector<unsigned long long> h((size_t)idx->sm_count * 8);
+    AHR_CUDA_CHECK(cudaMemcpyAsync(h.data(), stats, h.size() * 8, cudaMemcpyDeviceToHost, st));
+    AHR_CUDA_CHECK(cudaStreamSynchronize(st));
+    double sum[8] = {0}, total = 0;
+    int n_lead = 0;
+    for (int b = 0; b < idx->sm_count; ++b) {
+      for (int j = 0; j < 8; ++j) sum[j] += (double)h[(size_t)b * 8 + j];
+      if (h[(size_t)b * 8 + 3]) { total += (double)h[(size_t)b * 8 + 3]; ++n_lead; }
+    }
+    if (n_lead)
+      fprintf(stderr, "[ahr tc stats] leaders=%d avg cycles: total=%.0f mma_wait_full=%.0f mma_wait_tempty=%.0f | "
+              "per CTA: producer_wait_empty=%.0f epi_wait_tfull=%.0f epi_slow_chunks=%.0f\n", n_lead, total / n_lead,
+              sum[1] / n_lead, sum[2] / n_lead, sum[0] / idx->sm_count, sum[4] / idx->sm_count, sum[5] / idx->sm_count);
   }
   return select_topk(ps, pi, nullptr, (int64_t)S * k, (int64_t)S * k, nq, k, idx->id_base, false, out_scores, out_ids, st);
 }

@@ -17,6 +17,12 @@ int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows
                      int32_t n_slabs, int grid, float *part_scores, int32_t *part_ids, float *dbg_scores,
                      cudaStream_t stream);
 
+// ---- topk_tc2.cu (K1, CTA-pair variant) ----
+int tc2_make_corpus_map(CUtensorMap *map, const void *dev_rows, int64_t n_rows, int32_t dim);
+int tc2_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows, int32_t dim, int32_t nq, int32_t k,
+                      int32_t n_slabs, int n_pairs, int prefetch_tiles, float *part_scores, int32_t *part_ids,
+                      float *dbg_scores, unsigned long long *stats, cudaStream_t stream);
+
 // ---- select.cu ----
 // Per query: reduce n_cand candidates to the top k by (score desc, id asc).
 //   cand_scores[q * stride + i];  ids: cand_ids32 / cand_ids64 (one may be given) or implicit = i;

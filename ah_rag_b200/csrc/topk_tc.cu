@@ -21,51 +21,9 @@
 // TMEM: 512 columns = 2 accumulator stages x 256, so the epilogue drains tile i while tile i+1 is computed.
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_shared.cuh"
 
 namespace ahr {
-
-constexpr int TC_BM = 128;
-constexpr int TC_BN = 256;
-constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
-constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
-constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KB
-constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-
-struct TcParams {
-  int64_t n_rows;
-  int64_t n_ctiles;  // ceil(n_rows / 256)
-  int32_t nq;
-  int32_t dim;
-  int32_t n_qtiles;  // ceil(nq / 128)
-  int32_t n_slabs;   // S
-  int32_t k;         // entries kept per (query, slab), <= KLIST
-  float *part_scores;    // [nq_pad][S][k]
-  int32_t *part_ids;     // row index inside this index (local), -1 = empty
-  float *dbg_scores;     // optional [nq][n_rows] dump of the raw accumulators (tests)
-};
-
-__device__ __forceinline__ void slab_range(const TcParams &p, int slab, int64_t &t0, int64_t &t1) {
-  t0 = (p.n_ctiles * slab) / p.n_slabs;
-  t1 = (p.n_ctiles * (slab + 1)) / p.n_slabs;
-}
-
-// sorted insertion into one row's list (column `row` of the [KLIST][128] arrays); returns the new k-th
-// score.  Strict '<' keeps the earlier (lower) row id ahead on equal scores.  Kept out of line: it is the
-// rare path of the epilogue and would otherwise be inlined once per unrolled column.
-__device__ __noinline__ float list_insert(float *ls_row, int32_t *li_row, int k, float s, int32_t id) {
-  int pos = k - 1;
-  while (pos > 0) {
-    const float prev = ls_row[(pos - 1) * TC_BM];
-    if (!(prev < s)) break;
-    ls_row[pos * TC_BM] = prev;
-    li_row[pos * TC_BM] = li_row[(pos - 1) * TC_BM];
-    --pos;
-  }
-  ls_row[pos * TC_BM] = s;
-  li_row[pos * TC_BM] = id;
-  return ls_row[(k - 1) * TC_BM];
-}
 
 template <int KLIST, int TC_STAGES, bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -74,9 +32,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   // 128B-swizzled operand tiles need 1024-byte alignment
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *tiles = smem;
-  float *ls = reinterpret_cast<float *>(tiles + TC_STAGES * TC_STAGE_BYTES);  // [KLIST][128] scores, sorted desc
-  int32_t *li = reinterpret_cast<int32_t *>(ls + KLIST * TC_BM);              // [KLIST][128] row ids
-  uint64_t *bars = reinterpret_cast<uint64_t *>(li + KLIST * TC_BM);
+  unsigned long long *lists = reinterpret_cast<unsigned long long *>(tiles + TC_STAGES * TC_STAGE_BYTES);  // [128][KLIST] keys
+  uint64_t *bars = reinterpret_cast<uint64_t *>(lists + KLIST * TC_BM);
   uint64_t *full = bars;                  // [STAGES] TMA -> MMA
   uint64_t *empty = bars + TC_STAGES;     // [STAGES] MMA -> TMA
   uint64_t *tfull = bars + 2 * TC_STAGES; // [2] MMA -> epilogue
@@ -100,7 +57,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
-        mbar_init(&tempty[a], 128);
+        mbar_init(&tempty[a], 4);  // one arrival per epilogue warp
       }
       fence_mbar_init();
     }
@@ -135,6 +92,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
       }
     }
+    __syncwarp();  // reconverge before the block/cluster-wide barrier below
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
@@ -171,11 +129,12 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue: TMEM -> registers -> per-row top-k =====================
-    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;    // query row inside the tile == TMEM lane
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access; thread = query row = TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t lists_warp = smem_u32(lists) + (uint32_t)(quad * 32) * (KLIST * 8);
     const int k = p.k;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -183,58 +142,27 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const int slab = item / p.n_qtiles, qt = item % p.n_qtiles;
       int64_t t0, t1;
       slab_range(p, slab, t0, t1);
-      const int64_t q_global = (int64_t)qt * TC_BM + row;
+      const int64_t q_first = (int64_t)qt * TC_BM + quad * 32;
+      const int64_t q_global = q_first + lane;
       const bool row_valid = q_global < p.nq;
-      for (int j = 0; j < k; ++j) {
-        ls[j * TC_BM + row] = -INFINITY;
-        li[j * TC_BM + row] = -1;
-      }
+      lists_reset<KLIST>(lists_warp);
       float thr = -INFINITY;
+      int slot = 0;
       for (int64_t ct = t0; ct < t1; ++ct) {
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         const int64_t col0 = ct * TC_BN;
         const int ncols = (int)min((int64_t)TC_BN, p.n_rows - col0);
-        for (int c = 0; c < TC_BN; c += 32) {
-          if (c >= ncols) break;  // warp-uniform
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_lane + (uint32_t)(acc * TC_BN + c), v);
-          tmem_ld_wait();
-          if (ncols - c < 32) {  // ragged last corpus tile: TMA zero-filled rows are not candidates
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c + j >= ncols) v[j] = 0xFF800000u;  // -inf
-          }
-          if (row_valid) {
-            if (DBG) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c + j < ncols) p.dbg_scores[q_global * p.n_rows + col0 + c + j] = __uint_as_float(v[j]);
-            }
-            // fast path: one max per column, one compare per 32 columns
-            float m = __uint_as_float(v[0]);
-#pragma unroll
-            for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-            if (m > thr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float s = __uint_as_float(v[j]);
-                if (s > thr) thr = list_insert(ls + row, li + row, k, s, (int32_t)(col0 + c + j));
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(&tempty[acc]);  // 128 arrivals release the accumulator stage
+        uint64_t *release_bar = &tempty[acc];
+        epilogue_scan_tile<KLIST, TC_BN, DBG>(t_lane + (uint32_t)(acc * TC_BN), ncols, row_valid, k, col0, q_global, p,
+                                              lists_warp, thr, slot, nullptr, [&]() {
+                                                tc_fence_before();
+                                                __syncwarp();
+                                                if (lane == 0) mbar_arrive(release_bar);
+                                              });
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (row_valid) {
-        const int64_t base = (q_global * p.n_slabs + slab) * k;
-        for (int j = 0; j < k; ++j) {
-          p.part_scores[base + j] = ls[j * TC_BM + row];
-          p.part_ids[base + j] = li[j * TC_BM + row];
-        }
-      }
+      lists_flush<KLIST>(lists_warp, k, q_first, p, slab);
     }
   }
 
@@ -350,6 +278,7 @@ int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows
   p.part_scores = part_scores;
   p.part_ids = part_ids;
   p.dbg_scores = dbg_scores;
+  p.stats = nullptr;
   const int items = p.n_slabs * p.n_qtiles;
   if (grid > items) grid = items;
   if (dbg_scores) {

@@ -1,0 +1,265 @@
+// topk_tc2.cu -- K1, CTA-pair variant: the fused similarity GEMM + top-k epilogue on tcgen05.mma.cta_group::2.
+//
+// Why pairs: with one CTA per tile every SM has to pull A (16 KB) + B (32 KB) per 64-wide k-block from L2 =
+// 96 B/clk/SM at full MMA rate, and only 3 x 48 KB stages fit beside the 64 KB of per-row lists -- the ncu
+// capture of the single-CTA kernel (profiles/r1_k1_v1_1cta_ncu.md) shows a latency-bound pipeline at 16-35 %
+// tensor-pipe activity.  A CTA pair computes one 256 x 256 tile: each CTA stages its own 128 queries (A,
+// 16 KB) and HALF of the 256 corpus rows (B, 16 KB); the tensor core reads both halves of B from the two
+// SMs.  32 KB per stage -> 5 stages in flight and 64 B/clk/SM of L2 traffic.
+//
+//   pair (cluster of 2 CTAs) : item = (slab, 256-query tile); item -> cluster round-robin, slab-major
+//   CTA r of the pair        : query rows  qt*256 + r*128 .. +128   (its TMEM lanes / its epilogue / its lists)
+//                              corpus rows ct*256 + r*128 .. +128   (its half of every B tile)
+//   leader CTA (rank 0)      : issues every tcgen05.mma; its full barrier collects the TMA bytes of BOTH CTAs;
+//                              tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs;
+//                              the epilogue warps of both CTAs release the accumulator on the leader's barrier.
+//   L2 prefetch              : the producer issues cp.async.bulk.prefetch.tensor for the B half-tile a few
+//                              tiles ahead, so HBM latency is hidden without spending shared memory.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_shared.cuh"
+
+namespace ahr {
+
+constexpr int T2_BM = 128;                      // query rows per CTA
+constexpr int T2_BN = 256;                      // corpus rows per tile (pair)
+constexpr int T2_BN_HALF = 128;                 // corpus rows staged by each CTA
+constexpr uint32_t T2_A_BYTES = T2_BM * TC_BK * 2;        // 16 KB
+constexpr uint32_t T2_B_BYTES = T2_BN_HALF * TC_BK * 2;   // 16 KB
+constexpr uint32_t T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
+
+template <int KLIST, int STAGES, bool DBG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TcParams p,
+                int prefetch_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *tiles = smem;
+  unsigned long long *lists = reinterpret_cast<unsigned long long *>(tiles + STAGES * T2_STAGE_BYTES);  // [128][KLIST] keys
+  uint64_t *bars = reinterpret_cast<uint64_t *>(lists + KLIST * T2_BM);
+  uint64_t *full = bars;                 // [STAGES] leader's copy is the live one (bytes of both CTAs)
+  uint64_t *empty = bars + STAGES;       // [STAGES] per CTA: MMA done reading this stage
+  uint64_t *tfull = bars + 2 * STAGES;   // [2] per CTA: accumulator stage complete
+  uint64_t *tempty = tfull + 2;          // [2] leader's copy: both epilogues drained the stage
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int n_items = p.n_slabs * p.n_qtiles;  // n_qtiles counts 256-query tiles here
+  const int n_kblocks = (p.dim + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_q);
+    prefetch_tensormap(&map_x);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full[s], 1);   // the leader's arrive.expect_tx; TMA bytes of both CTAs complete it
+        mbar_init(&empty[s], 1);  // one multicast commit
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull[a], 1);   // one multicast commit
+        mbar_init(&tempty[a], 8);  // 4 epilogue warps x 2 CTAs
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm<512>(tmem_slot);  // same warp id, same smem offset in both CTAs
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers initialised and TMEM allocated in both CTAs before any remote access
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      unsigned long long w_empty = 0;
+      unsigned long long *acct = p.stats ? &w_empty : nullptr;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int slab = item / p.n_qtiles, qt = item % p.n_qtiles;
+        int64_t t0, t1;
+        slab_range(p, slab, t0, t1);
+        const int32_t q_row0 = qt * (2 * T2_BM) + (int32_t)rank * T2_BM;
+        for (int64_t ct = t0; ct < t1; ++ct) {
+          const int32_t x_row0 = (int32_t)(ct * T2_BN) + (int32_t)rank * T2_BN_HALF;
+          const bool pf = prefetch_tiles > 0 && ct + prefetch_tiles < t1;
+          for (int kb = 0; kb < n_kblocks; ++kb) {
+            if (pf) tma_prefetch_2d(&map_x, kb * TC_BK, x_row0 + prefetch_tiles * T2_BN);
+            mbar_wait_acct(&empty[stage], phase ^ 1, acct);
+            uint8_t *a_dst = tiles + stage * T2_STAGE_BYTES;
+            uint8_t *b_dst = a_dst + T2_A_BYTES;
+            const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * T2_STAGE_BYTES);
+            tma_load_2d_2sm(a_dst, &map_q, full_leader, kb * TC_BK, q_row0, kEvictLast);
+            tma_load_2d_2sm(b_dst, &map_x, full_leader, kb * TC_BK, x_row0, kEvictNormal);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      if (p.stats) p.stats[blockIdx.x * 8 + 0] = w_empty;
+    }
+    __syncwarp();  // reconverge before the block/cluster-wide barrier below
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * T2_BM, T2_BN);  // M = 256 across the pair, N = 256
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      unsigned long long w_full = 0, w_tempty = 0;
+      const long long t_begin = clock64();
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int slab = item / p.n_qtiles;
+        int64_t t0, t1;
+        slab_range(p, slab, t0, t1);
+        for (int64_t ct = t0; ct < t1; ++ct) {
+          mbar_wait_acct(&tempty[acc], acc_phase ^ 1, p.stats ? &w_tempty : nullptr);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * T2_BN;
+          for (int kb = 0; kb < n_kblocks; ++kb) {
+            mbar_wait_acct(&full[stage], phase, p.stats ? &w_full : nullptr);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(tiles + stage * T2_STAGE_BYTES);
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+            const uint64_t b_desc = make_smem_desc_sw128(a_addr + T2_A_BYTES);
+#pragma unroll
+            for (int k4 = 0; k4 < TC_BK / 16; ++k4)
+              umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), idesc,
+                               (kb | k4) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty[stage], 0x3);  // frees this stage in both CTAs
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_2sm(&tfull[acc], 0x3);  // accumulator ready in both CTAs
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+      if (p.stats) {
+        p.stats[blockIdx.x * 8 + 1] = w_full;
+        p.stats[blockIdx.x * 8 + 2] = w_tempty;
+        p.stats[blockIdx.x * 8 + 3] = (unsigned long long)(clock64() - t_begin);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (both CTAs): TMEM -> registers -> per-row top-k =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access; thread = query row = TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t lists_warp = smem_u32(lists) + (uint32_t)(quad * 32) * (KLIST * 8);
+    const int k = p.k;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    unsigned long long w_tfull = 0, n_slow = 0;
+    unsigned long long *acct = (p.stats && threadIdx.x == 64) ? &w_tfull : nullptr;
+    for (int item = cluster_id; item < n_items; item += n_clusters) {
+      const int slab = item / p.n_qtiles, qt = item % p.n_qtiles;
+      int64_t t0, t1;
+      slab_range(p, slab, t0, t1);
+      const int64_t q_first = (int64_t)qt * (2 * T2_BM) + (int64_t)rank * T2_BM + quad * 32;
+      const int64_t q_global = q_first + lane;
+      const bool row_valid = q_global < p.nq;
+      lists_reset<KLIST>(lists_warp);
+      float thr = -INFINITY;
+      int slot = 0;
+      for (int64_t ct = t0; ct < t1; ++ct) {
+        mbar_wait_acct(&tfull[acc], acc_phase, acct);
+        tc_fence_after();
+        const int64_t col0 = ct * T2_BN;
+        const int ncols = (int)min((int64_t)T2_BN, p.n_rows - col0);
+        const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[acc]), 0);
+        epilogue_scan_tile<KLIST, T2_BN, DBG>(t_lane + (uint32_t)(acc * T2_BN), ncols, row_valid, k, col0, q_global, p,
+                                              lists_warp, thr, slot, acct ? &n_slow : nullptr, [&]() {
+                                                tc_fence_before();
+                                                __syncwarp();
+                                                if (lane == 0) mbar_arrive_cluster(tempty_leader);  // leader's barrier
+                                              });
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      lists_flush<KLIST>(lists_warp, k, q_first, p, slab);
+    }
+    if (acct) {
+      p.stats[blockIdx.x * 8 + 4] = w_tfull;
+      p.stats[blockIdx.x * 8 + 5] = n_slow;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be reading our smem / signalling our barriers until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int make_bf16_tensor_map(CUtensorMap *map, const void *dev_ptr, int64_t rows, int32_t dim, int32_t box_rows);
+
+int tc2_make_corpus_map(CUtensorMap *map, const void *dev_rows, int64_t n_rows, int32_t dim) {
+  return make_bf16_tensor_map(map, dev_rows, n_rows, dim, T2_BN_HALF);
+}
+
+template <int KLIST, int STAGES>
+static constexpr size_t tc2_smem_bytes() {
+  return 1024 + (size_t)STAGES * T2_STAGE_BYTES + (size_t)KLIST * T2_BM * 8 + 256;
+}
+
+template <int KLIST, int STAGES, bool DBG>
+static int tc2_launch_t(const CUtensorMap &map_q, const CUtensorMap &map_x, const TcParams &p, int n_clusters,
+                        int prefetch_tiles, cudaStream_t stream) {
+  static bool configured = false;
+  constexpr size_t smem = tc2_smem_bytes<KLIST, STAGES>();
+  static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+  if (!configured) {
+    AHR_CUDA_CHECK(cudaFuncSetAttribute(topk_tc2_kernel<KLIST, STAGES, DBG>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  topk_tc2_kernel<KLIST, STAGES, DBG><<<2 * n_clusters, TC_THREADS, smem, stream>>>(map_q, map_x, p, prefetch_tiles);
+  AHR_KERNEL_CHECK();
+  return AHR_OK;
+}
+
+// Launch the CTA-pair K1.  part_* must hold nq * n_slabs * k entries; n_pairs = SM count / 2.
+int tc2_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows, int32_t dim, int32_t nq, int32_t k,
+                      int32_t n_slabs, int n_pairs, int prefetch_tiles, float *part_scores, int32_t *part_ids,
+                      float *dbg_scores, unsigned long long *stats, cudaStream_t stream) {
+  AHR_REQUIRE(k >= 1 && k <= 128, "tensor-core top-k supports 1 <= k <= 128 (got %d)", k);
+  AHR_REQUIRE(dim % 8 == 0, "bf16 index needs dim %% 8 == 0 for TMA (got %d)", dim);
+  AHR_REQUIRE(n_rows < (int64_t)INT32_MAX - T2_BN, "rows per index shard must fit int32 (got %lld)", (long long)n_rows);
+  CUtensorMap map_q;
+  int rc = make_bf16_tensor_map(&map_q, dev_q, nq, dim, T2_BM);
+  if (rc != AHR_OK) return rc;
+  TcParams p;
+  p.n_rows = n_rows;
+  p.n_ctiles = (n_rows + T2_BN - 1) / T2_BN;
+  p.nq = nq;
+  p.dim = dim;
+  p.n_qtiles = (nq + 2 * T2_BM - 1) / (2 * T2_BM);
+  p.n_slabs = n_slabs;
+  p.k = k;
+  p.part_scores = part_scores;
+  p.part_ids = part_ids;
+  p.dbg_scores = dbg_scores;
+  p.stats = stats;
+  const int items = p.n_slabs * p.n_qtiles;
+  int n_clusters = n_pairs < items ? n_pairs : items;
+  if (n_clusters < 1) n_clusters = 1;
+  if (dbg_scores) {
+    AHR_REQUIRE(k <= 64, "debug score dump supports k <= 64");
+    return tc2_launch_t<64, 5, true>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+  }
+  if (k <= 64) return tc2_launch_t<64, 5, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+  return tc2_launch_t<128, 3, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+}
+
+}  // namespace ahr

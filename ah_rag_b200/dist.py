@@ -61,7 +61,7 @@ class ShardedIndex:
             return scores, ids
         nq = int(scores.shape[0])
         mine = pack_candidates(scores, ids)
-        gathered = torch.empty((self.world, mine.numel()), dtype=torch.uint8, device=mine.device)
+        gathered = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=mine.device)
         dist.all_gather_into_tensor(gathered, mine, group=self.group)  # the single exchange of the path
         all_s, all_i = unpack_candidates(gathered, self.world, nq, k)
         return self.merge(all_s, all_i)
