@@ -43,6 +43,15 @@ GEN_CHUNK = 250_000
 METRIC = "queries/sec (top-k=50, 10M x 1024 bf16 corpus, 4096-query batch)"
 
 
+def _traffic(world: int):
+    """DRAM bytes per K1 launch from the committed ncu --set full capture (1-GPU c3 workload only)."""
+    path = os.path.join(ROOT, "profiles", "r1_k1_traffic.json")
+    if world == 1 and N_ROWS == 10_000_000 and DIM == 1024 and N_QUERIES == 4096 and os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -272,7 +281,9 @@ def main() -> int:
                     "d2h_bytes_per_step": N_QUERIES * TOP_K * 12},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": None, "kernel": "topk_tc_kernel (K1)",
+                         "frac": achieved / peaks["tflops"], "traffic": _traffic(world),
+                         "kernel": "ahr::topk_tc2_kernel (K1, CTA-pair tcgen05 GEMM + top-k epilogue)",
+                         "algorithmic_flops_per_launch": flops,
                          "kernel_ms": k1_ms, "kernel_share_of_step": k1_ms / ms_step if ms_step else None,
                          "peak_source": peaks["source"],
                          "hbm_floor_ms": (hi - lo) * DIM * 2 / (peaks["hbm_gbs"] * 1e9) * 1e3},
