@@ -22,7 +22,7 @@ OP_PARENTS, OP_CHILDREN, OP_RELATED = 0, 1, 2
 # every symbol include/ahrag_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "ahr_last_error", "ahr_version", "ahr_launch_count", "ahr_index_create", "ahr_index_destroy", "ahr_topk",
-    "ahr_topk_host", "ahr_merge_topk", "ahr_graph_create", "ahr_graph_destroy", "ahr_anchor_rerank", "ahr_expand",
+    "ahr_topk_host", "ahr_merge_topk", "ahr_merge_topk_packed", "ahr_graph_create", "ahr_graph_destroy", "ahr_anchor_rerank", "ahr_expand",
     "ahr_debug_tc_scores", "ahr_rescore", "ahr_debug_round4", "ahr_exact_stats", "ahr_set_profiling",
     "ahr_get_profile",
 ]
@@ -50,6 +50,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.ahr_topk.argtypes = [vp, vp, c_int32, c_int32, c_int, vp, vp, vp]
     lib.ahr_topk_host.argtypes = [vp, vp, c_int32, c_int32, c_int, vp, vp, vp]
     lib.ahr_merge_topk.argtypes = [c_int, vp, vp, c_int32, c_int32, c_int32, vp, vp, vp]
+    lib.ahr_merge_topk_packed.argtypes = [c_int, vp, c_int64, c_int32, c_int32, c_int32, vp, vp, vp]
     lib.ahr_graph_create.argtypes = [POINTER(vp), c_int, c_int64, POINTER(vp), POINTER(vp), vp, vp, vp, vp, vp]
     lib.ahr_graph_destroy.argtypes = [vp]
     lib.ahr_anchor_rerank.argtypes = [vp, c_int32, c_int32, vp, vp, POINTER(RerankParams), c_int32,

@@ -330,6 +330,23 @@ int ahr_merge_topk(int device, const float *dev_scores, const int64_t *dev_ids, 
                              dev_out_scores, dev_out_ids, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int ahr_merge_topk_packed(int device, const void *dev_packed, int64_t record_bytes, int32_t parts, int32_t nq, int32_t k,
+                          float *dev_out_scores, int64_t *dev_out_ids, void *stream) {
+  AHR_REQUIRE(parts >= 1 && nq >= 0 && k >= 1, "ahr_merge_topk_packed: bad sizes parts=%d nq=%d k=%d", parts, nq, k);
+  if (nq == 0) return AHR_OK;
+  const int64_t sb = (int64_t)nq * k * 4;
+  AHR_REQUIRE(dev_packed && dev_out_scores && dev_out_ids, "ahr_merge_topk_packed: NULL buffer");
+  AHR_REQUIRE(sb % 8 == 0 && record_bytes % 8 == 0 && record_bytes >= sb * 3,
+              "ahr_merge_topk_packed: record of %lld bytes cannot hold %d x %d (score, id) pairs 8-byte aligned",
+              (long long)record_bytes, nq, k);
+  DeviceGuard guard(device);
+  const float *scores = reinterpret_cast<const float *>(dev_packed);
+  const int64_t *ids = reinterpret_cast<const int64_t *>(reinterpret_cast<const uint8_t *>(dev_packed) + sb);
+  // part p: scores at + p * record_bytes / 4 floats, ids at + p * record_bytes / 8 int64
+  return select_topk_strided2(scores, nullptr, ids, k, (int64_t)parts * k, k, record_bytes / 4, record_bytes / 8, nq, k, 0,
+                              false, dev_out_scores, dev_out_ids, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int ahr_debug_tc_scores(ahr_index *idx, const void *dev_q, int32_t nq, float *dev_out, void *stream) {
   AHR_REQUIRE(idx && dev_q && dev_out && nq >= 1, "ahr_debug_tc_scores: bad arguments");
   AHR_REQUIRE(idx->n_rows >= 1, "ahr_debug_tc_scores: empty index");

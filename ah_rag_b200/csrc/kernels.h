@@ -35,6 +35,11 @@ int select_topk(const float *cand_scores, const int32_t *cand_ids32, const int64
 int select_topk_strided(const float *cand_scores, const int32_t *cand_ids32, const int64_t *cand_ids64, int64_t stride,
                         int64_t n_cand, int64_t inner, int64_t stride_outer, int32_t nq, int32_t k, int64_t id_offset,
                         bool carry_in, float *out_scores, int64_t *out_ids, cudaStream_t stream);
+// separate outer strides (in elements) for the score and id arrays
+int select_topk_strided2(const float *cand_scores, const int32_t *cand_ids32, const int64_t *cand_ids64, int64_t stride,
+                         int64_t n_cand, int64_t inner, int64_t stride_outer, int64_t stride_outer_ids, int32_t nq,
+                         int32_t k, int64_t id_offset, bool carry_in, float *out_scores, int64_t *out_ids,
+                         cudaStream_t stream);
 constexpr int SELECT_MAX_K = 1024;
 
 // ---- topk_exact.cu (K1x) ----

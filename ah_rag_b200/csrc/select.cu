@@ -68,7 +68,7 @@ __device__ void sel_reduce(SelSmem &sm, int k) {
 __global__ void __launch_bounds__(SEL_THREADS)
 select_topk_kernel(const float *__restrict__ cand_scores, const int32_t *__restrict__ ids32,
                    const int64_t *__restrict__ ids64, int64_t stride, int64_t n_cand, int64_t inner,
-                   int64_t stride_outer, int32_t k, int64_t id_offset, int carry_in,
+                   int64_t stride_outer, int64_t stride_outer_ids, int32_t k, int64_t id_offset, int carry_in,
                    float *__restrict__ out_scores, int64_t *__restrict__ out_ids) {
   __shared__ SelSmem sm;
   const int64_t q = blockIdx.x;
@@ -96,8 +96,9 @@ select_topk_kernel(const float *__restrict__ cand_scores, const int32_t *__restr
     const int64_t i = base + threadIdx.x;
     if (i < n_cand) {
       const int64_t at = q * stride + (i / inner) * stride_outer + (i % inner);
+      const int64_t at_id = q * stride + (i / inner) * stride_outer_ids + (i % inner);
       const float s = cand_scores[at];
-      int64_t id = ids32 ? (int64_t)ids32[at] : (ids64 ? ids64[at] : i);
+      int64_t id = ids32 ? (int64_t)ids32[at_id] : (ids64 ? ids64[at_id] : i);
       bool ok = id >= 0 && s == s;  // skip empty slots and NaN scores
       id += id_offset;
       if (ok && sm.have_thr) ok = ranks_before(s, id, sm.thr_s, sm.thr_id);
@@ -116,16 +117,25 @@ select_topk_kernel(const float *__restrict__ cand_scores, const int32_t *__restr
   }
 }
 
-int select_topk_strided(const float *cand_scores, const int32_t *cand_ids32, const int64_t *cand_ids64, int64_t stride,
-                        int64_t n_cand, int64_t inner, int64_t stride_outer, int32_t nq, int32_t k, int64_t id_offset,
-                        bool carry_in, float *out_scores, int64_t *out_ids, cudaStream_t stream) {
+int select_topk_strided2(const float *cand_scores, const int32_t *cand_ids32, const int64_t *cand_ids64, int64_t stride,
+                         int64_t n_cand, int64_t inner, int64_t stride_outer, int64_t stride_outer_ids, int32_t nq,
+                         int32_t k, int64_t id_offset, bool carry_in, float *out_scores, int64_t *out_ids,
+                         cudaStream_t stream) {
   AHR_REQUIRE(k >= 1 && k <= SELECT_MAX_K, "k must be in [1, %d] (got %d)", SELECT_MAX_K, k);
   if (nq <= 0) return AHR_OK;
   if (inner <= 0) inner = 1;
   select_topk_kernel<<<nq, SEL_THREADS, 0, stream>>>(cand_scores, cand_ids32, cand_ids64, stride, n_cand, inner,
-                                                     stride_outer, k, id_offset, carry_in ? 1 : 0, out_scores, out_ids);
+                                                     stride_outer, stride_outer_ids, k, id_offset, carry_in ? 1 : 0,
+                                                     out_scores, out_ids);
   AHR_KERNEL_CHECK();
   return AHR_OK;
+}
+
+int select_topk_strided(const float *cand_scores, const int32_t *cand_ids32, const int64_t *cand_ids64, int64_t stride,
+                        int64_t n_cand, int64_t inner, int64_t stride_outer, int32_t nq, int32_t k, int64_t id_offset,
+                        bool carry_in, float *out_scores, int64_t *out_ids, cudaStream_t stream) {
+  return select_topk_strided2(cand_scores, cand_ids32, cand_ids64, stride, n_cand, inner, stride_outer, stride_outer, nq,
+                              k, id_offset, carry_in, out_scores, out_ids, stream);
 }
 
 int select_topk(const float *cand_scores, const int32_t *cand_ids32, const int64_t *cand_ids64, int64_t stride,

@@ -43,6 +43,7 @@ class ShardedIndex:
     def __init__(self, local_topk: Callable, merge: Callable, group: Optional[dist.ProcessGroup] = None) -> None:
         self.local_topk = local_topk
         self.merge = merge
+        self.merge_packed: Optional[Callable] = None  # device fast path: merge out of the gathered buffer, no re-pack
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -53,13 +54,23 @@ class ShardedIndex:
         index = engine.VectorIndex(rows_local, id_base=id_base)
         obj = cls(index.topk, engine.merge_topk, group)
         obj.index = index
+        obj.merge_packed = engine.merge_topk_packed
         return obj
 
     def topk(self, q: torch.Tensor, k: int, mode: str = "bf16") -> Tuple[torch.Tensor, torch.Tensor]:
-        scores, ids = self.local_topk(q, k, mode)
         if self.world == 1:
-            return scores, ids
-        nq = int(scores.shape[0])
+            return self.local_topk(q, k, mode)
+        nq = int(q.shape[0])
+        if self.merge_packed is not None and (nq * k * 4) % 8 == 0:
+            # the local top-k writes straight into this rank's record of the exchange buffer
+            rec = nq * k * 12
+            mine = torch.empty(rec, dtype=torch.uint8, device=q.device)
+            out = (mine[: nq * k * 4].view(torch.float32).view(nq, k), mine[nq * k * 4:].view(torch.int64).view(nq, k))
+            self.local_topk(q, k, mode, out=out)
+            gathered = torch.empty(self.world * rec, dtype=torch.uint8, device=q.device)
+            dist.all_gather_into_tensor(gathered, mine, group=self.group)  # the single exchange of the path
+            return self.merge_packed(gathered, self.world, nq, k)
+        scores, ids = self.local_topk(q, k, mode)
         mine = pack_candidates(scores, ids)
         gathered = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=mine.device)
         dist.all_gather_into_tensor(gathered, mine, group=self.group)  # the single exchange of the path

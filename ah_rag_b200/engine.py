@@ -74,14 +74,23 @@ class VectorIndex:
             return _lib.AHR_MODE_EXACT
         raise ValueError(f"unknown mode {mode!r} (bf16 | exact)")
 
-    def topk(self, q: torch.Tensor, k: int, mode: str = "bf16") -> Tuple[torch.Tensor, torch.Tensor]:
-        """scores [nq, k] float32 and ids [nq, k] int64 on the device, sorted by (score desc, id asc)."""
+    def topk(self, q: torch.Tensor, k: int, mode: str = "bf16",
+             out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """scores [nq, k] float32 and ids [nq, k] int64 on the device, sorted by (score desc, id asc).
+        ``out``: preallocated contiguous (scores, ids) to write into (e.g. views of one exchange buffer)."""
         _require_cuda(q, "q")
         if q.dim() != 2 or q.shape[1] != self.dim or q.dtype != self.dtype:
             raise ValueError(f"q must be [nq, {self.dim}] {self.dtype}")
         nq = int(q.shape[0])
-        scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
-        ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        if out is not None:
+            scores, ids = out
+            _require_cuda(scores, "out scores")
+            _require_cuda(ids, "out ids")
+            if scores.dtype != torch.float32 or ids.dtype != torch.int64 or scores.numel() != nq * k or ids.numel() != nq * k:
+                raise ValueError("out must be (float32, int64) tensors of nq * k elements")
+        else:
+            scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+            ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
             check(self.lib.ahr_topk(self._h, q.data_ptr(), nq, int(k), self._mode(mode), scores.data_ptr(),
                                     ids.data_ptr(), _stream_ptr(self.device)), "ahr_topk")
@@ -147,6 +156,21 @@ def merge_topk(scores: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, t
     with torch.cuda.device(scores.device):
         check(lib.ahr_merge_topk(scores.device.index or 0, scores.data_ptr(), ids.data_ptr(), parts, nq, k,
                                  out_s.data_ptr(), out_i.data_ptr(), _stream_ptr(scores.device)), "ahr_merge_topk")
+    return out_s, out_i
+
+
+def merge_topk_packed(packed: torch.Tensor, parts: int, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge straight out of the all-gathered exchange buffer: ``parts`` records of [nq*k fp32 | nq*k int64]."""
+    _require_cuda(packed, "packed")
+    if packed.dtype != torch.uint8 or packed.numel() % parts:
+        raise ValueError("packed must be a uint8 buffer of parts equal records")
+    lib = _lib.load()
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=packed.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=packed.device)
+    with torch.cuda.device(packed.device):
+        check(lib.ahr_merge_topk_packed(packed.device.index or 0, packed.data_ptr(), packed.numel() // parts, parts, nq, k,
+                                        out_s.data_ptr(), out_i.data_ptr(), _stream_ptr(packed.device)),
+              "ahr_merge_topk_packed")
     return out_s, out_i
 
 

@@ -112,6 +112,12 @@ int ahr_topk_host(ahr_index *idx, const void *host_q, int32_t nq, int32_t k, int
 int ahr_merge_topk(int device, const float *dev_scores, const int64_t *dev_ids, int32_t parts, int32_t nq,
                    int32_t k, float *dev_out_scores, int64_t *dev_out_ids, void *stream);
 
+/* Same merge over the PACKED exchange buffer of the sharded path: `parts` consecutive records of
+ * record_bytes each, a record = [nq*k fp32 scores][nq*k int64 ids] exactly as one rank contributes it to the
+ * all-gather (record_bytes >= nq*k*12, nq*k*4 must be a multiple of 8).  Avoids re-packing copies. */
+int ahr_merge_topk_packed(int device, const void *dev_packed, int64_t record_bytes, int32_t parts, int32_t nq,
+                          int32_t k, float *dev_out_scores, int64_t *dev_out_ids, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Knowledge-graph CSR.  Replaces the NetworkX adjacency reads of
  *   src/ah_rag/graph/hierarchical_graph.py:441-462 (_neighbors_by_edge_type, get_belongs_to,

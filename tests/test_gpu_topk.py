@@ -147,3 +147,24 @@ def test_round4_device_matches_cpython(engine):
     got = engine.round4_device(torch.tensor(xs, dtype=torch.float64).cuda()).cpu().numpy()
     want = np.array([round(x, 4) for x in xs])
     assert np.array_equal(got, want)
+
+
+def test_packed_merge_equals_plain_merge(engine):
+    """The exchange-buffer fast path of the sharded index (no re-pack copies) == the [parts, nq, k] merge."""
+    n, dim, nq, k = 6000, 64, 32, 50
+    X, Q = _bf16(synth.unit_rows(n, dim, 31, clustered=4)), _bf16(synth.unit_rows(nq, dim, 32, clustered=4))
+    shards = 4
+    bounds = [n * g // shards for g in range(shards + 1)]
+    rec = nq * k * 12
+    packed = torch.empty(shards * rec, dtype=torch.uint8, device="cuda")
+    parts = []
+    for g in range(shards):
+        mine = packed[g * rec:(g + 1) * rec]
+        out = (mine[: nq * k * 4].view(torch.float32).view(nq, k), mine[nq * k * 4:].view(torch.int64).view(nq, k))
+        idx = engine.VectorIndex(X[bounds[g]:bounds[g + 1]].contiguous(), id_base=bounds[g])
+        parts.append(idx.topk(Q, k, mode="exact", out=out))
+    ps, pi = engine.merge_topk_packed(packed, shards, nq, k)
+    ms, mi = engine.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert torch.equal(ps, ms) and torch.equal(pi, mi)
+    fs, fi = engine.VectorIndex(X).topk(Q, k, mode="exact")
+    assert torch.equal(pi, fi) and torch.equal(ps, fs)
