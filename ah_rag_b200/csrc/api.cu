@@ -216,8 +216,9 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
     }
     if (n_lead)
       fprintf(stderr, "[ahr tc stats] leaders=%d avg cycles: total=%.0f mma_wait_full=%.0f mma_wait_tempty=%.0f | "
-              "per CTA: producer_wait_empty=%.0f epi_wait_tfull=%.0f epi_slow_chunks=%.0f\n", n_lead, total / n_lead,
-              sum[1] / n_lead, sum[2] / n_lead, sum[0] / idx->sm_count, sum[4] / idx->sm_count, sum[5] / idx->sm_count);
+              "per CTA: producer_wait_empty=%.0f epi_wait_tfull=%.0f epi_slow_chunks=%.0f epi_wait_tmem_ld=%.0f\n", n_lead,
+              total / n_lead, sum[1] / n_lead, sum[2] / n_lead, sum[0] / idx->sm_count, sum[4] / idx->sm_count,
+              sum[5] / idx->sm_count, sum[6] / idx->sm_count);
   }
   return select_topk(ps, pi, nullptr, (int64_t)S * k, (int64_t)S * k, nq, k, idx->id_base, false, out_scores, out_ids, st);
 }
@@ -234,7 +235,7 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   if (mode == AHR_MODE_BF16) {
-    AHR_REQUIRE(k <= 128, "AHR_MODE_BF16 supports k <= 128 (got %d); use AHR_MODE_EXACT", k);
+    AHR_REQUIRE(k <= 120, "AHR_MODE_BF16 supports k <= 120 (got %d); use AHR_MODE_EXACT", k);
     if (idx->n_rows == 0) return select_topk(dev_scores, nullptr, nullptr, 0, 0, nq, k, 0, false, dev_scores, dev_ids, st);
     return tc_topk(idx, dev_q, nq, k, dev_scores, dev_ids, nullptr, st);
   }
@@ -248,7 +249,7 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
     idx->n_fallback = nq;
     return exact_bruteforce(idx, dev_q, nullptr, nq, k, dev_scores, dev_ids, idx->ws, st);
   }
-  const int32_t kc = k <= 40 ? 64 : 128;  // candidates per query: k plus slack for the tensor-core rounding error
+  const int32_t kc = k <= 40 ? 56 : 112;  // candidates per query: k plus slack for the tensor-core rounding error
   // scratch: cand scores/ids [nq,kc], exact scores [nq,kc], eps [nq], flags [nq], list [nq], count
   const size_t nc = (size_t)nq * kc;
   size_t off = 0;

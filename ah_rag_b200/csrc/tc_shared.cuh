@@ -48,17 +48,21 @@ __device__ __forceinline__ void slab_range(const TcParams &p, int slab, int64_t 
 // ---------------------------------------------------------------------------------------------
 // Per-row candidate lists of the epilogue.
 //
-// One list per query row (= TMEM lane = epilogue thread), KLIST 64-bit keys, UNSORTED, row-major in shared
-// memory (keys[row][KLIST]); the owning thread keeps the smallest kept score `thr` and its slot in registers.
+// One list per query row (= TMEM lane = epilogue thread): KLIST 64-bit keys, row-major in shared memory
+// (keys[row][KLIST]); the owning thread keeps in registers the admission threshold `thr` and the fill count `cnt`.
 //   key = orderable(score) << 32 | ~row_id      (orderable: monotone uint32 image of the float)
-// so the minimum key is the lowest score and, among equal scores, the LARGEST row id -- the entry to evict
-// (lower ids survive ties).  Empty slots hold key(-inf, id -1), the smallest key of all.
-// The scan of the accumulator is per thread (one max per column, one compare per 32 columns); an actual
-// insertion is WARP-COOPERATIVE: the 32 lanes load the row's keys (2 each), min-reduce with shuffles and hand
-// the new minimum back to the owner.  The first version inserted per thread (sorted shift, later replace-min):
-// with ~4 insertions per tile per warp, each running alone on 1 of 32 lanes through generic-space loads, the
-// epilogue cost 18-22 k cycles per tile against 8 k for the MMA (profiles/r1_k1_epilogue_history.md).
-// select.cu sorts the flushed lists, so order inside a list is irrelevant.
+// so a larger key is a better candidate and, among equal scores, the LOWER row id is the larger key.
+//
+//   append      per thread, O(1): a column with score > thr is stored at keys[row][cnt++].  Every lane appends to
+//               its own row in the same instruction -- no serialisation, however many rows have candidates.
+//   compaction  when a row reaches KLIST entries the warp sorts that row (bitonic network over 2 keys per lane,
+//               shuffles only), keeps the best k, and the owner's threshold becomes the k-th score.  Amortised over
+//               KLIST - k appends.  The threshold is therefore slightly stale between compactions (admits a few
+//               extra candidates, never drops one).
+//
+// History (profiles/r1_k1_epilogue_history.md): sorted per-thread insertion -> per-thread replace-min -> warp-
+// cooperative replace-min per candidate (each ~65 instructions, serialised over rows: the per-item fill phase cost
+// 0.8x the MMA time on 1.25M-row shards) -> this scheme.  select.cu orders the flushed lists.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t float_orderable(float f) {
   const uint32_t u = __float_as_uint(f);
@@ -79,68 +83,101 @@ __device__ __forceinline__ void sts_u64(uint32_t addr, unsigned long long v) {
   asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
 
-// All 32 lanes call.  Replaces the entry at `slot` of the list at shared address `list_addr` by `newkey` and
-// returns the slot of the new minimum among the first k entries.
+// All 32 lanes call.  Sorts the first `cnt` entries of the list at shared address `list_addr` (best first), pads the
+// rest with the empty key, writes all KLIST slots back.  Returns the score of the k-th entry (-inf if cnt < k).
 template <int KLIST>
-static __device__ __noinline__ int warp_list_replace_min(uint32_t list_addr, int k, unsigned long long newkey, int slot) {
+static __device__ __noinline__ float warp_list_compact(uint32_t list_addr, int cnt, int k) {
+  constexpr int NPL = KLIST / 32;  // keys per lane; element index of register r in lane l is r * 32 + l
   const int lane = threadIdx.x & 31;
-  if (lane == 0) sts_u64(list_addr + slot * 8, newkey);
+  const unsigned long long empty = make_key(-INFINITY, -1);
+  unsigned long long key[NPL];
   __syncwarp();
-  unsigned long long key[KLIST / 32];
-  unsigned long long m = ~0ull;
 #pragma unroll
-  for (int i = 0; i < KLIST / 32; ++i) {
-    key[i] = (lane + 32 * i < k) ? lds_u64(list_addr + (lane + 32 * i) * 8) : ~0ull;
-    m = key[i] < m ? key[i] : m;
+  for (int r = 0; r < NPL; ++r) key[r] = (r * 32 + lane < cnt) ? lds_u64(list_addr + (r * 32 + lane) * 8) : empty;
+#pragma unroll
+  for (int size = 2; size <= KLIST; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {  // partner lives in another register of the same lane
+        const int rs = stride / 32;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          if ((r & rs) == 0) {
+            const bool desc = (((r * 32 + lane) & size) == 0);  // this block sorts best-first
+            const unsigned long long lo = key[r], hi = key[r ^ rs];
+            const bool swap = desc ? (lo < hi) : (lo > hi);
+            key[r] = swap ? hi : lo;
+            key[r ^ rs] = swap ? lo : hi;
+          }
+        }
+      } else {  // partner lives in lane ^ stride, same register
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key[r], stride);
+          const bool lower = (lane & stride) == 0;
+          const bool desc = (((r * 32 + lane) & size) == 0);
+          const bool keep_max = lower == desc;  // in a best-first block the lower index keeps the larger key
+          const unsigned long long mx = key[r] > other ? key[r] : other;
+          const unsigned long long mn = key[r] > other ? other : key[r];
+          key[r] = keep_max ? mx : mn;
+        }
+      }
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
-    m = other < m ? other : m;
-  }
-  int found = -1;
+  for (int r = 0; r < NPL; ++r) sts_u64(list_addr + (r * 32 + lane) * 8, key[r]);
+  unsigned long long kth = empty;
 #pragma unroll
-  for (int i = KLIST / 32 - 1; i >= 0; --i) {
-    const unsigned hit = __ballot_sync(0xffffffffu, key[i] == m);
-    if (hit) found = 32 * i + (__ffs(hit) - 1);
+  for (int r = 0; r < NPL; ++r) {
+    const unsigned long long c = __shfl_sync(0xffffffffu, key[r], (k - 1) & 31);
+    if (((k - 1) >> 5) == r) kth = c;
   }
-  return found;
+  __syncwarp();
+  return cnt >= k ? orderable_float((uint32_t)(kth >> 32)) : -INFINITY;
 }
 
 // Slow path of the scan, ONE copy in the binary (the unrolled scan must stay small: the first fused epilogue was
-// ~9000 straight-line instructions per tile and ran 80 % stalled on instruction fetch).  Called by all 32 lanes
-// when some lane saw a column above its threshold.  v[32] = this lane's scores of the chunk (local memory: the
-// column to insert is only known at run time), n_valid = columns of the chunk that exist in the corpus.
-// Per row, candidates are taken in ascending column order, so equal scores keep the lower row id.
+// ~9000 straight-line instructions per tile and ran 80 % stalled on instruction fetch).  Called by all 32 lanes when
+// some lane saw a column above its threshold.  v[32] = this lane's scores of the chunk, n_valid = columns of the
+// chunk that exist in the corpus (TMA zero-fills rows past the end).  Columns are taken in ascending order, so equal
+// scores keep the lower row id.
 template <int KLIST>
-static __device__ __noinline__ void epilogue_insert_chunk(const float *v, int n_valid, bool row_valid, int k, int32_t id0,
-                                                          uint32_t lists_warp, float &thr, int &slot) {
+static __device__ __noinline__ void epilogue_append_chunk(const float *v, int n_valid, bool row_valid, int k, int32_t id0,
+                                                          uint32_t lists_warp, float &thr_ref, int &cnt_ref) {
   const int lane = threadIdx.x & 31;
+  const uint32_t my_list = lists_warp + (uint32_t)lane * (KLIST * 8);
+  float thr = thr_ref;
+  int cnt = cnt_ref;
+  // candidate columns of this lane: 32 independent loads + compares (no cross-iteration latency chain)
   unsigned bits = 0;
-  if (row_valid) {
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) bits |= (v[j] > thr ? 1u : 0u) << j;
-    if (n_valid < 32) bits &= (1u << n_valid) - 1u;  // TMA zero-filled rows past the end are not candidates
-  }
-  for (;;) {
-    const unsigned lanes = __ballot_sync(0xffffffffu, bits != 0);
-    if (!lanes) break;
-    const int owner = __ffs(lanes) - 1;
-    const int j_own = __ffs(bits) - 1;  // lowest pending column of this lane (meaningful in the owner)
-    const int j = __shfl_sync(0xffffffffu, j_own, owner);
-    const float s = __shfl_sync(0xffffffffu, v[j & 31], owner);
-    const float thr_o = __shfl_sync(0xffffffffu, thr, owner);
-    if (lane == owner) bits &= bits - 1;
-    if (!(s > thr_o)) continue;  // the owner's threshold rose since the bit was set
-    const int slot_o = __shfl_sync(0xffffffffu, slot, owner);
-    const uint32_t list = lists_warp + (uint32_t)owner * (KLIST * 8);
-    const int new_slot = warp_list_replace_min<KLIST>(list, k, make_key(s, id0 + j), slot_o);
-    const unsigned long long new_min = lds_u64(list + new_slot * 8);  // same address in every lane: broadcast
-    if (lane == owner) {
-      slot = new_slot;
-      thr = orderable_float((uint32_t)(new_min >> 32));
+#pragma unroll
+  for (int j = 0; j < 32; ++j) bits |= (v[j] > thr ? 1u : 0u) << j;
+  if (n_valid < 32) bits &= (1u << n_valid) - 1u;  // TMA zero-filled rows past the end are not candidates
+  if (!row_valid) bits = 0;
+  // every lane appends its own lowest pending column per round; rounds = max candidates of any row (usually 1-2)
+  while (__any_sync(0xffffffffu, bits != 0)) {
+    if (bits) {
+      const int j = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const float s = v[j];
+      if (s > thr) {  // re-check: a compaction may have raised the threshold since the mask was built
+        sts_u64(my_list + cnt * 8, make_key(s, id0 + j));
+        ++cnt;
+      }
+    }
+    unsigned full = __ballot_sync(0xffffffffu, cnt == KLIST);
+    while (full) {  // rare: a row's buffer is full -> the warp compacts it
+      const int owner = __ffs(full) - 1;
+      full &= full - 1;
+      const float kth = warp_list_compact<KLIST>(lists_warp + (uint32_t)owner * (KLIST * 8), KLIST, k);
+      if (lane == owner) {
+        cnt = k;
+        thr = kth;
+      }
     }
   }
+  thr_ref = thr;
+  cnt_ref = cnt;
 }
 
 // Scan one accumulator tile (BN fp32 columns of this thread's TMEM lane) against the row's threshold.
@@ -151,14 +188,21 @@ static __device__ __noinline__ void epilogue_insert_chunk(const float *v, int n_
 template <int KLIST, int BN, bool DBG, typename Release>
 __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bool row_valid, int k, int64_t col0,
                                                    int64_t q_global, const TcParams &p, uint32_t lists_warp, float &thr,
-                                                   int &slot, unsigned long long *n_slow, Release release) {
+                                                   int &cnt, unsigned long long *n_slow, Release release) {
   uint32_t va[32], vb[32];
   tmem_ld_32x32b_x32(t_acc, va);
   auto scan = [&](uint32_t(&v)[32], int c) {
     if (c >= ncols) return;  // warp-uniform: ragged last corpus tile
-    float m = __uint_as_float(v[0]);
+    // four independent max chains (ILP: a single warp per scheduler is latency-bound on dependent chains)
+    float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
-    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+    for (int j = 4; j < 32; j += 4) {
+      m0 = fmaxf(m0, __uint_as_float(v[j]));
+      m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+      m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+      m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+    }
+    const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     if (DBG || __any_sync(0xffffffffu, row_valid && m > thr)) {
       float vl[32];
 #pragma unroll
@@ -167,15 +211,27 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bo
       if (DBG && row_valid)
         for (int j = 0; j < n_valid; ++j) p.dbg_scores[q_global * p.n_rows + col0 + c + j] = vl[j];
       if (n_slow) ++*n_slow;
-      epilogue_insert_chunk<KLIST>(vl, n_valid, row_valid, k, (int32_t)(col0 + c), lists_warp, thr, slot);
+      epilogue_append_chunk<KLIST>(vl, n_valid, row_valid, k, (int32_t)(col0 + c), lists_warp, thr, cnt);
     }
   };
 #pragma unroll 1
   for (int c = 0; c < BN; c += 64) {  // two chunks per iteration: the register buffers alternate statically
-    tmem_ld_wait();
+    if (n_slow) {  // instrumentation (AHR_TC_STATS): cycles this thread spends waiting for TMEM loads
+      const long long t0 = clock64();
+      tmem_ld_wait();
+      n_slow[1] += (unsigned long long)(clock64() - t0);
+    } else {
+      tmem_ld_wait();
+    }
     tmem_ld_32x32b_x32(t_acc + (uint32_t)(c + 32), vb);
     scan(va, c);
-    tmem_ld_wait();
+    if (n_slow) {
+      const long long t0 = clock64();
+      tmem_ld_wait();
+      n_slow[1] += (unsigned long long)(clock64() - t0);
+    } else {
+      tmem_ld_wait();
+    }
     if (c + 64 < BN) {
       tmem_ld_32x32b_x32(t_acc + (uint32_t)(c + 64), va);
     } else {
@@ -185,30 +241,26 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bo
   }
 }
 
-// 32 lists of a warp <- empty
+// Final compaction of the warp's 32 lists and flush to part[q][slab][k] (sorted best first, padded with empties;
+// coalesced: the warp walks one row's list at a time).
 template <int KLIST>
-__device__ __forceinline__ void lists_reset(uint32_t lists_warp) {
+__device__ __forceinline__ void lists_flush(uint32_t lists_warp, int k, int cnt, int64_t q_first, const TcParams &p,
+                                            int slab) {
   const int lane = threadIdx.x & 31;
-  const unsigned long long empty = make_key(-INFINITY, -1);
-  for (int i = lane; i < 32 * KLIST; i += 32) sts_u64(lists_warp + i * 8, empty);
-  __syncwarp();
-}
-
-// 32 lists of a warp -> part[q][slab][k] (coalesced: the warp walks one row's list at a time)
-template <int KLIST>
-__device__ __forceinline__ void lists_flush(uint32_t lists_warp, int k, int64_t q_first, const TcParams &p, int slab) {
-  const int lane = threadIdx.x & 31;
-  __syncwarp();
   for (int r = 0; r < 32; ++r) {
     const int64_t q = q_first + r;
-    if (q >= p.nq) break;
+    if (q >= p.nq) break;  // warp-uniform
+    const int cnt_r = __shfl_sync(0xffffffffu, cnt, r);
+    const uint32_t list = lists_warp + (uint32_t)r * (KLIST * 8);
+    warp_list_compact<KLIST>(list, cnt_r, k);
     const int64_t base = (q * p.n_slabs + slab) * k;
     for (int j = lane; j < k; j += 32) {
-      const unsigned long long key = lds_u64(lists_warp + (uint32_t)(r * KLIST + j) * 8);
+      const unsigned long long key = lds_u64(list + j * 8);
       p.part_scores[base + j] = orderable_float((uint32_t)(key >> 32));
       p.part_ids[base + j] = (int32_t)(~(uint32_t)key);
     }
   }
+  __syncwarp();
 }
 
 }  // namespace ahr

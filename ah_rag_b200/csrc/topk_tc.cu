@@ -145,9 +145,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const int64_t q_first = (int64_t)qt * TC_BM + quad * 32;
       const int64_t q_global = q_first + lane;
       const bool row_valid = q_global < p.nq;
-      lists_reset<KLIST>(lists_warp);
-      float thr = -INFINITY;
-      int slot = 0;
+      float thr = -INFINITY;  // admission threshold of this thread's row
+      int cnt = 0;            // entries in this thread's list
       for (int64_t ct = t0; ct < t1; ++ct) {
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
@@ -155,14 +154,14 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int ncols = (int)min((int64_t)TC_BN, p.n_rows - col0);
         uint64_t *release_bar = &tempty[acc];
         epilogue_scan_tile<KLIST, TC_BN, DBG>(t_lane + (uint32_t)(acc * TC_BN), ncols, row_valid, k, col0, q_global, p,
-                                              lists_warp, thr, slot, nullptr, [&]() {
+                                              lists_warp, thr, cnt, nullptr, [&]() {
                                                 tc_fence_before();
                                                 __syncwarp();
                                                 if (lane == 0) mbar_arrive(release_bar);
                                               });
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      lists_flush<KLIST>(lists_warp, k, q_first, p, slab);
+      lists_flush<KLIST>(lists_warp, k, cnt, q_first, p, slab);
     }
   }
 
@@ -261,7 +260,7 @@ static int tc_launch_t(const CUtensorMap &map_q, const CUtensorMap &map_x, const
 int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows, int32_t dim, int32_t nq, int32_t k,
                      int32_t n_slabs, int grid, float *part_scores, int32_t *part_ids, float *dbg_scores,
                      cudaStream_t stream) {
-  AHR_REQUIRE(k >= 1 && k <= 128, "tensor-core top-k supports 1 <= k <= 128 (got %d)", k);
+  AHR_REQUIRE(k >= 1 && k <= 120, "tensor-core top-k supports 1 <= k <= 120 (got %d)", k);
   AHR_REQUIRE(dim % 8 == 0, "bf16 index needs dim %% 8 == 0 for TMA (got %d)", dim);
   AHR_REQUIRE(n_rows < (int64_t)INT32_MAX - TC_BN, "rows per index shard must fit int32 (got %lld)", (long long)n_rows);
   CUtensorMap map_q;
@@ -282,10 +281,11 @@ int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows
   const int items = p.n_slabs * p.n_qtiles;
   if (grid > items) grid = items;
   if (dbg_scores) {
-    AHR_REQUIRE(k <= 64, "debug score dump supports k <= 64");
+    AHR_REQUIRE(k <= 56, "debug score dump supports k <= 56");
     return tc_launch_t<64, 3, true>(map_q, map_x, p, grid, stream);
   }
-  if (k <= 64) return tc_launch_t<64, 3, false>(map_q, map_x, p, grid, stream);
+  if (k <= 56) return  // the list needs room beyond k: KLIST - k appends amortise one compaction
+    tc_launch_t<64, 3, false>(map_q, map_x, p, grid, stream);
   return tc_launch_t<128, 2, false>(map_q, map_x, p, grid, stream);
 }
 

@@ -157,8 +157,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int k = p.k;
     int acc = 0;
     uint32_t acc_phase = 0;
-    unsigned long long w_tfull = 0, n_slow = 0;
-    unsigned long long *acct = (p.stats && threadIdx.x == 64) ? &w_tfull : nullptr;
+    unsigned long long w_tfull = 0, n_slow[2] = {0, 0};
+    unsigned long long *acct = p.stats ? &w_tfull : nullptr;  // warp-uniform (tcgen05.wait::ld is .aligned); thread 64 reports
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int slab = item / p.n_qtiles, qt = item % p.n_qtiles;
       int64_t t0, t1;
@@ -166,9 +166,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int64_t q_first = (int64_t)qt * (2 * T2_BM) + (int64_t)rank * T2_BM + quad * 32;
       const int64_t q_global = q_first + lane;
       const bool row_valid = q_global < p.nq;
-      lists_reset<KLIST>(lists_warp);
-      float thr = -INFINITY;
-      int slot = 0;
+      float thr = -INFINITY;  // admission threshold of this thread's row
+      int cnt = 0;            // entries in this thread's list
       for (int64_t ct = t0; ct < t1; ++ct) {
         mbar_wait_acct(&tfull[acc], acc_phase, acct);
         tc_fence_after();
@@ -176,18 +175,19 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int ncols = (int)min((int64_t)T2_BN, p.n_rows - col0);
         const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[acc]), 0);
         epilogue_scan_tile<KLIST, T2_BN, DBG>(t_lane + (uint32_t)(acc * T2_BN), ncols, row_valid, k, col0, q_global, p,
-                                              lists_warp, thr, slot, acct ? &n_slow : nullptr, [&]() {
+                                              lists_warp, thr, cnt, p.stats ? n_slow : nullptr, [&]() {  // uniform: every lane counts
                                                 tc_fence_before();
                                                 __syncwarp();
                                                 if (lane == 0) mbar_arrive_cluster(tempty_leader);  // leader's barrier
                                               });
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      lists_flush<KLIST>(lists_warp, k, q_first, p, slab);
+      lists_flush<KLIST>(lists_warp, k, cnt, q_first, p, slab);
     }
-    if (acct) {
+    if (acct && threadIdx.x == 64) {
       p.stats[blockIdx.x * 8 + 4] = w_tfull;
-      p.stats[blockIdx.x * 8 + 5] = n_slow;
+      p.stats[blockIdx.x * 8 + 5] = n_slow[0];
+      p.stats[blockIdx.x * 8 + 6] = n_slow[1];
     }
   }
 
@@ -233,7 +233,7 @@ static int tc2_launch_t(const CUtensorMap &map_q, const CUtensorMap &map_x, cons
 int tc2_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows, int32_t dim, int32_t nq, int32_t k,
                       int32_t n_slabs, int n_pairs, int prefetch_tiles, float *part_scores, int32_t *part_ids,
                       float *dbg_scores, unsigned long long *stats, cudaStream_t stream) {
-  AHR_REQUIRE(k >= 1 && k <= 128, "tensor-core top-k supports 1 <= k <= 128 (got %d)", k);
+  AHR_REQUIRE(k >= 1 && k <= 120, "tensor-core top-k supports 1 <= k <= 120 (got %d)", k);
   AHR_REQUIRE(dim % 8 == 0, "bf16 index needs dim %% 8 == 0 for TMA (got %d)", dim);
   AHR_REQUIRE(n_rows < (int64_t)INT32_MAX - T2_BN, "rows per index shard must fit int32 (got %lld)", (long long)n_rows);
   CUtensorMap map_q;
@@ -255,10 +255,11 @@ int tc2_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_row
   int n_clusters = n_pairs < items ? n_pairs : items;
   if (n_clusters < 1) n_clusters = 1;
   if (dbg_scores) {
-    AHR_REQUIRE(k <= 64, "debug score dump supports k <= 64");
+    AHR_REQUIRE(k <= 56, "debug score dump supports k <= 56");
     return tc2_launch_t<64, 5, true>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
   }
-  if (k <= 64) return tc2_launch_t<64, 5, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+  if (k <= 56) return  // the list needs room beyond k: KLIST - k appends amortise one compaction
+    tc2_launch_t<64, 5, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
   return tc2_launch_t<128, 3, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
 }
 

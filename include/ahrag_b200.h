@@ -92,7 +92,7 @@ int ahr_index_destroy(ahr_index *idx);
  * dev_q: [nq, dim] in the index dtype.  Outputs [nq, k]: scores = <q, x> (the reference's
  * `semantic` is 1 - fl32(1 - score), :723) and ids, sorted by (score desc, id asc); lists shorter than k
  * (n_rows < k) are padded with (-inf, -1).
- *   AHR_MODE_BF16 : k <= 128.  scores are the tensor-core fp32 accumulations.
+ *   AHR_MODE_BF16 : k <= 120.  scores are the tensor-core fp32 accumulations.
  *   AHR_MODE_EXACT: canonical scores, bit-reproducible; ids bit-identical to the CPU oracle.
  *                   May synchronise the stream internally (certification of the candidate set).
  */
