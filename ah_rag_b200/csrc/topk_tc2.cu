@@ -5,7 +5,7 @@
 // capture of the single-CTA kernel (profiles/r1_k1_v1_1cta_ncu.md) shows a latency-bound pipeline at 16-35 %
 // tensor-pipe activity.  A CTA pair computes one 256 x 256 tile: each CTA stages its own 128 queries (A,
 // 16 KB) and HALF of the 256 corpus rows (B, 16 KB); the tensor core reads both halves of B from the two
-// SMs.  32 KB per stage -> 5 stages in flight and 64 B/clk/SM of L2 traffic.
+// SMs.  32 KB per stage -> 4 stages in flight (128 KB, leaving room for L1) and 64 B/clk/SM of L2 traffic.
 //
 //   pair (cluster of 2 CTAs) : item = (slab, 256-query tile); item -> cluster round-robin, slab-major
 //   CTA r of the pair        : query rows  qt*256 + r*128 .. +128   (its TMEM lanes / its epilogue / its lists)
@@ -256,10 +256,16 @@ int tc2_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_row
   if (n_clusters < 1) n_clusters = 1;
   if (dbg_scores) {
     AHR_REQUIRE(k <= 56, "debug score dump supports k <= 56");
-    return tc2_launch_t<64, 5, true>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+    return tc2_launch_t<64, 4, true>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
   }
-  if (k <= 56) return  // the list needs room beyond k: KLIST - k appends amortise one compaction
-    tc2_launch_t<64, 5, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+  if (k <= 56) {  // the list needs room beyond k: KLIST - k appends amortise one compaction
+    // 4 stages (128 KB) + 64 KB of lists leave ~30 KB of the SM's 228 KB to L1, which is where the slow path's
+    // local-memory chunk copy lives: measured 64.9 ms vs 71.4 ms with 5 stages (L1 ~3 KB) on c3, equal on c4.
+    static const int stages = getenv("AHR_TC_STAGES") ? atoi(getenv("AHR_TC_STAGES")) : 4;  // experiments: 3 | 4 | 5
+    if (stages == 5) return tc2_launch_t<64, 5, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+    if (stages == 3) return tc2_launch_t<64, 3, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+    return tc2_launch_t<64, 4, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+  }
   return tc2_launch_t<128, 3, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
 }
 

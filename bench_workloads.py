@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench_workloads.py -- the BASELINE.json configurations other than the headline (which is bench.py's job).
+
+    python bench_workloads.py [c3x] [c4] [c5] [c2]        (default: all; one GPU; a few minutes)
+
+  c3x  c3 in fp32-EXACT mode: bit-exact ids at tensor-core speed (candidates + canonical rescoring + certification)
+  c4   one shard of the 100M x 768 corpus at 8 GPUs (12.5M rows), 256-query batch: the HBM-bound regime of K1
+  c5   synthetic hierarchical graph, 20M nodes / ~500M edges: anchor expansion + rerank for 1024 environments x 50
+       seeds (hop 1) and one frontier expansion per environment (hop 2), checked on a sample against the array oracle
+  c2   HotpotQA-scale synthetic graph (the shipped graph is empty): fp32 index, all 7405 dev-question-sized batch,
+       exact top-5 + anchor expansion/rerank per query (the naive_rag / semantic_anchor retrieval step)
+
+Each line printed is one JSON object.  Peaks from MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from ah_rag_b200 import engine  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained") or d["bf16_tflops"]), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+def unit_bf16(n, dim, seed, dev, chunk=500_000):
+    out = torch.empty((n, dim), dtype=torch.bfloat16, device=dev)
+    for c0 in range(0, n, chunk):
+        g = torch.Generator(device=dev).manual_seed(seed + c0 // chunk)
+        x = torch.randn((min(chunk, n - c0), dim), generator=g, device=dev)
+        x /= x.norm(dim=1, keepdim=True)
+        out[c0:c0 + x.shape[0]] = x.to(torch.bfloat16)
+    return out
+
+
+def timed(fn, steps=5, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_c3x(dev):
+    n, dim, nq, k = 10_000_000, 1024, 4096, 50
+    X, Q = unit_bf16(n, dim, 1234, dev), unit_bf16(nq, dim, 5678, dev)
+    idx = engine.VectorIndex(X)
+    ms = timed(lambda: idx.topk(Q, k, mode="exact"), steps=3, warmup=2)
+    cert, fb = idx.exact_stats()
+    s, i = idx.topk(Q, k, mode="exact")
+    # spot-check 8 queries bit-exactly against the C oracle (full scan of the 10M rows on the host)
+    from oracle import exact
+    sel = [0, 1, 777, 2048, 4095]
+    bits = lambda t: t.view(torch.int16).cpu().numpy().view(np.uint16)
+    rs, ri = exact.exact_topk(bits(X), bits(Q[sel]), k)
+    ok = bool(np.array_equal(i[sel].cpu().numpy(), ri) and np.array_equal(s[sel].cpu().numpy().view(np.uint32), rs.view(np.uint32)))
+    print(json.dumps({"workload": "c3x: 10M x 1024 bf16, Q=4096, k=50, fp32-exact mode", "ms": ms, "queries_per_s": nq / ms * 1e3,
+                      "certified": cert, "fallback": fb, "bit_exact_vs_oracle_on_sample": ok, "sample_queries": sel}))
+    del idx, X, Q
+
+
+def run_c4(dev):
+    n, dim, nq, k = 12_500_000, 768, 256, 50
+    hbm, tf, src = peaks()
+    X, Q = unit_bf16(n, dim, 1234, dev), unit_bf16(nq, dim, 5678, dev)
+    idx = engine.VectorIndex(X)
+    idx.set_profiling(True)
+    ms = timed(lambda: idx.topk(Q, k, mode="bf16"), steps=10, warmup=3)
+    prof = idx.get_profile()
+    k1 = prof["k1_ms_total"] / max(1, prof["k1_launches"])
+    gbs = 2.0 * n * dim / (k1 * 1e-3) / 1e9
+    tfl = 2.0 * nq * n * dim / (k1 * 1e-3) / 1e12
+    print(json.dumps({"workload": "c4 shard: 12.5M x 768 bf16 (1/8 of 100M), Q=256, k=50, bf16 mode", "ms": ms, "k1_ms": k1,
+                      "queries_per_s_per_gpu": nq / ms * 1e3, "n_slabs": prof["n_slabs"],
+                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                   "tensor_tflops": tfl, "tensor_frac": tfl / tf, "peak_source": src,
+                                   "t_mem_ms": 2.0 * n * dim / (hbm * 1e9) * 1e3,
+                                   "t_mma_ms": 2.0 * nq * n * dim / (tf * 1e12) * 1e3}}))
+    del idx, X, Q
+
+
+def make_c5_graph(dev, scale=1.0, seed=42):
+    """CSR arrays on the device: [entities | L1 | L2 | hyperedges]; ~25 directed edges per node at scale 1."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    n_ent, n_l1, n_l2, n_h = int(16_000_000 * scale), int(1_800_000 * scale), int(200_000 * scale), int(2_000_000 * scale)
+    e0, s1, s2, h0 = 0, n_ent, n_ent + n_l1, n_ent + n_l1 + n_l2
+    n = h0 + n_h
+    rel_deg = 260  # ~468M related_to + ~33M belongs_to/participates_in edges = ~500M edges (1.0e9 CSR entries)
+
+    def csr_from_counts(counts_by_node, cols):
+        rp = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        rp[1:] = torch.cumsum(counts_by_node, 0)
+        return rp, cols.to(torch.int32)
+
+    def transpose(src, dst):
+        """edges src->dst (link order = src-major) -> CSR keyed by dst, neighbours in link order (stable)."""
+        order = torch.sort(dst, stable=True).indices
+        counts = torch.bincount(dst, minlength=n)
+        return csr_from_counts(counts, src[order])
+
+    zeros = torch.zeros(n, dtype=torch.int64, device=dev)
+    # belongs_to: entity -> 1..2 L1 parents ; L1 -> one L2
+    cnt_e = torch.randint(1, 3, (n_ent,), generator=g, device=dev)
+    src_b = torch.repeat_interleave(torch.arange(n_ent, device=dev), cnt_e)
+    dst_b = s1 + torch.randint(0, n_l1, (src_b.numel(),), generator=g, device=dev)
+    src_b2 = s1 + torch.arange(n_l1, device=dev)
+    dst_b2 = s2 + torch.randint(0, n_l2, (n_l1,), generator=g, device=dev)
+    cb = zeros.clone(); cb[:n_ent] = cnt_e; cb[s1:s2] = 1
+    bel_out = csr_from_counts(cb, torch.cat([dst_b, dst_b2]))
+    bel_in = transpose(torch.cat([src_b, src_b2]), torch.cat([dst_b, dst_b2]))
+    # participates_in: hyperedge h has 2..5 entity participants (in-CSR built directly), out-CSR by transpose
+    ar = torch.randint(2, 6, (n_h,), generator=g, device=dev)
+    hs = h0 + torch.repeat_interleave(torch.arange(n_h, device=dev), ar)
+    es = torch.randint(0, n_ent, (hs.numel(),), generator=g, device=dev)
+    cp = zeros.clone(); cp[h0:] = ar
+    part_in = csr_from_counts(cp, es)
+    part_out = transpose(hs, es)  # keyed by entity, values = hyperedges
+    # related_to among L1 summaries: rel_deg out-neighbours each
+    src_r = s1 + torch.repeat_interleave(torch.arange(n_l1, device=dev), rel_deg)
+    dst_r = s1 + torch.randint(0, n_l1, (src_r.numel(),), generator=g, device=dev)
+    cr = zeros.clone(); cr[s1:s2] = rel_deg
+    rel_out = csr_from_counts(cr, dst_r)
+    rel_in = transpose(src_r, dst_r)
+    node_type = torch.zeros(n, dtype=torch.uint8, device=dev)
+    node_type[s1:h0] = 1
+    node_type[h0:] = 2
+    level = torch.zeros(n, dtype=torch.uint8, device=dev)
+    level[s2:h0] = 2
+    judge = torch.full((n,), float("nan"), dtype=torch.float64, device=dev)
+    conf = torch.full((n,), float("nan"), dtype=torch.float64, device=dev)
+    ns = n_l1 + n_l2
+    judge[s1:h0] = torch.round(torch.rand(ns, generator=g, device=dev, dtype=torch.float64) * 100) / 10
+    conf[s1:h0] = torch.round(torch.rand(ns, generator=g, device=dev, dtype=torch.float64) * 1000) / 100
+    jt = torch.zeros(n, dtype=torch.float64, device=dev)
+    # judge_term evaluated by the HOST with numpy's scalar exp, as the reference does (hierarchical_graph.py:766)
+    jh = judge[s1:h0].cpu().numpy()
+    jt[s1:h0] = torch.from_numpy(np.array([1.0 / (1.0 + np.exp(-((float(x) or 0.0) / 10.0))) for x in jh])).to(dev)
+    slots = [part_out, part_in, bel_out, bel_in, rel_out, rel_in]
+    n_edges = int(bel_out[1].numel() + part_in[1].numel() + rel_out[1].numel())
+    return {"n_nodes": n, "row_ptr": [s[0] for s in slots], "col_idx": [s[1] for s in slots], "node_type": node_type,
+            "level": level, "judge": judge, "judge_term": jt, "conf": conf, "n_edges": n_edges,
+            "ranges": {"entity": (e0, s1), "l1": (s1, s2), "l2": (s2, h0), "hyperedge": (h0, n)}}
+
+
+class DeviceGraph(engine.GraphCSR):
+    """GraphCSR over tensors that already live on the device (no host round trip for the 5 GB CSR)."""
+
+    def __init__(self, a, dev):
+        import ctypes
+        from ah_rag_b200 import _lib
+        self.lib = _lib.load()
+        self.device = dev
+        self.n_nodes = int(a["n_nodes"])
+        self.row_ptr, self.col_idx = a["row_ptr"], a["col_idx"]
+        self.node_type, self.level, self.judge, self.judge_term, self.conf = (a["node_type"], a["level"], a["judge"],
+                                                                             a["judge_term"], a["conf"])
+        rp = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in self.row_ptr])
+        ci = (ctypes.c_void_p * 6)(*[t.data_ptr() if t.numel() else None for t in self.col_idx])
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.ahr_graph_create(ctypes.byref(self._h), dev.index or 0, self.n_nodes, rp, ci,
+                                             self.node_type.data_ptr(), self.level.data_ptr(), self.judge.data_ptr(),
+                                             self.judge_term.data_ptr(), self.conf.data_ptr()), "ahr_graph_create")
+
+
+def run_c5(dev, scale=1.0):
+    from oracle import array_graph
+    hbm, _, src = peaks()
+    t0 = time.time()
+    a = make_c5_graph(dev, scale)
+    torch.cuda.synchronize()
+    g = DeviceGraph(a, dev)
+    n = a["n_nodes"]
+    n_env, n_seeds, top_k, m, limit = 1024, 50, 50, 5, 10
+    gen = torch.Generator(device=dev).manual_seed(7)
+    e_lo, e_hi = a["ranges"]["entity"]
+    l_lo, l_hi = a["ranges"]["l1"]
+    # seeds: 80 % entities, 20 % L1 summaries (the index holds entities + summaries), distinct per env, scores descending
+    seeds = torch.where(torch.rand((n_env, n_seeds), generator=gen, device=dev) < 0.8,
+                        torch.randint(e_lo, e_hi, (n_env, n_seeds), generator=gen, device=dev),
+                        torch.randint(l_lo, l_hi, (n_env, n_seeds), generator=gen, device=dev)).to(torch.int32)
+    scores = torch.sort(torch.rand((n_env, n_seeds), generator=gen, device=dev) * 0.9 + 0.05, dim=1, descending=True).values
+    scores = scores.to(torch.float32).contiguous()
+    prm = engine.SearchParams(member_top_m=m)
+    out = g.anchor_rerank(seeds, scores, prm, top_k)
+    ms_anchor = timed(lambda: g.anchor_rerank(seeds, scores, prm, top_k, want_cluster=False), steps=20)
+    # hop 2: one expand per env on the first ids of the reranked list, ops uniform over {parents, children, related}
+    ops = torch.randint(0, 3, (n_env,), generator=gen, device=dev).to(torch.int32)
+    take = torch.where(ops == 2, 1, 2)
+    sel = out["nodes"][:, :2].contiguous()
+    offs = torch.zeros(n_env + 1, dtype=torch.int32, device=dev)
+    offs[1:] = torch.cumsum(take, 0).to(torch.int32)
+    flat = torch.cat([sel[e, :int(t)] for e, t in enumerate(take.tolist())]).to(torch.int32).contiguous()
+    oi, oc = g.expand(ops, flat, offs, limit)
+    ms_expand = timed(lambda: g.expand(ops, flat, offs, limit), steps=50)
+    # uncapped-ish variant: limit 2048 lets the walk read whole neighbour lists (bandwidth view)
+    oi2, oc2 = g.expand(ops, flat, offs, 2048)
+    ms_expand_big = timed(lambda: g.expand(ops, flat, offs, 2048), steps=20)
+    # parity on a sample of environments against the array oracle (host copy of the CSR)
+    host = {"row_ptr": [t.cpu().numpy() for t in a["row_ptr"]], "col_idx": [t.cpu().numpy() for t in a["col_idx"]],
+            "node_type": a["node_type"].cpu().numpy(), "judge": a["judge"].cpu().numpy(),
+            "judge_term": a["judge_term"].cpu().numpy(), "conf": a["conf"].cpu().numpy()}
+    sample = list(range(0, n_env, 16))
+    outh = {k_: v.cpu().numpy() for k_, v in out.items()}
+    sh, sch = seeds.cpu().numpy(), scores.cpu().numpy()
+    ok_anchor = all(array_graph.anchor_rerank(host, sh[e], sch[e], top_k, m) ==
+                    [(int(outh["nodes"][e, j]), float(outh["semantic"][e, j]), float(outh["score"][e, j]))
+                     for j in range(outh["count"][e])] for e in sample)
+    oih, och, oi2h, oc2h = oi.cpu().numpy(), oc.cpu().numpy(), oi2.cpu().numpy(), oc2.cpu().numpy()
+    offh, flath, opsh = offs.cpu().numpy(), flat.cpu().numpy(), ops.cpu().numpy()
+    ok_expand = all(array_graph.expand(host, int(opsh[e]), flath[offh[e]:offh[e + 1]], limit) == list(oih[e, :och[e]]) and
+                    array_graph.expand(host, int(opsh[e]), flath[offh[e]:offh[e + 1]], 2048) == list(oi2h[e, :oc2h[e]])
+                    for e in sample)
+    emitted = int(oc2.sum().item())
+    print(json.dumps({"workload": f"c5: synthetic hierarchical graph {n} nodes / {a['n_edges']} edges (scale {scale}), 1024 envs x 50 seeds",
+                      "graph_bytes": g.nbytes(), "build_s": round(time.time() - t0, 1),
+                      "hop1_anchor_rerank_ms": ms_anchor, "hop1_envs_per_s": n_env / ms_anchor * 1e3,
+                      "hop2_expand_limit10_ms": ms_expand, "hop2_envs_per_s": n_env / ms_expand * 1e3,
+                      "hop2_expand_limit2048_ms": ms_expand_big, "hop2_nodes_emitted": emitted,
+                      "parity_sample_envs": len(sample), "anchor_rerank_bit_exact": bool(ok_anchor),
+                      "expand_bit_exact": bool(ok_expand), "hbm_peak_gbs": hbm, "peak_source": src}))
+
+
+def run_c2(dev):
+    """HotpotQA-scale substitute: 500k nodes, D=384 fp32 index (entities + summaries), 7405 queries, top_k=5."""
+    a = make_c5_graph(dev, scale=0.025, seed=3)  # 400k entities, 45k L1, 5k L2, 50k hyperedges
+    g = DeviceGraph(a, dev)
+    e_lo, e_hi = a["ranges"]["entity"]
+    s_lo, s_hi = a["ranges"]["l1"][0], a["ranges"]["l2"][1]
+    n_index = s_hi  # entities + all summaries are indexed (hierarchical_graph.py:629-649), rows in node order
+    dim, nq, k = 384, 7405, 5
+    gen = torch.Generator(device=dev).manual_seed(11)
+    X = torch.randn((n_index, dim), generator=gen, device=dev)
+    X /= X.norm(dim=1, keepdim=True)
+    Q = torch.randn((nq, dim), generator=gen, device=dev)
+    Q /= Q.norm(dim=1, keepdim=True)
+    idx = engine.VectorIndex(X.contiguous())
+    prm = engine.SearchParams(member_top_m=5)
+
+    def step():
+        s, i = idx.topk(Q, k, mode="exact")
+        return g.anchor_rerank(i.to(torch.int32), s, prm, k, want_cluster=False)
+
+    ms = timed(step, steps=3, warmup=1)
+    Xb, Qb = X.to(torch.bfloat16).contiguous(), Q.to(torch.bfloat16).contiguous()
+    idxb = engine.VectorIndex(Xb)
+
+    def step_b():
+        s, i = idxb.topk(Qb, k, mode="bf16")
+        return g.anchor_rerank(i.to(torch.int32), s, prm, k, want_cluster=False)
+
+    msb = timed(step_b, steps=10, warmup=3)
+    print(json.dumps({"workload": f"c2 substitute: synthetic graph {a['n_nodes']} nodes, index {n_index} x {dim}, {nq} queries, top_k={k} "
+                                  "(the shipped hotpotqa_distractor graph is empty)",
+                      "fp32_exact_ms": ms, "fp32_exact_queries_per_s": nq / ms * 1e3,
+                      "bf16_ms": msb, "bf16_queries_per_s": nq / msb * 1e3}))
+
+
+def main():
+    assert torch.cuda.is_available(), "no CUDA device: the engine has no CPU fallback"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    which = sys.argv[1:] or ["c3x", "c4", "c5", "c2"]
+    for w in which:
+        if w == "c3x":
+            run_c3x(dev)
+        elif w == "c4":
+            run_c4(dev)
+        elif w == "c5":
+            run_c5(dev, float(os.environ.get("AHR_C5_SCALE", "1.0")))
+        elif w == "c2":
+            run_c2(dev)
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
