@@ -216,9 +216,9 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
     }
     if (n_lead)
       fprintf(stderr, "[ahr tc stats] leaders=%d avg cycles: total=%.0f mma_wait_full=%.0f mma_wait_tempty=%.0f | "
-              "per CTA: producer_wait_empty=%.0f epi_wait_tfull=%.0f epi_slow_chunks=%.0f epi_wait_tmem_ld=%.0f\n", n_lead,
+              "per CTA: producer_wait_empty=%.0f epi_wait_tfull=%.0f epi_slow_chunks=%.0f epi_slow_cycles=%.0f epi_row_compactions=%.0f\n", n_lead,
               total / n_lead, sum[1] / n_lead, sum[2] / n_lead, sum[0] / idx->sm_count, sum[4] / idx->sm_count,
-              sum[5] / idx->sm_count, sum[6] / idx->sm_count);
+              sum[5] / idx->sm_count, sum[6] / idx->sm_count, sum[7] / idx->sm_count);
   }
   return select_topk(ps, pi, nullptr, (int64_t)S * k, (int64_t)S * k, nq, k, idx->id_base, false, out_scores, out_ids, st);
 }

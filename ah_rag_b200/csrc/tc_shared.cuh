@@ -136,37 +136,39 @@ static __device__ __noinline__ float warp_list_compact(uint32_t list_addr, int c
   return cnt >= k ? orderable_float((uint32_t)(kth >> 32)) : -INFINITY;
 }
 
-// Slow path of the scan, ONE copy in the binary (the unrolled scan must stay small: the first fused epilogue was
-// ~9000 straight-line instructions per tile and ran 80 % stalled on instruction fetch).  Called by all 32 lanes when
-// some lane saw a column above its threshold.  v[32] = this lane's scores of the chunk, n_valid = columns of the
-// chunk that exist in the corpus (TMA zero-fills rows past the end).  Columns are taken in ascending order, so equal
-// scores keep the lower row id.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// Rare path, ONE copy in the binary: some lane's list is full (and may still have `pending` candidate columns of
+// the current chunk).  The warp compacts the full rows, their owners re-filter the pending columns against the
+// refreshed threshold and store what still qualifies; repeats until no list is full.
+// scratch_lane: shared address of this lane's column of the warp's chunk scratch (score of column j at + j*128).
 template <int KLIST>
-static __device__ __noinline__ void epilogue_append_chunk(const float *v, int n_valid, bool row_valid, int k, int32_t id0,
-                                                          uint32_t lists_warp, float &thr_ref, int &cnt_ref) {
+static __device__ __noinline__ void epilogue_overflow(uint32_t scratch_lane, unsigned pending, int k, int32_t id0,
+                                                      uint32_t lists_warp, float &thr_ref, int &cnt_ref) {
   const int lane = threadIdx.x & 31;
   const uint32_t my_list = lists_warp + (uint32_t)lane * (KLIST * 8);
   float thr = thr_ref;
   int cnt = cnt_ref;
-  // candidate columns of this lane: 32 independent loads + compares (no cross-iteration latency chain)
-  unsigned bits = 0;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) bits |= (v[j] > thr ? 1u : 0u) << j;
-  if (n_valid < 32) bits &= (1u << n_valid) - 1u;  // TMA zero-filled rows past the end are not candidates
-  if (!row_valid) bits = 0;
-  // every lane appends its own lowest pending column per round; rounds = max candidates of any row (usually 1-2)
-  while (__any_sync(0xffffffffu, bits != 0)) {
-    if (bits) {
-      const int j = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const float s = v[j];
-      if (s > thr) {  // re-check: a compaction may have raised the threshold since the mask was built
+  for (;;) {
+    while (pending != 0 && cnt < KLIST) {  // per lane, ascending column order: store what fits
+      const int j = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const float s = lds_f32(scratch_lane + j * 128);
+      if (s > thr) {  // re-check: a compaction may have raised this row's threshold
         sts_u64(my_list + cnt * 8, make_key(s, id0 + j));
         ++cnt;
       }
     }
     unsigned full = __ballot_sync(0xffffffffu, cnt == KLIST);
-    while (full) {  // rare: a row's buffer is full -> the warp compacts it
+    if (!full) break;  // no full list left, hence nothing pending either
+    while (full) {
       const int owner = __ffs(full) - 1;
       full &= full - 1;
       const float kth = warp_list_compact<KLIST>(lists_warp + (uint32_t)owner * (KLIST * 8), KLIST, k);
@@ -181,19 +183,28 @@ static __device__ __noinline__ void epilogue_append_chunk(const float *v, int n_
 }
 
 // Scan one accumulator tile (BN fp32 columns of this thread's TMEM lane) against the row's threshold.
-//   t_acc      TMEM address of (this warp's lane quadrant, first column of the accumulator stage)
-//   lists_warp shared address of the 32 lists of this warp (row-major, KLIST keys each)
-//   release()  called once every column of the tile is in registers: hands the TMEM stage back to the MMA
-// Fast path per 32 columns: one TMEM load (double buffered), 16 three-input max, one compare, one vote.
+//   t_acc        TMEM address of (this warp's lane quadrant, first column of the accumulator stage)
+//   lists_warp   shared address of the 32 lists of this warp (row-major, KLIST keys each)
+//   scratch_warp shared address of this warp's 4 KB chunk scratch ([32 columns][32 lanes] fp32)
+//   release()    called once every column of the tile is in registers: hands the TMEM stage back to the MMA
+// Per 32 columns: one TMEM load (double buffered), a 4-way max tree, one compare.  A thread whose maximum beats its
+// threshold builds the bitmask of its candidate columns from registers, parks the chunk in the scratch (the column
+// to store is only known at run time; local memory would go to L2 in this kernel, shared memory is 30 cycles) and
+// appends its candidates itself -- no warp cooperation, no function call.  One vote per chunk detects full lists,
+// which take the out-of-line path above.
 template <int KLIST, int BN, bool DBG, typename Release>
 __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bool row_valid, int k, int64_t col0,
-                                                   int64_t q_global, const TcParams &p, uint32_t lists_warp, float &thr,
-                                                   int &cnt, unsigned long long *n_slow, Release release) {
+                                                   int64_t q_global, const TcParams &p, uint32_t lists_warp,
+                                                   uint32_t scratch_warp, float &thr, int &cnt,
+                                                   unsigned long long *n_slow, Release release) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t my_list = lists_warp + (uint32_t)lane * (KLIST * 8);
+  const uint32_t scratch_lane = scratch_warp + (uint32_t)lane * 4;
   uint32_t va[32], vb[32];
   tmem_ld_32x32b_x32(t_acc, va);
   auto scan = [&](uint32_t(&v)[32], int c) {
     if (c >= ncols) return;  // warp-uniform: ragged last corpus tile
-    // four independent max chains (ILP: a single warp per scheduler is latency-bound on dependent chains)
+    // four independent max chains (a single warp per scheduler is latency-bound on dependent chains)
     float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
     for (int j = 4; j < 32; j += 4) {
@@ -203,35 +214,41 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bo
       m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
     }
     const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-    if (DBG || __any_sync(0xffffffffu, row_valid && m > thr)) {
-      float vl[32];
+    unsigned pending = 0;
+    const bool hit = row_valid && m > thr;
+    if (DBG || __any_sync(0xffffffffu, hit)) {
+      if (n_slow) ++n_slow[0];
+      // park the chunk: conflict-free (lane = bank), static register indices
 #pragma unroll
-      for (int j = 0; j < 32; ++j) vl[j] = __uint_as_float(v[j]);
-      const int n_valid = min(32, ncols - c);
+      for (int j = 0; j < 32; ++j) sts_f32(scratch_lane + j * 128, __uint_as_float(v[j]));
+      const int n_valid = min(32, ncols - c);  // TMA zero-filled rows past the end are not candidates
       if (DBG && row_valid)
-        for (int j = 0; j < n_valid; ++j) p.dbg_scores[q_global * p.n_rows + col0 + c + j] = vl[j];
-      if (n_slow) ++*n_slow;
-      epilogue_append_chunk<KLIST>(vl, n_valid, row_valid, k, (int32_t)(col0 + c), lists_warp, thr, cnt);
+        for (int j = 0; j < n_valid; ++j) p.dbg_scores[q_global * p.n_rows + col0 + c + j] = lds_f32(scratch_lane + j * 128);
+      if (hit) {  // divergent: only the threads with a candidate in this chunk
+        unsigned bits = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
+        if (n_valid < 32) bits &= (1u << n_valid) - 1u;
+        const int32_t id0 = (int32_t)(col0 + c);
+        while (bits != 0 && cnt < KLIST) {  // ascending column order: equal scores keep the lower row id
+          const int j = __ffs(bits) - 1;
+          bits &= bits - 1;
+          sts_u64(my_list + cnt * 8, make_key(lds_f32(scratch_lane + j * 128), id0 + j));
+          ++cnt;
+        }
+        pending = bits;
+      }
+      // a full list is compacted right away, even with nothing pending: its threshold is stale
+      if (__any_sync(0xffffffffu, cnt == KLIST))
+        epilogue_overflow<KLIST>(scratch_lane, pending, k, (int32_t)(col0 + c), lists_warp, thr, cnt);
     }
   };
 #pragma unroll 1
   for (int c = 0; c < BN; c += 64) {  // two chunks per iteration: the register buffers alternate statically
-    if (n_slow) {  // instrumentation (AHR_TC_STATS): cycles this thread spends waiting for TMEM loads
-      const long long t0 = clock64();
-      tmem_ld_wait();
-      n_slow[1] += (unsigned long long)(clock64() - t0);
-    } else {
-      tmem_ld_wait();
-    }
+    tmem_ld_wait();
     tmem_ld_32x32b_x32(t_acc + (uint32_t)(c + 32), vb);
     scan(va, c);
-    if (n_slow) {
-      const long long t0 = clock64();
-      tmem_ld_wait();
-      n_slow[1] += (unsigned long long)(clock64() - t0);
-    } else {
-      tmem_ld_wait();
-    }
+    tmem_ld_wait();
     if (c + 64 < BN) {
       tmem_ld_32x32b_x32(t_acc + (uint32_t)(c + 64), va);
     } else {

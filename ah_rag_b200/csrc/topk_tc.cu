@@ -33,7 +33,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *tiles = smem;
   unsigned long long *lists = reinterpret_cast<unsigned long long *>(tiles + TC_STAGES * TC_STAGE_BYTES);  // [128][KLIST] keys
-  uint64_t *bars = reinterpret_cast<uint64_t *>(lists + KLIST * TC_BM);
+  float *scratch = reinterpret_cast<float *>(lists + KLIST * TC_BM);  // [4 warps][32 columns][32 lanes] chunk scratch
+  uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 4 * 32 * 32);
   uint64_t *full = bars;                  // [STAGES] TMA -> MMA
   uint64_t *empty = bars + TC_STAGES;     // [STAGES] MMA -> TMA
   uint64_t *tfull = bars + 2 * TC_STAGES; // [2] MMA -> epilogue
@@ -135,6 +136,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access; thread = query row = TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t lists_warp = smem_u32(lists) + (uint32_t)(quad * 32) * (KLIST * 8);
+    const uint32_t scratch_warp = smem_u32(scratch) + (uint32_t)quad * (32 * 32 * 4);
     const int k = p.k;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -154,7 +156,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int ncols = (int)min((int64_t)TC_BN, p.n_rows - col0);
         uint64_t *release_bar = &tempty[acc];
         epilogue_scan_tile<KLIST, TC_BN, DBG>(t_lane + (uint32_t)(acc * TC_BN), ncols, row_valid, k, col0, q_global, p,
-                                              lists_warp, thr, cnt, nullptr, [&]() {
+                                              lists_warp, scratch_warp, thr, cnt, nullptr, [&]() {
                                                 tc_fence_before();
                                                 __syncwarp();
                                                 if (lane == 0) mbar_arrive(release_bar);
@@ -237,7 +239,7 @@ int tc_choose_slabs(int32_t n_qtiles, int64_t n_ctiles, int grid) {
 
 template <int KLIST, int STAGES>
 static constexpr size_t tc_smem_bytes() {
-  return 1024 + (size_t)STAGES * TC_STAGE_BYTES + (size_t)KLIST * TC_BM * 8 + 128;
+  return 1024 + (size_t)STAGES * TC_STAGE_BYTES + (size_t)KLIST * TC_BM * 8 + 4 * 32 * 32 * 4 + 128;
 }
 
 template <int KLIST, int STAGES, bool DBG>
@@ -284,9 +286,8 @@ int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows
     AHR_REQUIRE(k <= 56, "debug score dump supports k <= 56");
     return tc_launch_t<64, 3, true>(map_q, map_x, p, grid, stream);
   }
-  if (k <= 56) return  // the list needs room beyond k: KLIST - k appends amortise one compaction
-    tc_launch_t<64, 3, false>(map_q, map_x, p, grid, stream);
-  return tc_launch_t<128, 2, false>(map_q, map_x, p, grid, stream);
+  AHR_REQUIRE(k <= 56, "the single-CTA variant (AHR_TC_VARIANT=1) supports k <= 56 (got %d)", k);
+  return tc_launch_t<64, 3, false>(map_q, map_x, p, grid, stream);
 }
 
 }  // namespace ahr

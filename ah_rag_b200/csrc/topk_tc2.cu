@@ -36,7 +36,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *tiles = smem;
   unsigned long long *lists = reinterpret_cast<unsigned long long *>(tiles + STAGES * T2_STAGE_BYTES);  // [128][KLIST] keys
-  uint64_t *bars = reinterpret_cast<uint64_t *>(lists + KLIST * T2_BM);
+  float *scratch = reinterpret_cast<float *>(lists + KLIST * T2_BM);  // [4 warps][32 columns][32 lanes] chunk scratch
+  uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 4 * 32 * 32);
   uint64_t *full = bars;                 // [STAGES] leader's copy is the live one (bytes of both CTAs)
   uint64_t *empty = bars + STAGES;       // [STAGES] per CTA: MMA done reading this stage
   uint64_t *tfull = bars + 2 * STAGES;   // [2] per CTA: accumulator stage complete
@@ -154,10 +155,11 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access; thread = query row = TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t lists_warp = smem_u32(lists) + (uint32_t)(quad * 32) * (KLIST * 8);
+    const uint32_t scratch_warp = smem_u32(scratch) + (uint32_t)quad * (32 * 32 * 4);
     const int k = p.k;
     int acc = 0;
     uint32_t acc_phase = 0;
-    unsigned long long w_tfull = 0, n_slow[2] = {0, 0};
+    unsigned long long w_tfull = 0, n_slow[4] = {0, 0, 0, 0};
     unsigned long long *acct = p.stats ? &w_tfull : nullptr;  // warp-uniform (tcgen05.wait::ld is .aligned); thread 64 reports
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int slab = item / p.n_qtiles, qt = item % p.n_qtiles;
@@ -175,7 +177,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int ncols = (int)min((int64_t)T2_BN, p.n_rows - col0);
         const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[acc]), 0);
         epilogue_scan_tile<KLIST, T2_BN, DBG>(t_lane + (uint32_t)(acc * T2_BN), ncols, row_valid, k, col0, q_global, p,
-                                              lists_warp, thr, cnt, p.stats ? n_slow : nullptr, [&]() {  // uniform: every lane counts
+                                              lists_warp, scratch_warp, thr, cnt, p.stats ? n_slow : nullptr, [&]() {  // uniform: every lane counts
                                                 tc_fence_before();
                                                 __syncwarp();
                                                 if (lane == 0) mbar_arrive_cluster(tempty_leader);  // leader's barrier
@@ -187,7 +189,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (acct && threadIdx.x == 64) {
       p.stats[blockIdx.x * 8 + 4] = w_tfull;
       p.stats[blockIdx.x * 8 + 5] = n_slow[0];
-      p.stats[blockIdx.x * 8 + 6] = n_slow[1];
+      p.stats[blockIdx.x * 8 + 6] = n_slow[2];  // cycles inside the slow path
+      p.stats[blockIdx.x * 8 + 7] = n_slow[3];  // row compactions
     }
   }
 
@@ -210,7 +213,7 @@ int tc2_make_corpus_map(CUtensorMap *map, const void *dev_rows, int64_t n_rows, 
 
 template <int KLIST, int STAGES>
 static constexpr size_t tc2_smem_bytes() {
-  return 1024 + (size_t)STAGES * T2_STAGE_BYTES + (size_t)KLIST * T2_BM * 8 + 256;
+  return 1024 + (size_t)STAGES * T2_STAGE_BYTES + (size_t)KLIST * T2_BM * 8 + 4 * 32 * 32 * 4 + 256;
 }
 
 template <int KLIST, int STAGES, bool DBG>
@@ -261,12 +264,11 @@ int tc2_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_row
   if (k <= 56) {  // the list needs room beyond k: KLIST - k appends amortise one compaction
     // 4 stages (128 KB) + 64 KB of lists leave ~30 KB of the SM's 228 KB to L1, which is where the slow path's
     // local-memory chunk copy lives: measured 64.9 ms vs 71.4 ms with 5 stages (L1 ~3 KB) on c3, equal on c4.
-    static const int stages = getenv("AHR_TC_STAGES") ? atoi(getenv("AHR_TC_STAGES")) : 4;  // experiments: 3 | 4 | 5
-    if (stages == 5) return tc2_launch_t<64, 5, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+    static const int stages = getenv("AHR_TC_STAGES") ? atoi(getenv("AHR_TC_STAGES")) : 4;  // experiments: 3 | 4
     if (stages == 3) return tc2_launch_t<64, 3, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
     return tc2_launch_t<64, 4, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
   }
-  return tc2_launch_t<128, 3, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+  return tc2_launch_t<128, 2, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
 }
 
 }  // namespace ahr
