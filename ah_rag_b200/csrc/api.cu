@@ -62,6 +62,9 @@ struct ahr_index {
   int variant = 2;     // AHR_TC_VARIANT: 2 = CTA pairs (default), 1 = single CTA
   int prefetch_tiles = 0;  // AHR_TC_PREFETCH: L2 prefetch distance in corpus tiles (0 = off, the default: measured slower)
   int force_slabs = 0;     // AHR_TC_SLABS: override the slab heuristic (experiments)
+  DevBuf x_hi, x_lo;   // fp32 index: bf16 hi/lo halves of the rows (library-owned), maps below point at them
+  CUtensorMap map_x2_lo;
+  DevBuf q_split;      // fp32 queries split per call
   bool tc_stats = false;   // AHR_TC_STATS=1: per-role wait-cycle counters of K1, printed to stderr (debug)
   DevBuf stats_buf;
   DevBuf ws;        // partial lists / score chunks
@@ -119,6 +122,17 @@ int ahr_index_create(ahr_index **out, int device, int64_t n_rows, int32_t dim, i
     if (rc != AHR_OK) { delete idx; return rc; }
     idx->has_map = true;
   }
+  if (dtype == AHR_DTYPE_F32 && n_rows > 0 && dim % 8 == 0) {
+    // tensor-core candidate generation for fp32 rows: keep hi/lo bf16 halves (same bytes as the fp32 original)
+    const int64_t ne = n_rows * (int64_t)dim;
+    int rc = idx->x_hi.reserve((size_t)ne * 2);
+    if (rc == AHR_OK) rc = idx->x_lo.reserve((size_t)ne * 2);
+    if (rc == AHR_OK) rc = split_f32_hi_lo(reinterpret_cast<const float *>(dev_rows), ne, idx->x_hi.ptr, idx->x_lo.ptr, 0);
+    if (rc == AHR_OK) rc = tc2_make_corpus_map(&idx->map_x2, idx->x_hi.ptr, n_rows, dim);
+    if (rc == AHR_OK) rc = tc2_make_corpus_map(&idx->map_x2_lo, idx->x_lo.ptr, n_rows, dim);
+    if (rc != AHR_OK) { idx->x_hi.release(); idx->x_lo.release(); delete idx; return rc; }
+    idx->has_map = true;
+  }
   if (const char *e = getenv("AHR_TC_VARIANT")) idx->variant = atoi(e) == 1 ? 1 : 2;
   if (const char *e = getenv("AHR_TC_PREFETCH")) idx->prefetch_tiles = std::max(0, atoi(e));
   if (const char *e = getenv("AHR_TC_SLABS")) idx->force_slabs = std::max(0, atoi(e));
@@ -135,7 +149,7 @@ int ahr_index_create(ahr_index **out, int device, int64_t n_rows, int32_t dim, i
 int ahr_index_destroy(ahr_index *idx) {
   if (!idx) return AHR_OK;
   DeviceGuard guard(idx->device);
-  idx->stats_buf.release(); idx->ws.release(); idx->ws2.release(); idx->hq.release(); idx->hs.release(); idx->hi.release();
+  idx->x_hi.release(); idx->x_lo.release(); idx->q_split.release(); idx->stats_buf.release(); idx->ws.release(); idx->ws2.release(); idx->hq.release(); idx->hs.release(); idx->hi.release();
   if (idx->d_max_norm) cudaFree(idx->d_max_norm);
   delete idx;
   return AHR_OK;
@@ -166,11 +180,23 @@ static int exact_bruteforce(ahr_index *idx, const void *dev_q, const int32_t *q_
 // tensor-core path: per-slab partial lists (K1) + per-query reduction, results [nq, k] with global ids
 static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, float *out_scores, int64_t *out_ids,
                    float *dbg_scores, cudaStream_t st) {
-  AHR_REQUIRE(idx->dtype == AHR_DTYPE_BF16, "the tensor-core path needs a bf16 index");
-  AHR_REQUIRE(idx->has_map, "bf16 index is not TMA-addressable (dim %% 8 != 0 or rows not 16-byte aligned)");
+  AHR_REQUIRE(idx->has_map, "index is not TMA-addressable (dim %% 8 != 0 or rows not 16-byte aligned)");
   AHR_REQUIRE((reinterpret_cast<uintptr_t>(dev_q) & 15) == 0, "queries must be 16-byte aligned");
+  const bool split = idx->dtype == AHR_DTYPE_F32;  // fp32 operands: hi + lo bf16 halves, 3 operand segments
+  const void *q_hi = dev_q, *q_lo = nullptr;
+  if (split) {
+    const int64_t ne = (int64_t)nq * idx->dim;
+    int rc0 = idx->q_split.reserve((size_t)ne * 4 + 512);
+    if (rc0 != AHR_OK) return rc0;
+    uint8_t *base = reinterpret_cast<uint8_t *>(idx->q_split.ptr);
+    void *hi = base, *lo = base + (((size_t)ne * 2 + 255) & ~(size_t)255);
+    rc0 = split_f32_hi_lo(reinterpret_cast<const float *>(dev_q), ne, hi, lo, st);
+    if (rc0 != AHR_OK) return rc0;
+    q_hi = hi;
+    q_lo = lo;
+  }
   const int64_t n_ctiles = (idx->n_rows + 255) / 256;
-  const bool pairs = idx->variant == 2;
+  const bool pairs = idx->variant == 2 || split;
   const int32_t n_qtiles = pairs ? (nq + 255) / 256 : (nq + 127) / 128;
   const int n_units = pairs ? std::max(1, idx->sm_count / 2) : idx->sm_count;  // CTA pairs or CTAs
   int S = tc_choose_slabs(n_qtiles, n_ctiles, n_units);
@@ -195,8 +221,8 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
     AHR_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)idx->sm_count * 64, st));
   }
   if (pairs)
-    rc = tc2_topk_partials(idx->map_x2, dev_q, idx->n_rows, idx->dim, nq, k, S, n_units, idx->prefetch_tiles, ps, pi,
-                           dbg_scores, stats, st);
+    rc = tc2_topk_partials(idx->map_x2, split ? &idx->map_x2_lo : nullptr, q_hi, q_lo, idx->n_rows, idx->dim, nq, k, S,
+                           n_units, idx->prefetch_tiles, ps, pi, dbg_scores, stats, st);
   else
     rc = tc_topk_partials(idx->map_x, dev_q, idx->n_rows, idx->dim, nq, k, S, idx->sm_count, ps, pi, dbg_scores, st);
   if (rc != AHR_OK) return rc;
@@ -243,8 +269,7 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
   // ---- exact mode ----
   idx->n_certified = 0;
   idx->n_fallback = 0;
-  const bool use_tc = idx->dtype == AHR_DTYPE_BF16 && idx->has_map && k <= 96 && idx->n_rows > 4096 &&
-                      (reinterpret_cast<uintptr_t>(dev_q) & 15) == 0;
+  const bool use_tc = idx->has_map && k <= 96 && idx->n_rows > 4096 && (reinterpret_cast<uintptr_t>(dev_q) & 15) == 0;
   if (!use_tc) {
     idx->n_fallback = nq;
     return exact_bruteforce(idx, dev_q, nullptr, nq, k, dev_scores, dev_ids, idx->ws, st);
@@ -276,7 +301,11 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
   if (rc != AHR_OK) return rc;
   // |tensor - canonical| <= eps_rel * ||q|| * ||x||: fp32 accumulation over dim/16 MMA steps plus the in-step
   // alignment of 16 exact products; 2^-23 per accumulation step with generous headroom
-  const float eps_rel = (float)((idx->dim / 8 + 32) * std::ldexp(1.0, -23));
+  // fp32 rows go through the hi/lo split: 3x the accumulation steps plus the dropped lo*lo and residual terms
+  // (|x - hi - lo| <= 2^-18 |x| per operand -> <= 3 * 2^-18, rounded up to 2^-16)
+  const float eps_rel = idx->dtype == AHR_DTYPE_F32
+                            ? (float)((3 * idx->dim / 8 + 32) * std::ldexp(1.0, -23) + std::ldexp(1.0, -16))
+                            : (float)((idx->dim / 8 + 32) * std::ldexp(1.0, -23));
   rc = query_eps(dev_q, idx->dtype, nq, idx->dim, idx->d_max_norm, eps_rel, eps, st);
   if (rc != AHR_OK) return rc;
   AHR_CUDA_CHECK(cudaMemsetAsync(fcnt, 0, 4, st));

@@ -20,6 +20,8 @@ struct TcParams {
   int32_t n_qtiles;  // ceil(nq / 128)
   int32_t n_slabs;   // S
   int32_t k;         // entries kept per (query, slab), <= KLIST
+  int32_t n_seg;     // 1: plain bf16 operands.  3: fp32 operands split as hi + lo bf16 -- the K loop runs over
+                     // (q_hi, x_hi), (q_lo, x_hi), (q_hi, x_lo), i.e. q.x up to the 2^-18-relative lo*lo term
   float *part_scores;    // [nq_pad][S][k]
   int32_t *part_ids;     // row index inside this index (local), -1 = empty
   float *dbg_scores;     // optional [nq][n_rows] dump of the raw accumulators (tests)

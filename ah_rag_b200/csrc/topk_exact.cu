@@ -272,6 +272,26 @@ int query_eps(const void *dev_q, int dtype, int32_t nq, int32_t dim, const float
   return AHR_OK;
 }
 
+// fp32 -> two bf16 halves: hi = rn_bf16(x), lo = rn_bf16(x - hi); |x - hi - lo| <= 2^-18 |x|
+__global__ void split_hi_lo_kernel(const float *__restrict__ src, int64_t n, __nv_bfloat16 *__restrict__ hi,
+                                   __nv_bfloat16 *__restrict__ lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+int split_f32_hi_lo(const float *src, int64_t n_elems, void *hi, void *lo, cudaStream_t stream) {
+  if (n_elems <= 0) return AHR_OK;
+  const int blocks = (int)std::min<int64_t>((n_elems + 255) / 256, 148 * 16);
+  split_hi_lo_kernel<<<blocks, 256, 0, stream>>>(src, n_elems, reinterpret_cast<__nv_bfloat16 *>(hi),
+                                                 reinterpret_cast<__nv_bfloat16 *>(lo));
+  AHR_KERNEL_CHECK();
+  return AHR_OK;
+}
+
 // scatter == false: dst[i] = src[sel[i]] ; scatter == true: dst[sel[i]] = src[i]   (rows of k entries)
 __global__ void gather_rows_kernel(const float *__restrict__ src_s, const int64_t *__restrict__ src_i,
                                    const int32_t *__restrict__ sel, int32_t n_sel, int32_t k, float *__restrict__ dst_s,

@@ -280,6 +280,7 @@ int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows
   p.part_ids = part_ids;
   p.dbg_scores = dbg_scores;
   p.stats = nullptr;
+  p.n_seg = 1;
   const int items = p.n_slabs * p.n_qtiles;
   if (grid > items) grid = items;
   if (dbg_scores) {

@@ -30,7 +30,8 @@ constexpr uint32_t T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
 
 template <int KLIST, int STAGES, bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TcParams p,
+topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                const __grid_constant__ CUtensorMap map_q_lo, const __grid_constant__ CUtensorMap map_x_lo, TcParams p,
                 int prefetch_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -51,11 +52,14 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
   const int n_items = p.n_slabs * p.n_qtiles;  // n_qtiles counts 256-query tiles here
-  const int n_kblocks = (p.dim + TC_BK - 1) / TC_BK;
+  const int kb_per_seg = (p.dim + TC_BK - 1) / TC_BK;
+  const int n_kblocks = kb_per_seg * p.n_seg;  // k-blocks per tile over all operand segments
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_q);
     prefetch_tensormap(&map_x);
+    prefetch_tensormap(&map_q_lo);
+    prefetch_tensormap(&map_x_lo);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -92,15 +96,18 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int64_t ct = t0; ct < t1; ++ct) {
           const int32_t x_row0 = (int32_t)(ct * T2_BN) + (int32_t)rank * T2_BN_HALF;
           const bool pf = prefetch_tiles > 0 && ct + prefetch_tiles < t1;
-          for (int kb = 0; kb < n_kblocks; ++kb) {
-            if (pf) tma_prefetch_2d(&map_x, kb * TC_BK, x_row0 + prefetch_tiles * T2_BN);
+          for (int t = 0; t < n_kblocks; ++t) {
+            const int seg = t / kb_per_seg, kb = t - seg * kb_per_seg;
+            const CUtensorMap *mq = seg == 1 ? &map_q_lo : &map_q;  // (q_hi,x_hi) (q_lo,x_hi) (q_hi,x_lo)
+            const CUtensorMap *mx = seg == 2 ? &map_x_lo : &map_x;
+            if (pf) tma_prefetch_2d(mx, kb * TC_BK, x_row0 + prefetch_tiles * T2_BN);
             mbar_wait_acct(&empty[stage], phase ^ 1, acct);
             uint8_t *a_dst = tiles + stage * T2_STAGE_BYTES;
             uint8_t *b_dst = a_dst + T2_A_BYTES;
             const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
             if (leader) mbar_arrive_expect_tx(&full[stage], 2 * T2_STAGE_BYTES);
-            tma_load_2d_2sm(a_dst, &map_q, full_leader, kb * TC_BK, q_row0, kEvictLast);
-            tma_load_2d_2sm(b_dst, &map_x, full_leader, kb * TC_BK, x_row0, kEvictNormal);
+            tma_load_2d_2sm(a_dst, mq, full_leader, kb * TC_BK, q_row0, kEvictLast);
+            tma_load_2d_2sm(b_dst, mx, full_leader, kb * TC_BK, x_row0, kEvictNormal);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -217,8 +224,9 @@ static constexpr size_t tc2_smem_bytes() {
 }
 
 template <int KLIST, int STAGES, bool DBG>
-static int tc2_launch_t(const CUtensorMap &map_q, const CUtensorMap &map_x, const TcParams &p, int n_clusters,
-                        int prefetch_tiles, cudaStream_t stream) {
+static int tc2_launch_t(const CUtensorMap &map_q, const CUtensorMap &map_x, const CUtensorMap &map_q_lo,
+                        const CUtensorMap &map_x_lo, const TcParams &p, int n_clusters, int prefetch_tiles,
+                        cudaStream_t stream) {
   static bool configured = false;
   constexpr size_t smem = tc2_smem_bytes<KLIST, STAGES>();
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
@@ -227,22 +235,33 @@ static int tc2_launch_t(const CUtensorMap &map_q, const CUtensorMap &map_x, cons
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  topk_tc2_kernel<KLIST, STAGES, DBG><<<2 * n_clusters, TC_THREADS, smem, stream>>>(map_q, map_x, p, prefetch_tiles);
+  topk_tc2_kernel<KLIST, STAGES, DBG><<<2 * n_clusters, TC_THREADS, smem, stream>>>(map_q, map_x, map_q_lo, map_x_lo, p,
+                                                                                    prefetch_tiles);
   AHR_KERNEL_CHECK();
   return AHR_OK;
 }
 
 // Launch the CTA-pair K1.  part_* must hold nq * n_slabs * k entries; n_pairs = SM count / 2.
-int tc2_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows, int32_t dim, int32_t nq, int32_t k,
-                      int32_t n_slabs, int n_pairs, int prefetch_tiles, float *part_scores, int32_t *part_ids,
-                      float *dbg_scores, unsigned long long *stats, cudaStream_t stream) {
+int tc2_topk_partials(const CUtensorMap &map_x, const CUtensorMap *map_x_lo, const void *dev_q, const void *dev_q_lo,
+                      int64_t n_rows, int32_t dim, int32_t nq, int32_t k, int32_t n_slabs, int n_pairs,
+                      int prefetch_tiles, float *part_scores, int32_t *part_ids, float *dbg_scores,
+                      unsigned long long *stats, cudaStream_t stream) {
   AHR_REQUIRE(k >= 1 && k <= 120, "tensor-core top-k supports 1 <= k <= 120 (got %d)", k);
   AHR_REQUIRE(dim % 8 == 0, "bf16 index needs dim %% 8 == 0 for TMA (got %d)", dim);
   AHR_REQUIRE(n_rows < (int64_t)INT32_MAX - T2_BN, "rows per index shard must fit int32 (got %lld)", (long long)n_rows);
-  CUtensorMap map_q;
+  CUtensorMap map_q, map_q_lo;
   int rc = make_bf16_tensor_map(&map_q, dev_q, nq, dim, T2_BM);
   if (rc != AHR_OK) return rc;
+  const bool split = map_x_lo != nullptr && dev_q_lo != nullptr;  // fp32 operands as hi + lo bf16 halves
+  if (split) {
+    rc = make_bf16_tensor_map(&map_q_lo, dev_q_lo, nq, dim, T2_BM);
+    if (rc != AHR_OK) return rc;
+  } else {
+    map_q_lo = map_q;
+  }
+  const CUtensorMap &mx_lo = split ? *map_x_lo : map_x;
   TcParams p;
+  p.n_seg = split ? 3 : 1;
   p.n_rows = n_rows;
   p.n_ctiles = (n_rows + T2_BN - 1) / T2_BN;
   p.nq = nq;
@@ -259,16 +278,16 @@ int tc2_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_row
   if (n_clusters < 1) n_clusters = 1;
   if (dbg_scores) {
     AHR_REQUIRE(k <= 56, "debug score dump supports k <= 56");
-    return tc2_launch_t<64, 4, true>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+    return tc2_launch_t<64, 4, true>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, prefetch_tiles, stream);
   }
   if (k <= 56) {  // the list needs room beyond k: KLIST - k appends amortise one compaction
     // 4 stages (128 KB) + 64 KB of lists leave ~30 KB of the SM's 228 KB to L1, which is where the slow path's
     // local-memory chunk copy lives: measured 64.9 ms vs 71.4 ms with 5 stages (L1 ~3 KB) on c3, equal on c4.
     static const int stages = getenv("AHR_TC_STAGES") ? atoi(getenv("AHR_TC_STAGES")) : 4;  // experiments: 3 | 4
-    if (stages == 3) return tc2_launch_t<64, 3, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
-    return tc2_launch_t<64, 4, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+    if (stages == 3) return tc2_launch_t<64, 3, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, prefetch_tiles, stream);
+    return tc2_launch_t<64, 4, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, prefetch_tiles, stream);
   }
-  return tc2_launch_t<128, 2, false>(map_q, map_x, p, n_clusters, prefetch_tiles, stream);
+  return tc2_launch_t<128, 2, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, prefetch_tiles, stream);
 }
 
 }  // namespace ahr

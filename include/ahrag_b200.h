@@ -80,7 +80,9 @@ int64_t ahr_launch_count(void);
  *   {"hnsw:space": "cosine"} / Collection.upsert)
  * by a device-resident row-major [n_rows, dim] matrix the caller already holds.  Rows are expected
  * L2-normalised by the producer, as the reference does (:655-656); ids are id_base + row.
- * dim must be a multiple of 8 for bf16 indexes (16-byte TMA row pitch).
+ * dim must be a multiple of 8 for the tensor-core path (16-byte TMA row pitch); other dims fall back to the
+ * brute-force exact scan.  For fp32 rows the library additionally keeps its own hi/lo bf16 split of the matrix
+ * (2 x n_rows x dim x 2 bytes) so that fp32 indexes also run on the tensor cores (3 operand segments per tile).
  * ---------------------------------------------------------------------------------------------- */
 int ahr_index_create(ahr_index **out, int device, int64_t n_rows, int32_t dim, int dtype,
                      const void *dev_rows, int64_t id_base);
@@ -92,9 +94,12 @@ int ahr_index_destroy(ahr_index *idx);
  * dev_q: [nq, dim] in the index dtype.  Outputs [nq, k]: scores = <q, x> (the reference's
  * `semantic` is 1 - fl32(1 - score), :723) and ids, sorted by (score desc, id asc); lists shorter than k
  * (n_rows < k) are padded with (-inf, -1).
- *   AHR_MODE_BF16 : k <= 120.  scores are the tensor-core fp32 accumulations.
- *   AHR_MODE_EXACT: canonical scores, bit-reproducible; ids bit-identical to the CPU oracle.
- *                   May synchronise the stream internally (certification of the candidate set).
+ *   AHR_MODE_BF16 : k <= 120.  scores are the tensor-core fp32 accumulations (fp32 indexes: hi/lo split, ~2^-16).
+ *   AHR_MODE_EXACT: canonical scores, bit-reproducible; ids bit-identical to the CPU oracle.  The tensor cores
+ *                   propose k + slack candidates, which are re-scored canonically and CERTIFIED (k-th exact score
+ *                   above the last candidate's tensor score + error bound); queries that cannot be certified, and
+ *                   shapes the tensor path does not take (k > 96, n_rows <= 4096, dim % 8 != 0), run the brute-force
+ *                   fp64 scan.  Synchronises the stream internally (certification count).
  */
 int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode, float *dev_scores,
              int64_t *dev_ids, void *stream);

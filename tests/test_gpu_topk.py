@@ -168,3 +168,22 @@ def test_packed_merge_equals_plain_merge(engine):
     assert torch.equal(ps, ms) and torch.equal(pi, mi)
     fs, fi = engine.VectorIndex(X).topk(Q, k, mode="exact")
     assert torch.equal(pi, fi) and torch.equal(ps, fs)
+
+
+@pytest.mark.parametrize("n,dim,nq", [(5000, 384, 40), (9000, 128, 257)])
+def test_fp32_index_tensor_core_scores_hi_lo_split(engine, n, dim, nq):
+    """fp32 rows run on the tensor cores as hi + lo bf16 halves (3 operand segments): accumulators must be within
+    the certification bound of the canonical fp32 score, and exact mode must certify and stay bit-exact."""
+    Xn, Qn = synth.unit_rows(n, dim, 61, clustered=8), synth.unit_rows(nq, dim, 62, clustered=8)
+    X, Q = torch.from_numpy(Xn).cuda(), torch.from_numpy(Qn).cuda()
+    idx = engine.VectorIndex(X)
+    got = idx.debug_tc_scores(Q).cpu().numpy()
+    want = exact.canonical_scores(Xn, Qn)
+    bound = (3 * dim / 8 + 32) * 2.0 ** -23 + 2.0 ** -16
+    assert np.abs(got - want).max() <= bound / 2, np.abs(got - want).max()
+    k = 10
+    s, i = idx.topk(Q, k, mode="exact")
+    cert, fb = idx.exact_stats()
+    assert cert >= nq * 0.9 and cert + fb == nq
+    rs, ri = exact.exact_topk(Xn, Qn, k)
+    assert np.array_equal(i.cpu().numpy(), ri) and np.array_equal(s.cpu().numpy().view(np.uint32), rs.view(np.uint32))
