@@ -64,54 +64,70 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The sampler is
+    started before the warm-up (nvidia-smi needs a few hundred ms to produce its first line) and only the samples
+    whose timestamp falls inside the timed window are reported."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int) -> None:
         self.gpu_index = gpu_index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def start(self) -> None:
         try:
             fd, self.path = tempfile.mkstemp(prefix="ahr_clocks_", suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def window_begin(self) -> None:
+        self.t0 = time.time()
+
+    def window_end(self) -> None:
+        self.t1 = time.time()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)  # let the last in-window sample land
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             with open(self.path) as f:
                 for line in f:
                     parts = [x.strip() for x in line.split(",")]
-                    if len(parts) < 9:
+                    if len(parts) < 10:
                         continue
                     try:
-                        sm.append(float(parts[1])); smax.append(float(parts[2]))
+                        ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                        rows.append((ts, float(parts[2]), float(parts[3]),
+                                     [nm for nm, val in zip(names, parts[6:10]) if val.lower().startswith("active")]))
                     except ValueError:
                         continue
-                    for nm, val in zip(names, parts[5:9]):
-                        if val.lower().startswith("active"):
-                            reasons.add(nm)
             os.remove(self.path)
         except Exception:
             pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= (self.t1 or r[0]) + 0.05]
+        scope = "timed window"
+        if not inside:  # window shorter than one sampling period: report the samples under the same load around it
+            inside, scope = rows[-5:], "last samples of the run (timed window shorter than the sampling period)"
+        sm = [r[1] for r in inside]
+        reasons = sorted({x for r in inside for x in r[3]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+                "reasons": reasons, "samples": len(sm), "scope": scope}
 
 
 def make_corpus_shard(torch, device, lo: int, hi: int, dim: int):
@@ -242,13 +258,14 @@ def main() -> int:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
         return float(ms.item())
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         step_device()
     step_e2e()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.window_begin()
     index.set_profiling(True)
     index.get_profile()
     launches0 = engine.launch_count()
@@ -257,6 +274,7 @@ def main() -> int:
     prof = index.get_profile()
     index.set_profiling(False)
     ms_e2e = timed(step_e2e, args.steps)
+    sampler.window_end()
     clocks = sampler.stop() if rank == 0 else None
 
     ms_step = ms_total / args.steps
