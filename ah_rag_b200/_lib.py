@@ -24,7 +24,7 @@ EXPORTS = [
     "ahr_last_error", "ahr_version", "ahr_launch_count", "ahr_index_create", "ahr_index_destroy", "ahr_topk",
     "ahr_topk_host", "ahr_merge_topk", "ahr_merge_topk_packed", "ahr_graph_create", "ahr_graph_destroy", "ahr_anchor_rerank", "ahr_expand",
     "ahr_debug_tc_scores", "ahr_rescore", "ahr_debug_round4", "ahr_exact_stats", "ahr_set_profiling",
-    "ahr_get_profile",
+    "ahr_get_profile", "ahr_env_reset", "ahr_env_step",
 ]
 
 
@@ -37,6 +37,14 @@ class RerankParams(ctypes.Structure):
         ("has_judge_min", c_int32), ("has_conf_min", c_int32),
         ("type_mask", c_int32), ("member_top_m", c_int32), ("parent_cap", c_int32), ("reserved", c_int32),
     ]
+
+
+class EnvBatch(ctypes.Structure):
+    """Mirror of ``struct ahr_env_batch`` (device pointers of the batched environment state)."""
+    _fields_ = [("n_env", c_int32), ("cap_sel", c_int32), ("cap_fr", c_int32), ("reserved", c_int32)] + [
+        (name, c_void_p) for name in ("sel_ids", "sel_cnt", "fr_ids", "fr_cnt", "shown_ids", "shown_score", "shown_sem",
+                                      "shown_cnt", "n_seeds", "obs_step", "obs_sel", "obs_fr", "env_steps", "gym_steps",
+                                      "last_action", "done", "overflow")]
 
 
 def _declare(lib: ctypes.CDLL) -> None:
@@ -62,6 +70,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.ahr_exact_stats.argtypes = [vp, POINTER(c_int64), POINTER(c_int64)]
     lib.ahr_set_profiling.argtypes = [vp, c_int]
     lib.ahr_get_profile.argtypes = [vp, POINTER(c_double), POINTER(c_int64), POINTER(c_int32)]
+    lib.ahr_env_reset.argtypes = [vp, POINTER(EnvBatch), vp, vp, vp, vp, c_int32, c_int32, vp, vp, vp]
+    lib.ahr_env_step.argtypes = [vp, POINTER(EnvBatch), vp, c_int32, c_double, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("ahr_last_error", "ahr_launch_count"):

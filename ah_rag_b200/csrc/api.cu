@@ -510,4 +510,27 @@ int ahr_expand(ahr_graph *g, int32_t n_env, const int32_t *dev_ops, const int32_
                       reinterpret_cast<cudaStream_t>(stream));
 }
 
+int ahr_env_reset(ahr_graph *g, const ahr_env_batch *env, const int32_t *dev_nodes, const double *dev_semantic,
+                  const double *dev_score, const int32_t *dev_count, int32_t top_k, int32_t n_seeds, float *dev_features,
+                  uint8_t *dev_mask, void *stream) {
+  AHR_REQUIRE(g && env, "ahr_env_reset: NULL handle or env");
+  AHR_REQUIRE(top_k >= 1 && top_k <= 10 && n_seeds >= 0, "ahr_env_reset: top_k must be in [1, 10] (got %d)", top_k);
+  if (env->n_env == 0) return AHR_OK;
+  AHR_REQUIRE(dev_nodes && dev_semantic && dev_score && dev_count && dev_features && dev_mask, "ahr_env_reset: NULL buffer");
+  DeviceGuard guard(g->device);
+  return env_reset(g->view, *env, dev_nodes, dev_semantic, dev_score, dev_count, top_k, n_seeds, dev_features, dev_mask,
+                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ahr_env_step(ahr_graph *g, const ahr_env_batch *env, const int32_t *dev_actions, int32_t max_steps,
+                 double repeat_penalty, float *dev_features, double *dev_rewards, uint8_t *dev_done, uint8_t *dev_mask,
+                 void *stream) {
+  AHR_REQUIRE(g && env, "ahr_env_step: NULL handle or env");
+  if (env->n_env == 0) return AHR_OK;
+  AHR_REQUIRE(dev_actions && dev_features && dev_rewards && dev_done && dev_mask, "ahr_env_step: NULL buffer");
+  DeviceGuard guard(g->device);
+  return env_step(g->view, *env, dev_actions, max_steps, repeat_penalty, dev_features, dev_rewards, dev_done, dev_mask,
+                  reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

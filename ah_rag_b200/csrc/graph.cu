@@ -12,6 +12,7 @@
 // NetworkX graph, so "first occurrence in reference order" == "lowest position in the generated list".
 #include "common.cuh"
 #include "kernels.h"
+#include "graph_shared.cuh"
 
 namespace ahr {
 
@@ -267,51 +268,6 @@ int graph_anchor_rerank(const GraphView &g, int32_t nq, int32_t n_seeds, const i
 // ---------------------------------------------------------------------------------------------
 // frontier expansion: one warp per environment
 // ---------------------------------------------------------------------------------------------
-constexpr int EXP_WARPS = 4;
-
-struct ExpandState {
-  int32_t *out;  // this warp's list in shared memory
-  int count;
-  int raw;
-  int limit;
-};
-
-// append values to the order-preserving unique list; returns true once the list is full
-__device__ __forceinline__ bool expand_push(ExpandState &st, int32_t val, bool valid, int lane) {
-  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  st.raw += __popc(vmask);
-  bool dup = false;
-  if (valid) {
-    for (int t = 0; t < st.count; ++t) dup |= (st.out[t] == val);
-  }
-  // duplicates inside this batch of 32: the lowest lane carrying the value is the first occurrence
-  const unsigned peers = __match_any_sync(0xffffffffu, valid ? val : (int32_t)(-2 - lane));
-  const bool first_in_batch = (__ffs(peers & vmask) - 1) == lane;
-  const bool fresh = valid && !dup && first_in_batch;
-  const unsigned nmask = __ballot_sync(0xffffffffu, fresh);
-  const int pos = st.count + __popc(nmask & ((1u << lane) - 1u));
-  if (fresh && pos < st.limit) st.out[pos] = val;
-  st.count = min(st.limit, st.count + __popc(nmask));
-  __syncwarp();
-  return st.count >= st.limit;
-}
-
-__device__ __forceinline__ bool expand_segment(ExpandState &st, const GraphView &g, int slot, int32_t v, int32_t exclude,
-                                               int lane) {
-  const int64_t p0 = g.row_ptr[slot][v], p1 = g.row_ptr[slot][v + 1];
-  for (int64_t b = p0; b < p1; b += 32) {
-    const int64_t i = b + lane;
-    int32_t val = -1;
-    bool valid = i < p1;
-    if (valid) {
-      val = g.col_idx[slot][i];  // coalesced: consecutive lanes read consecutive neighbours
-      valid = val != exclude;
-    }
-    if (expand_push(st, val, valid, lane)) return true;
-  }
-  return false;
-}
-
 __global__ void __launch_bounds__(EXP_WARPS * 32)
 expand_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const int32_t *__restrict__ in_ids,
               const int32_t *__restrict__ in_offsets, int32_t limit, int32_t *__restrict__ out_ids,
@@ -323,30 +279,7 @@ expand_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const
   ExpandState st;
   st.out = sm_out + (size_t)w * limit;
   st.count = 0; st.raw = 0; st.limit = limit;
-  const int op = ops[env];
-  bool full = false;
-  for (int idx = in_offsets[env]; idx < in_offsets[env + 1] && !full; ++idx) {
-    const int32_t v = in_ids[idx];
-    if (v < 0 || v >= g.n_nodes) continue;  // `if nid not in G: continue`
-    if (op == AHR_OP_PARENTS) {
-      full = expand_segment(st, g, AHR_CSR_BEL_OUT, v, -1, lane);
-    } else if (op == AHR_OP_CHILDREN) {
-      full = expand_segment(st, g, AHR_CSR_BEL_IN, v, -1, lane);
-    } else {
-      full = expand_segment(st, g, AHR_CSR_REL_OUT, v, -1, lane);
-      if (!full) full = expand_segment(st, g, AHR_CSR_REL_IN, v, -1, lane);
-      if (!full && g.node_type[v] == AHR_NT_ENTITY) {
-        // second hop: every hyperedge h of v, then the other participants of h  (environment.py:456-467)
-        const int64_t h0 = g.row_ptr[AHR_CSR_PART_OUT][v], h1 = g.row_ptr[AHR_CSR_PART_OUT][v + 1];
-        for (int64_t hi = h0; hi < h1 && !full; ++hi) {
-          const int32_t h = g.col_idx[AHR_CSR_PART_OUT][hi];
-          full = expand_push(st, h, lane == 0, lane);
-          if (!full) full = expand_segment(st, g, AHR_CSR_PART_IN, h, v, lane);
-        }
-      }
-    }
-    if (st.raw >= limit) break;  // stop rule on the UN-deduplicated length, checked after finishing v
-  }
+  expand_walk(st, g, ops[env], in_ids + in_offsets[env], in_offsets[env + 1] - in_offsets[env], lane);
   for (int j = lane; j < limit; j += 32) out_ids[(int64_t)env * limit + j] = j < st.count ? st.out[j] : -1;
   if (lane == 0) out_counts[env] = st.count;
 }

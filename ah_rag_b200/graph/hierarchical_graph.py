@@ -394,30 +394,17 @@ class HierarchicalGraph:
             model_name = model_name or vi.get("model", "all-MiniLM-L6-v2")
         return db_path, model_name
 
-    def search_batch(self, query_embeddings, top_k: int = 5, member_top_m: int = 5,
-                     alpha: Optional[float] = None, beta: Optional[float] = None, gamma: Optional[float] = None,
-                     delta: Optional[float] = None, judge_overall_min: Optional[float] = None,
-                     confidence_min: Optional[float] = None, type_filter: Optional[List[str]] = None,
-                     return_cluster: bool = False, db_path: Optional[str] = None) -> List[Any]:
-        """Batched search: ``query_embeddings`` [B, d] (numpy or torch, host or device).  Per item the result
-        equals ``search`` on that query.  One fused top-k launch + one expansion/rerank launch for the batch."""
+    def _device_search(self, query_embeddings, top_k: int, params, want_cluster: bool, db_path: str):
+        """Top-k + anchor expansion/rerank for a batch, results left on the device (no host synchronisation).
+        -> (dict of device tensors from ``GraphCSR.anchor_rerank``, index rows [B, k_eff] of the seeds)."""
         import torch
-        params = self._resolve(member_top_m, alpha, beta, gamma, delta, judge_overall_min, confidence_min, type_filter)
-        db_path, _ = self._resolve_index(db_path, "unused")
         dg = self._device_graph()
         di = self._device_index(db_path)
-        csr, arrays, store = dg["csr"], dg["arrays"], di["store"]
+        csr = dg["csr"]
         dev = csr.device
         q = query_embeddings if isinstance(query_embeddings, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(query_embeddings, dtype=np.float32))
-        B = int(q.shape[0])
-        n_index = len(store.ids)
-        if B == 0:
-            return []
-        if n_index == 0 or top_k <= 0:
-            empty = {"seeds": [], "expanded": [], "reranked": []}
-            return [dict(empty) if return_cluster else [] for _ in range(B)]
-        k_eff = min(int(top_k), n_index)  # Chroma returns at most the collection size
+        k_eff = min(int(top_k), len(di["store"].ids))
         if self.index_dtype == "bf16":
             qd = q.to(dev).to(torch.bfloat16).contiguous()
             scores, rows = di["index"].topk(qd, k_eff, mode="bf16")
@@ -426,7 +413,30 @@ class HierarchicalGraph:
             scores, rows = di["index"].topk(qd, k_eff, mode="exact")
         seed_nodes = torch.where(rows >= 0, di["row_to_node"][rows.clamp(min=0)], torch.full_like(rows, -1, dtype=torch.int32))
         out = csr.anchor_rerank(seed_nodes.to(torch.int32).contiguous(), scores, params, int(top_k),
-                                want_cluster=return_cluster)
+                                want_cluster=want_cluster)
+        return out, rows
+
+    def search_batch(self, query_embeddings, top_k: int = 5, member_top_m: int = 5,
+                     alpha: Optional[float] = None, beta: Optional[float] = None, gamma: Optional[float] = None,
+                     delta: Optional[float] = None, judge_overall_min: Optional[float] = None,
+                     confidence_min: Optional[float] = None, type_filter: Optional[List[str]] = None,
+                     return_cluster: bool = False, db_path: Optional[str] = None) -> List[Any]:
+        """Batched search: ``query_embeddings`` [B, d] (numpy or torch, host or device).  Per item the result
+        equals ``search`` on that query.  One fused top-k launch + one expansion/rerank launch for the batch."""
+        params = self._resolve(member_top_m, alpha, beta, gamma, delta, judge_overall_min, confidence_min, type_filter)
+        db_path, _ = self._resolve_index(db_path, "unused")
+        dg = self._device_graph()
+        di = self._device_index(db_path)
+        arrays, store = dg["arrays"], di["store"]
+        B = len(query_embeddings)
+        n_index = len(store.ids)
+        if B == 0:
+            return []
+        if n_index == 0 or top_k <= 0:
+            empty = {"seeds": [], "expanded": [], "reranked": []}
+            return [dict(empty) if return_cluster else [] for _ in range(B)]
+        k_eff = min(int(top_k), n_index)  # Chroma returns at most the collection size
+        out, rows = self._device_search(query_embeddings, int(top_k), params, return_cluster, db_path)
         host = {k: v.cpu().numpy() for k, v in out.items()}
         rows_h = rows.cpu().numpy() if return_cluster else None
         node_ids, G = arrays["node_ids"], self.G

@@ -186,6 +186,41 @@ int ahr_expand(ahr_graph *g, int32_t n_env, const int32_t *dev_ops, const int32_
                const int32_t *dev_in_offsets, int32_t limit, int32_t *dev_out_ids, int32_t *dev_out_counts,
                void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident batched gym environment.  Replaces, for n_env environments per launch,
+ *   AHRAGGymEnv.reset / .step / .get_action_mask        src/ah_rag/agent/gym_env.py:41-125
+ *   featurize_observation                                src/ah_rag/agent/featurizer.py:21-56
+ *   step_reward                                          src/ah_rag/agent/reward.py:6-26
+ * over GraphEnvironment's state rules (src/ah_rag/agent/environment.py:155-241, :301-355, :393-480).
+ * All arrays are caller-owned device memory (the Python wrapper allocates them once per batch):
+ *   sel_ids [n_env, cap_sel] / sel_cnt [n_env]   selection_set        fr_ids [n_env, cap_fr] / fr_cnt   frontier_set
+ *   shown_ids / shown_score / shown_sem [n_env, 10], shown_cnt       the nodes of the current obs["selection"]
+ *   n_seeds, obs_step, obs_sel, obs_fr [n_env]                       len(obs["seeds"]), obs["step"], sizes in obs["state"]
+ *                                                                    (-1: the observation has no "state", :325-333)
+ *   env_steps, gym_steps, last_action [n_env], done [n_env], overflow [1]
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ahr_env_batch {
+  int32_t n_env, cap_sel, cap_fr, reserved;
+  int32_t *sel_ids, *sel_cnt, *fr_ids, *fr_cnt;
+  int32_t *shown_ids;
+  double *shown_score, *shown_sem;
+  int32_t *shown_cnt, *n_seeds, *obs_step, *obs_sel, *obs_fr, *env_steps, *gym_steps, *last_action;
+  uint8_t *done;
+  int32_t *overflow;
+} ahr_env_batch;
+
+/* reset from the output of ahr_anchor_rerank run with top_k (gym: 5): dev_nodes/dev_semantic/dev_score [n_env, top_k],
+ * dev_count [n_env]; n_seeds = number of seeds every query had.  Writes features [n_env, 84] fp32 and the action mask
+ * [n_env, 6] u8. */
+int ahr_env_reset(ahr_graph *g, const ahr_env_batch *env, const int32_t *dev_nodes, const double *dev_semantic,
+                  const double *dev_score, const int32_t *dev_count, int32_t top_k, int32_t n_seeds,
+                  float *dev_features, uint8_t *dev_mask, void *stream);
+/* one gym step per environment: dev_actions [n_env] in 0..5.  Writes features [n_env, 84], rewards [n_env] f64,
+ * done [n_env] u8, mask [n_env, 6] u8. */
+int ahr_env_step(ahr_graph *g, const ahr_env_batch *env, const int32_t *dev_actions, int32_t max_steps,
+                 double repeat_penalty, float *dev_features, double *dev_rewards, uint8_t *dev_done, uint8_t *dev_mask,
+                 void *stream);
+
 /* ---- diagnostics used by the parity tests (not part of the reference seam) ---------------------- */
 /* full [nq, n_rows] score matrix of the tensor-core path (small inputs only) */
 int ahr_debug_tc_scores(ahr_index *idx, const void *dev_q, int32_t nq, float *dev_out, void *stream);
