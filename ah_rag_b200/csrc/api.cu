@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_shared.cuh"
 
 namespace ahr {
 
@@ -59,8 +60,9 @@ struct ahr_index {
   bool has_map = false;
   CUtensorMap map_x;   // box 64 x 256 rows (single-CTA K1)
   CUtensorMap map_x2;  // box 64 x 128 rows (CTA-pair K1: each CTA stages half a corpus tile)
-  int variant = 2;     // AHR_TC_VARIANT: 2 = CTA pairs (default), 1 = single CTA
-  int prefetch_tiles = 0;  // AHR_TC_PREFETCH: L2 prefetch distance in corpus tiles (0 = off, the default: measured slower)
+  int variant = 0;     // AHR_TC_VARIANT: 0 = by batch size (default), 1 = single CTA where it applies, 2 = CTA pairs
+  int seed_stride = 0;   // AHR_TC_SEED_STRIDE: sample pass over every n-th corpus tile seeds the thresholds.  Off by
+                         // default: exact and tested, but since the v5 epilogue it buys nothing measurable (history file)
   int force_slabs = 0;     // AHR_TC_SLABS: override the slab heuristic (experiments)
   DevBuf x_hi, x_lo;   // fp32 index: bf16 hi/lo halves of the rows (library-owned), maps below point at them
   CUtensorMap map_x2_lo;
@@ -133,8 +135,8 @@ int ahr_index_create(ahr_index **out, int device, int64_t n_rows, int32_t dim, i
     if (rc != AHR_OK) { idx->x_hi.release(); idx->x_lo.release(); delete idx; return rc; }
     idx->has_map = true;
   }
-  if (const char *e = getenv("AHR_TC_VARIANT")) idx->variant = atoi(e) == 1 ? 1 : 2;
-  if (const char *e = getenv("AHR_TC_PREFETCH")) idx->prefetch_tiles = std::max(0, atoi(e));
+  if (const char *e = getenv("AHR_TC_VARIANT")) idx->variant = std::min(2, std::max(0, atoi(e)));
+  if (const char *e = getenv("AHR_TC_SEED_STRIDE")) idx->seed_stride = std::max(0, atoi(e));
   if (const char *e = getenv("AHR_TC_SLABS")) idx->force_slabs = std::max(0, atoi(e));
   if (const char *e = getenv("AHR_TC_STATS")) idx->tc_stats = atoi(e) != 0;
   cudaError_t e = cudaMalloc(&idx->d_max_norm, sizeof(float));
@@ -178,34 +180,62 @@ static int exact_bruteforce(ahr_index *idx, const void *dev_q, const int32_t *q_
 }
 
 // tensor-core path: per-slab partial lists (K1) + per-query reduction, results [nq, k] with global ids
+//
+// Dispatch by batch size (profiles/r2_qsweep.md): up to 128 queries one CTA per tile (M = 128: the MMA takes half the
+// time of the HBM stream, the kernel runs at the memory roofline); above, CTA pairs (M = 256 per corpus tile read).
+// Queries are padded to a whole tile in a library buffer: TMA boxes that are mostly out of bounds are slow to fill
+// (Q = 1 took 2x the time of Q = 128 on the same corpus).
+// Optional sample pass (AHR_TC_SEED_STRIDE=n): a 1/n sample of the corpus tiles is scored first and its k-th best score
+// per query seeds every list's admission threshold in the main pass (tc_shared.cuh: seed_threshold).
 static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, float *out_scores, int64_t *out_ids,
                    float *dbg_scores, cudaStream_t st) {
   AHR_REQUIRE(idx->has_map, "index is not TMA-addressable (dim %% 8 != 0 or rows not 16-byte aligned)");
   AHR_REQUIRE((reinterpret_cast<uintptr_t>(dev_q) & 15) == 0, "queries must be 16-byte aligned");
   const bool split = idx->dtype == AHR_DTYPE_F32;  // fp32 operands: hi + lo bf16 halves, 3 operand segments
+  const bool pairs = split || k > 56 || idx->variant == 2 || (idx->variant == 0 && nq > 128);
+  const int32_t q_tile = pairs ? 256 : 128;
+  const int32_t nq_pad = (nq + q_tile - 1) / q_tile * q_tile;
   const void *q_hi = dev_q, *q_lo = nullptr;
+  const int64_t ne = (int64_t)nq * idx->dim, ne_pad = (int64_t)nq_pad * idx->dim;
   if (split) {
-    const int64_t ne = (int64_t)nq * idx->dim;
-    int rc0 = idx->q_split.reserve((size_t)ne * 4 + 512);
+    int rc0 = idx->q_split.reserve((size_t)ne_pad * 4 + 512);
     if (rc0 != AHR_OK) return rc0;
     uint8_t *base = reinterpret_cast<uint8_t *>(idx->q_split.ptr);
-    void *hi = base, *lo = base + (((size_t)ne * 2 + 255) & ~(size_t)255);
+    void *hi = base, *lo = base + (((size_t)ne_pad * 2 + 255) & ~(size_t)255);
     rc0 = split_f32_hi_lo(reinterpret_cast<const float *>(dev_q), ne, hi, lo, st);
     if (rc0 != AHR_OK) return rc0;
+    if (nq_pad > nq) {
+      AHR_CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<uint8_t *>(hi) + ne * 2, 0, (size_t)(ne_pad - ne) * 2, st));
+      AHR_CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<uint8_t *>(lo) + ne * 2, 0, (size_t)(ne_pad - ne) * 2, st));
+    }
     q_hi = hi;
     q_lo = lo;
+  } else if (nq_pad > nq) {
+    int rc0 = idx->q_split.reserve((size_t)ne_pad * 2);
+    if (rc0 != AHR_OK) return rc0;
+    AHR_CUDA_CHECK(cudaMemcpyAsync(idx->q_split.ptr, dev_q, (size_t)ne * 2, cudaMemcpyDeviceToDevice, st));
+    AHR_CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<uint8_t *>(idx->q_split.ptr) + ne * 2, 0, (size_t)(ne_pad - ne) * 2, st));
+    q_hi = idx->q_split.ptr;
   }
   const int64_t n_ctiles = (idx->n_rows + 255) / 256;
-  const bool pairs = idx->variant == 2 || split;
-  const int32_t n_qtiles = pairs ? (nq + 255) / 256 : (nq + 127) / 128;
+  const int32_t n_qtiles = nq_pad / q_tile;
   const int n_units = pairs ? std::max(1, idx->sm_count / 2) : idx->sm_count;  // CTA pairs or CTAs
   int S = tc_choose_slabs(n_qtiles, n_ctiles, n_units);
   if (idx->force_slabs > 0) S = (int)std::min<int64_t>(idx->force_slabs, n_ctiles);
-  const size_t n_part = (size_t)nq * S * k;
-  int rc = idx->ws.reserve(n_part * 8);
+  // sample pass geometry: every seed_stride-th corpus tile; worth it only when the sample is a few thousand rows
+  const int stride = (!dbg_scores && idx->seed_stride > 1 && n_ctiles / idx->seed_stride >= 32) ? idx->seed_stride : 1;
+  const int64_t n_stiles = (n_ctiles + stride - 1) / stride;
+  const int Ss = stride > 1 ? tc_choose_slabs(n_qtiles, n_stiles, n_units) : 0;
+  const size_t n_part = (size_t)nq * S * k, n_spart = (size_t)nq * Ss * k;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_ps = carve(n_part * 4), o_pi = carve(n_part * 4), o_ss = carve(n_spart * 4), o_si = carve(n_spart * 4),
+               o_ts = carve((size_t)nq * k * 4), o_ti = carve((size_t)nq * k * 8);
+  int rc = idx->ws.reserve(off);
   if (rc != AHR_OK) return rc;
-  float *ps = reinterpret_cast<float *>(idx->ws.ptr);
-  int32_t *pi = reinterpret_cast<int32_t *>(ps + n_part);
+  uint8_t *w = reinterpret_cast<uint8_t *>(idx->ws.ptr);
+  float *ps = reinterpret_cast<float *>(w + o_ps);
+  int32_t *pi = reinterpret_cast<int32_t *>(w + o_pi);
   idx->last_slabs = S;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (idx->profile) {
@@ -220,11 +250,29 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
     stats = reinterpret_cast<unsigned long long *>(idx->stats_buf.ptr);
     AHR_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)idx->sm_count * 64, st));
   }
-  if (pairs)
-    rc = tc2_topk_partials(idx->map_x2, split ? &idx->map_x2_lo : nullptr, q_hi, q_lo, idx->n_rows, idx->dim, nq, k, S,
-                           n_units, idx->prefetch_tiles, ps, pi, dbg_scores, stats, st);
-  else
-    rc = tc_topk_partials(idx->map_x, dev_q, idx->n_rows, idx->dim, nq, k, S, idx->sm_count, ps, pi, dbg_scores, st);
+  auto launch = [&](int slabs, float *part_s, int32_t *part_i, const TcExtra &ex, unsigned long long *stats_p) {
+    if (pairs)
+      return tc2_topk_partials(idx->map_x2, split ? &idx->map_x2_lo : nullptr, q_hi, q_lo, idx->n_rows, idx->dim, nq, k,
+                               slabs, n_units, part_s, part_i, dbg_scores, stats_p, ex, st);
+    return tc_topk_partials(idx->map_x, q_hi, idx->n_rows, idx->dim, nq, k, slabs, idx->sm_count, part_s, part_i,
+                            dbg_scores, ex, st);
+  };
+  TcExtra ex;
+  ex.q_rows = nq_pad;
+  if (stride > 1) {
+    float *ss = reinterpret_cast<float *>(w + o_ss), *ts = reinterpret_cast<float *>(w + o_ts);
+    int32_t *si = reinterpret_cast<int32_t *>(w + o_si);
+    int64_t *ti = reinterpret_cast<int64_t *>(w + o_ti);
+    TcExtra exs = ex;
+    exs.tile_stride = stride;
+    rc = launch(Ss, ss, si, exs, nullptr);
+    if (rc != AHR_OK) return rc;
+    rc = select_topk(ss, si, nullptr, (int64_t)Ss * k, (int64_t)Ss * k, nq, k, 0, false, ts, ti, st);
+    if (rc != AHR_OK) return rc;
+    ex.thr_src = ts + (k - 1);  // k-th best sample score of each query (-inf when the sample holds fewer than k rows)
+    ex.thr_stride = k;
+  }
+  rc = launch(S, ps, pi, ex, stats);
   if (rc != AHR_OK) return rc;
   if (idx->profile) {
     AHR_CUDA_CHECK(cudaEventRecord(e1, st));

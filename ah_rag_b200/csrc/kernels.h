@@ -15,15 +15,15 @@ int tc_make_corpus_map(CUtensorMap *map, const void *dev_rows, int64_t n_rows, i
 int tc_choose_slabs(int32_t n_qtiles, int64_t n_ctiles, int grid);
 int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows, int32_t dim, int32_t nq, int32_t k,
                      int32_t n_slabs, int grid, float *part_scores, int32_t *part_ids, float *dbg_scores,
-                     cudaStream_t stream);
+                     const struct TcExtra &ex, cudaStream_t stream);
 
 // ---- topk_tc2.cu (K1, CTA-pair variant) ----
 int tc2_make_corpus_map(CUtensorMap *map, const void *dev_rows, int64_t n_rows, int32_t dim);
 // map_x_lo / dev_q_lo non-null: fp32 operands split into hi + lo bf16 halves (3 operand segments per tile)
 int tc2_topk_partials(const CUtensorMap &map_x, const CUtensorMap *map_x_lo, const void *dev_q, const void *dev_q_lo,
                       int64_t n_rows, int32_t dim, int32_t nq, int32_t k, int32_t n_slabs, int n_pairs,
-                      int prefetch_tiles, float *part_scores, int32_t *part_ids, float *dbg_scores,
-                      unsigned long long *stats, cudaStream_t stream);
+                      float *part_scores, int32_t *part_ids, float *dbg_scores,
+                      unsigned long long *stats, const struct TcExtra &ex, cudaStream_t stream);
 // fp32 [n, dim] -> hi = bf16(x), lo = bf16(x - hi)
 int split_f32_hi_lo(const float *src, int64_t n_elems, void *hi, void *lo, cudaStream_t stream);
 

@@ -26,6 +26,17 @@ struct TcParams {
   int32_t *part_ids;     // row index inside this index (local), -1 = empty
   float *dbg_scores;     // optional [nq][n_rows] dump of the raw accumulators (tests)
   unsigned long long *stats;  // optional [grid][8] cycle counters: where each role waits (AHR_TC_STATS=1)
+  int32_t tile_stride;   // corpus tile i of this launch is tile i * tile_stride of the index (sample pass: > 1)
+  int32_t thr_stride;    // thr_src[q * thr_stride] = k-th best score of query q over a SAMPLE of the corpus rows
+  const float *thr_src;  // optional: seeds every list's admission threshold (see seed_threshold)
+};
+
+// Optional knobs of a K1 launch (host side).
+struct TcExtra {
+  int32_t q_rows = 0;        // rows addressable behind dev_q (>= nq; padded so TMA never fills out-of-bounds rows)
+  int32_t tile_stride = 1;
+  const float *thr_src = nullptr;
+  int32_t thr_stride = 0;
 };
 
 // mbarrier wait that optionally accounts the cycles spent waiting
@@ -83,6 +94,20 @@ __device__ __forceinline__ unsigned long long lds_u64(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_u64(uint32_t addr, unsigned long long v) {
   asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+
+// Sample-seeded admission threshold.  thr_src holds, per query, the k-th best score over a subset of the corpus rows
+// (a strided sample of tiles scored by this same kernel).  The global k-th best score is >= that value, so a row
+// scoring below it can never reach the global top-k: every list starts at the largest float below it instead of -inf
+// (the sample rows themselves are scanned again by the main pass and are admitted, scores being bit-identical).
+// Without it every (slab, query) list re-learns its threshold from scratch: ~k ln(rows per slab / k) appends and a
+// compaction every KLIST - k of them, front-loaded on every item.
+__device__ __forceinline__ float seed_threshold(const TcParams &p, int64_t q, bool row_valid) {
+  if (p.thr_src == nullptr || !row_valid) return -INFINITY;
+  const float s = p.thr_src[q * p.thr_stride];
+  if (!(s > -INFINITY)) return -INFINITY;       // fewer than k sample rows (or NaN): no bound
+  if (s == 0.0f) return -1.401298464e-45f;      // +-0 compare equal: step below both
+  return orderable_float(float_orderable(s) - 1u);
 }
 
 // All 32 lanes call.  Sorts the first `cnt` entries of the list at shared address `list_addr` (best first), pads the

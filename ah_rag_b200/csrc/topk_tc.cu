@@ -87,7 +87,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
             // queries are re-read by every corpus tile: keep them in L2; the corpus streams through
             tma_load_2d(a_dst, &map_q, &full[stage], kb * TC_BK, qt * TC_BM, kEvictLast);
-            tma_load_2d(b_dst, &map_x, &full[stage], kb * TC_BK, (int32_t)(ct * TC_BN), kEvictNormal);
+            tma_load_2d(b_dst, &map_x, &full[stage], kb * TC_BK, (int32_t)(ct * p.tile_stride * TC_BN), kEvictNormal);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -147,12 +147,12 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const int64_t q_first = (int64_t)qt * TC_BM + quad * 32;
       const int64_t q_global = q_first + lane;
       const bool row_valid = q_global < p.nq;
-      float thr = -INFINITY;  // admission threshold of this thread's row
+      float thr = seed_threshold(p, q_global, row_valid);  // admission threshold of this thread's row
       int cnt = 0;            // entries in this thread's list
       for (int64_t ct = t0; ct < t1; ++ct) {
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        const int64_t col0 = ct * TC_BN;
+        const int64_t col0 = ct * p.tile_stride * TC_BN;
         const int ncols = (int)min((int64_t)TC_BN, p.n_rows - col0);
         uint64_t *release_bar = &tempty[acc];
         epilogue_scan_tile<KLIST, TC_BN, DBG>(t_lane + (uint32_t)(acc * TC_BN), ncols, row_valid, k, col0, q_global, p,
@@ -261,16 +261,19 @@ static int tc_launch_t(const CUtensorMap &map_q, const CUtensorMap &map_x, const
 // Launch K1.  part_* must hold nq * n_slabs * k entries.  k <= 128.
 int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows, int32_t dim, int32_t nq, int32_t k,
                      int32_t n_slabs, int grid, float *part_scores, int32_t *part_ids, float *dbg_scores,
-                     cudaStream_t stream) {
+                     const TcExtra &ex, cudaStream_t stream) {
   AHR_REQUIRE(k >= 1 && k <= 120, "tensor-core top-k supports 1 <= k <= 120 (got %d)", k);
   AHR_REQUIRE(dim % 8 == 0, "bf16 index needs dim %% 8 == 0 for TMA (got %d)", dim);
   AHR_REQUIRE(n_rows < (int64_t)INT32_MAX - TC_BN, "rows per index shard must fit int32 (got %lld)", (long long)n_rows);
   CUtensorMap map_q;
-  int rc = make_bf16_tensor_map(&map_q, dev_q, nq, dim, TC_BM);
+  int rc = make_bf16_tensor_map(&map_q, dev_q, std::max(ex.q_rows, nq), dim, TC_BM);
   if (rc != AHR_OK) return rc;
   TcParams p;
   p.n_rows = n_rows;
-  p.n_ctiles = (n_rows + TC_BN - 1) / TC_BN;
+  p.tile_stride = std::max(1, ex.tile_stride);
+  p.n_ctiles = ((n_rows + TC_BN - 1) / TC_BN + p.tile_stride - 1) / p.tile_stride;
+  p.thr_src = ex.thr_src;
+  p.thr_stride = ex.thr_stride;
   p.nq = nq;
   p.dim = dim;
   p.n_qtiles = (nq + TC_BM - 1) / TC_BM;

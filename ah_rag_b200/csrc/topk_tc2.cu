@@ -13,8 +13,15 @@
 //   leader CTA (rank 0)      : issues every tcgen05.mma; its full barrier collects the TMA bytes of BOTH CTAs;
 //                              tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs;
 //                              the epilogue warps of both CTAs release the accumulator on the leader's barrier.
-//   L2 prefetch              : the producer issues cp.async.bulk.prefetch.tensor for the B half-tile a few
-//                              tiles ahead, so HBM latency is hidden without spending shared memory.
+//   operand rings            : A (queries, re-read from L2 for every corpus tile) and B (corpus, streamed from HBM)
+//                              have SEPARATE rings: NA slots of A, NB > NA slots of B.  One producer thread issues
+//                              B(t) and then A(t - (NB - NA)): both wait for the same event (the MMA finished k-block
+//                              t - NB), so nothing blocks, but the HBM stream runs NB k-blocks ahead while the L2
+//                              stream only needs NA.  Measured (profiles/r1_k1_epilogue_history.md, "rings"):
+//                              NA = 3 starves the tensor-bound workload (L2 latency under load > 3 k-blocks) and a
+//                              deeper corpus ring does not help the HBM-bound one, so the default is NA = NB = 4;
+//                              what did help both was taking the integer divisions out of the producer's loop.
+//                              L2 prefetch (cp.async.bulk.prefetch.tensor) was tried as well and is slower.
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_shared.cuh"
@@ -26,22 +33,26 @@ constexpr int T2_BN = 256;                      // corpus rows per tile (pair)
 constexpr int T2_BN_HALF = 128;                 // corpus rows staged by each CTA
 constexpr uint32_t T2_A_BYTES = T2_BM * TC_BK * 2;        // 16 KB
 constexpr uint32_t T2_B_BYTES = T2_BN_HALF * TC_BK * 2;   // 16 KB
-constexpr uint32_t T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
 
-template <int KLIST, int STAGES, bool DBG>
+template <int KLIST, int NA, int NB, bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
-                const __grid_constant__ CUtensorMap map_q_lo, const __grid_constant__ CUtensorMap map_x_lo, TcParams p,
-                int prefetch_tiles) {
+                const __grid_constant__ CUtensorMap map_q_lo, const __grid_constant__ CUtensorMap map_x_lo, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *tiles = smem;
-  unsigned long long *lists = reinterpret_cast<unsigned long long *>(tiles + STAGES * T2_STAGE_BYTES);  // [128][KLIST] keys
+  static_assert(NB >= NA && NA >= 1, "the corpus ring is at least as deep as the query ring");
+  constexpr int LAG = NB - NA;  // the producer issues A(t - LAG) right after B(t)
+  uint8_t *a_tiles = smem;                                // [NA][16 KB]
+  uint8_t *b_tiles = smem + NA * T2_A_BYTES;              // [NB][16 KB]
+  unsigned long long *lists = reinterpret_cast<unsigned long long *>(b_tiles + NB * T2_B_BYTES);  // [128][KLIST] keys
   float *scratch = reinterpret_cast<float *>(lists + KLIST * T2_BM);  // [4 warps][32 columns][32 lanes] chunk scratch
   uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 4 * 32 * 32);
-  uint64_t *full = bars;                 // [STAGES] leader's copy is the live one (bytes of both CTAs)
-  uint64_t *empty = bars + STAGES;       // [STAGES] per CTA: MMA done reading this stage
-  uint64_t *tfull = bars + 2 * STAGES;   // [2] per CTA: accumulator stage complete
+  uint64_t *full_a = bars;               // [NA] leader's copy is the live one (bytes of both CTAs)
+  uint64_t *full_b = full_a + NA;        // [NB]
+  uint64_t *done = full_b + NB;          // [NB] per CTA: the MMA finished k-block t (slot t mod NB): frees B slot t mod NB
+                                         //      and A slot t mod NA -- ONE commit per k-block (a second one per
+                                         //      k-block cost 30 % on the tensor-bound workload)
+  uint64_t *tfull = done + NB;           // [2] per CTA: accumulator stage complete
   uint64_t *tempty = tfull + 2;          // [2] leader's copy: both epilogues drained the stage
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
@@ -63,9 +74,10 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) {
-        mbar_init(&full[s], 1);   // the leader's arrive.expect_tx; TMA bytes of both CTAs complete it
-        mbar_init(&empty[s], 1);  // one multicast commit
+      for (int s = 0; s < NA; ++s) mbar_init(&full_a[s], 1);  // the leader's arrive.expect_tx; TMA bytes of both CTAs
+      for (int s = 0; s < NB; ++s) {
+        mbar_init(&full_b[s], 1);
+        mbar_init(&done[s], 1);  // one multicast commit
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);   // one multicast commit
@@ -84,33 +96,67 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
       unsigned long long w_empty = 0;
       unsigned long long *acct = p.stats ? &w_empty : nullptr;
-      for (int item = cluster_id; item < n_items; item += n_clusters) {
-        const int slab = item / p.n_qtiles, qt = item % p.n_qtiles;
-        int64_t t0, t1;
-        slab_range(p, slab, t0, t1);
-        const int32_t q_row0 = qt * (2 * T2_BM) + (int32_t)rank * T2_BM;
-        for (int64_t ct = t0; ct < t1; ++ct) {
-          const int32_t x_row0 = (int32_t)(ct * T2_BN) + (int32_t)rank * T2_BN_HALF;
-          const bool pf = prefetch_tiles > 0 && ct + prefetch_tiles < t1;
-          for (int t = 0; t < n_kblocks; ++t) {
-            const int seg = t / kb_per_seg, kb = t - seg * kb_per_seg;
-            const CUtensorMap *mq = seg == 1 ? &map_q_lo : &map_q;  // (q_hi,x_hi) (q_lo,x_hi) (q_hi,x_lo)
-            const CUtensorMap *mx = seg == 2 ? &map_x_lo : &map_x;
-            if (pf) tma_prefetch_2d(mx, kb * TC_BK, x_row0 + prefetch_tiles * T2_BN);
-            mbar_wait_acct(&empty[stage], phase ^ 1, acct);
-            uint8_t *a_dst = tiles + stage * T2_STAGE_BYTES;
-            uint8_t *b_dst = a_dst + T2_A_BYTES;
-            const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
-            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * T2_STAGE_BYTES);
-            tma_load_2d_2sm(a_dst, mq, full_leader, kb * TC_BK, q_row0, kEvictLast);
-            tma_load_2d_2sm(b_dst, mx, full_leader, kb * TC_BK, x_row0, kEvictNormal);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
+      // a cursor walks this pair's (item, corpus tile, segment, k-block) sequence; the A cursor trails the B cursor by
+      // LAG.  No division on the per-k-block path: this single thread has to issue a block every ~500 cycles and an
+      // integer division is ~100 cycles of dependent latency (three of them cost 26 % on the tensor-bound workload).
+      struct Cursor {
+        int item, seg, kb;
+        int32_t q_row0;
+        int64_t ct, t1;
+        bool done;
+      };
+      auto open_item = [&](Cursor &c) {
+        c.done = c.item >= n_items;
+        if (c.done) return;
+        const int slab = c.item / p.n_qtiles, qt = c.item - slab * p.n_qtiles;
+        int64_t t0;
+        slab_range(p, slab, t0, c.t1);
+        c.ct = t0;
+        c.seg = 0;
+        c.kb = 0;
+        c.q_row0 = qt * (2 * T2_BM) + (int32_t)rank * T2_BM;
+      };
+      auto advance = [&](Cursor &c) {
+        if (++c.kb < kb_per_seg) return;
+        c.kb = 0;
+        if (++c.seg < p.n_seg) return;
+        c.seg = 0;
+        if (++c.ct < c.t1) return;
+        c.item += n_clusters;
+        open_item(c);
+      };
+      Cursor ca{cluster_id, 0, 0, 0, 0, 0, false}, cb{cluster_id, 0, 0, 0, 0, 0, false};
+      open_item(ca);
+      open_item(cb);
+      int sa = 0, sb = 0;
+      uint32_t pb = 0;
+      const uint32_t full_a0 = mapa_u32(smem_u32(&full_a[0]), 0), full_b0 = mapa_u32(smem_u32(&full_b[0]), 0);  // leader's
+      // A(j) needs "k-block j - NA finished" = the event B(j + LAG) waits for: the caller has just waited for it
+      auto issue_a = [&]() {
+        const CUtensorMap *mq = ca.seg == 1 ? &map_q_lo : &map_q;  // (q_hi,x_hi) (q_lo,x_hi) (q_hi,x_lo)
+        if (leader) mbar_arrive_expect_tx(&full_a[sa], 2 * T2_A_BYTES);
+        // queries are re-read by every corpus tile: keep them in L2
+        tma_load_2d_2sm(a_tiles + sa * T2_A_BYTES, mq, full_a0 + sa * 8, ca.kb * TC_BK, ca.q_row0, kEvictLast);
+        if (++sa == NA) sa = 0;
+        advance(ca);
+      };
+      int lead = 0;
+      while (!cb.done) {
+        const CUtensorMap *mx = cb.seg == 2 ? &map_x_lo : &map_x;
+        const int32_t x_row0 = (int32_t)cb.ct * (p.tile_stride * T2_BN) + (int32_t)rank * T2_BN_HALF;
+        mbar_wait_acct(&done[sb], pb ^ 1, acct);  // k-block t - NB finished
+        if (leader) mbar_arrive_expect_tx(&full_b[sb], 2 * T2_B_BYTES);
+        tma_load_2d_2sm(b_tiles + sb * T2_B_BYTES, mx, full_b0 + sb * 8, cb.kb * TC_BK, x_row0, kEvictNormal);  // streams through
+        if (++sb == NB) { sb = 0; pb ^= 1; }
+        advance(cb);
+        if (lead < LAG) ++lead; else issue_a();
+      }
+      while (!ca.done) {  // the last LAG query blocks: keep walking the `done` ring as if B blocks followed
+        mbar_wait_acct(&done[sb], pb ^ 1, acct);
+        if (++sb == NB) { sb = 0; pb ^= 1; }
+        issue_a();
       }
       if (p.stats) p.stats[blockIdx.x * 8 + 0] = w_empty;
     }
@@ -119,8 +165,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * T2_BM, T2_BN);  // M = 256 across the pair, N = 256
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       unsigned long long w_full = 0, w_tempty = 0;
@@ -134,17 +180,18 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * T2_BN;
           for (int kb = 0; kb < n_kblocks; ++kb) {
-            mbar_wait_acct(&full[stage], phase, p.stats ? &w_full : nullptr);
+            mbar_wait_acct(&full_b[sb], pb, p.stats ? &w_full : nullptr);
+            mbar_wait_acct(&full_a[sa], pa, p.stats ? &w_full : nullptr);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(tiles + stage * T2_STAGE_BYTES);
-            const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-            const uint64_t b_desc = make_smem_desc_sw128(a_addr + T2_A_BYTES);
+            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(a_tiles + sa * T2_A_BYTES));
+            const uint64_t b_desc = make_smem_desc_sw128(smem_u32(b_tiles + sb * T2_B_BYTES));
 #pragma unroll
             for (int k4 = 0; k4 < TC_BK / 16; ++k4)
               umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), idesc,
                                (kb | k4) != 0 ? 1u : 0u);
-            umma_commit_2sm(&empty[stage], 0x3);  // frees this stage in both CTAs
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            umma_commit_2sm(&done[sb], 0x3);  // frees A slot sa and B slot sb in both CTAs
+            if (++sa == NA) { sa = 0; pa ^= 1; }
+            if (++sb == NB) { sb = 0; pb ^= 1; }
           }
           umma_commit_2sm(&tfull[acc], 0x3);  // accumulator ready in both CTAs
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -175,12 +222,12 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int64_t q_first = (int64_t)qt * (2 * T2_BM) + (int64_t)rank * T2_BM + quad * 32;
       const int64_t q_global = q_first + lane;
       const bool row_valid = q_global < p.nq;
-      float thr = -INFINITY;  // admission threshold of this thread's row
+      float thr = seed_threshold(p, q_global, row_valid);  // admission threshold of this thread's row
       int cnt = 0;            // entries in this thread's list
       for (int64_t ct = t0; ct < t1; ++ct) {
         mbar_wait_acct(&tfull[acc], acc_phase, acct);
         tc_fence_after();
-        const int64_t col0 = ct * T2_BN;
+        const int64_t col0 = ct * p.tile_stride * T2_BN;
         const int ncols = (int)min((int64_t)T2_BN, p.n_rows - col0);
         const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[acc]), 0);
         epilogue_scan_tile<KLIST, T2_BN, DBG>(t_lane + (uint32_t)(acc * T2_BN), ncols, row_valid, k, col0, q_global, p,
@@ -218,25 +265,24 @@ int tc2_make_corpus_map(CUtensorMap *map, const void *dev_rows, int64_t n_rows, 
   return make_bf16_tensor_map(map, dev_rows, n_rows, dim, T2_BN_HALF);
 }
 
-template <int KLIST, int STAGES>
+template <int KLIST, int NA, int NB>
 static constexpr size_t tc2_smem_bytes() {
-  return 1024 + (size_t)STAGES * T2_STAGE_BYTES + (size_t)KLIST * T2_BM * 8 + 4 * 32 * 32 * 4 + 256;
+  return 1024 + (size_t)NA * T2_A_BYTES + (size_t)NB * T2_B_BYTES + (size_t)KLIST * T2_BM * 8 + 4 * 32 * 32 * 4 + 256;
 }
 
-template <int KLIST, int STAGES, bool DBG>
+template <int KLIST, int NA, int NB, bool DBG>
 static int tc2_launch_t(const CUtensorMap &map_q, const CUtensorMap &map_x, const CUtensorMap &map_q_lo,
-                        const CUtensorMap &map_x_lo, const TcParams &p, int n_clusters, int prefetch_tiles,
+                        const CUtensorMap &map_x_lo, const TcParams &p, int n_clusters,
                         cudaStream_t stream) {
   static bool configured = false;
-  constexpr size_t smem = tc2_smem_bytes<KLIST, STAGES>();
+  constexpr size_t smem = tc2_smem_bytes<KLIST, NA, NB>();
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
   if (!configured) {
-    AHR_CUDA_CHECK(cudaFuncSetAttribute(topk_tc2_kernel<KLIST, STAGES, DBG>,
+    AHR_CUDA_CHECK(cudaFuncSetAttribute(topk_tc2_kernel<KLIST, NA, NB, DBG>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  topk_tc2_kernel<KLIST, STAGES, DBG><<<2 * n_clusters, TC_THREADS, smem, stream>>>(map_q, map_x, map_q_lo, map_x_lo, p,
-                                                                                    prefetch_tiles);
+  topk_tc2_kernel<KLIST, NA, NB, DBG><<<2 * n_clusters, TC_THREADS, smem, stream>>>(map_q, map_x, map_q_lo, map_x_lo, p);
   AHR_KERNEL_CHECK();
   return AHR_OK;
 }
@@ -244,17 +290,18 @@ static int tc2_launch_t(const CUtensorMap &map_q, const CUtensorMap &map_x, cons
 // Launch the CTA-pair K1.  part_* must hold nq * n_slabs * k entries; n_pairs = SM count / 2.
 int tc2_topk_partials(const CUtensorMap &map_x, const CUtensorMap *map_x_lo, const void *dev_q, const void *dev_q_lo,
                       int64_t n_rows, int32_t dim, int32_t nq, int32_t k, int32_t n_slabs, int n_pairs,
-                      int prefetch_tiles, float *part_scores, int32_t *part_ids, float *dbg_scores,
-                      unsigned long long *stats, cudaStream_t stream) {
+                      float *part_scores, int32_t *part_ids, float *dbg_scores,
+                      unsigned long long *stats, const TcExtra &ex, cudaStream_t stream) {
   AHR_REQUIRE(k >= 1 && k <= 120, "tensor-core top-k supports 1 <= k <= 120 (got %d)", k);
   AHR_REQUIRE(dim % 8 == 0, "bf16 index needs dim %% 8 == 0 for TMA (got %d)", dim);
   AHR_REQUIRE(n_rows < (int64_t)INT32_MAX - T2_BN, "rows per index shard must fit int32 (got %lld)", (long long)n_rows);
   CUtensorMap map_q, map_q_lo;
-  int rc = make_bf16_tensor_map(&map_q, dev_q, nq, dim, T2_BM);
+  const int32_t q_rows = std::max(ex.q_rows, nq);
+  int rc = make_bf16_tensor_map(&map_q, dev_q, q_rows, dim, T2_BM);
   if (rc != AHR_OK) return rc;
   const bool split = map_x_lo != nullptr && dev_q_lo != nullptr;  // fp32 operands as hi + lo bf16 halves
   if (split) {
-    rc = make_bf16_tensor_map(&map_q_lo, dev_q_lo, nq, dim, T2_BM);
+    rc = make_bf16_tensor_map(&map_q_lo, dev_q_lo, q_rows, dim, T2_BM);
     if (rc != AHR_OK) return rc;
   } else {
     map_q_lo = map_q;
@@ -263,7 +310,10 @@ int tc2_topk_partials(const CUtensorMap &map_x, const CUtensorMap *map_x_lo, con
   TcParams p;
   p.n_seg = split ? 3 : 1;
   p.n_rows = n_rows;
-  p.n_ctiles = (n_rows + T2_BN - 1) / T2_BN;
+  p.tile_stride = std::max(1, ex.tile_stride);
+  p.n_ctiles = ((n_rows + T2_BN - 1) / T2_BN + p.tile_stride - 1) / p.tile_stride;
+  p.thr_src = ex.thr_src;
+  p.thr_stride = ex.thr_stride;
   p.nq = nq;
   p.dim = dim;
   p.n_qtiles = (nq + 2 * T2_BM - 1) / (2 * T2_BM);
@@ -278,16 +328,17 @@ int tc2_topk_partials(const CUtensorMap &map_x, const CUtensorMap *map_x_lo, con
   if (n_clusters < 1) n_clusters = 1;
   if (dbg_scores) {
     AHR_REQUIRE(k <= 56, "debug score dump supports k <= 56");
-    return tc2_launch_t<64, 4, true>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, prefetch_tiles, stream);
+    return tc2_launch_t<64, 4, 4, true>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
   }
   if (k <= 56) {  // the list needs room beyond k: KLIST - k appends amortise one compaction
-    // 4 stages (128 KB) + 64 KB of lists leave ~30 KB of the SM's 228 KB to L1, which is where the slow path's
-    // local-memory chunk copy lives: measured 64.9 ms vs 71.4 ms with 5 stages (L1 ~3 KB) on c3, equal on c4.
-    static const int stages = getenv("AHR_TC_STAGES") ? atoi(getenv("AHR_TC_STAGES")) : 4;  // experiments: 3 | 4
-    if (stages == 3) return tc2_launch_t<64, 3, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, prefetch_tiles, stream);
-    return tc2_launch_t<64, 4, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, prefetch_tiles, stream);
+    // rings: 4 x 16 KB of queries + 4 x 16 KB of corpus (128 KB), next to 64 KB of lists and 16 KB of chunk scratch;
+    // the rest of the SM's 228 KB stays L1.  AHR_TC_RING = "35" | "36" select deeper corpus rings (experiments).
+    static const int ring = getenv("AHR_TC_RING") ? atoi(getenv("AHR_TC_RING")) : 44;
+    if (ring == 35) return tc2_launch_t<64, 3, 5, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
+    if (ring == 36) return tc2_launch_t<64, 3, 6, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
+    return tc2_launch_t<64, 4, 4, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
   }
-  return tc2_launch_t<128, 2, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, prefetch_tiles, stream);
+  return tc2_launch_t<128, 2, 2, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
 }
 
 }  // namespace ahr

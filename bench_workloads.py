@@ -98,6 +98,70 @@ def run_c4(dev):
     del idx, X, Q
 
 
+def run_qsweep(dev):
+    """K1 over one c4 shard (12.5M x 768 bf16) for query batches from 1 to 1024: which roofline binds where."""
+    n, dim, k = 12_500_000, 768, 50
+    hbm, tf, src = peaks()
+    X = unit_bf16(n, dim, 1234, dev)
+    Qall = unit_bf16(1024, dim, 5678, dev)
+    for variant in os.environ.get("AHR_SWEEP_VARIANTS", "2,1").split(","):
+        os.environ["AHR_TC_VARIANT"] = variant
+        idx = engine.VectorIndex(X)
+        for nq in [int(x) for x in os.environ.get("AHR_SWEEP_NQ", "1,8,32,64,128,256,512,1024").split(",")]:
+            Q = Qall[:nq].contiguous()
+            idx.set_profiling(True)
+            ms = timed(lambda: idx.topk(Q, k, mode="bf16"), steps=5, warmup=2)
+            prof = idx.get_profile()
+            idx.set_profiling(False)
+            k1 = prof["k1_ms_total"] / max(1, prof["k1_launches"])
+            print(json.dumps({"workload": "qsweep 12.5M x 768 bf16, k=50", "variant": int(variant), "nq": nq, "ms": round(ms, 4),
+                              "k1_ms": round(k1, 4), "n_slabs": prof["n_slabs"], "hbm_gbs": round(2.0 * n * dim / (k1 * 1e-3) / 1e9, 1),
+                              "hbm_frac": round(2.0 * n * dim / (k1 * 1e-3) / 1e9 / hbm, 3),
+                              "tflops": round(2.0 * nq * n * dim / (k1 * 1e-3) / 1e12, 1), "qps": round(nq / ms * 1e3, 1)}), flush=True)
+        del idx
+    os.environ.pop("AHR_TC_VARIANT", None)
+    del X
+
+
+def run_shard8(dev):
+    """The per-rank work of c3 on 8 GPUs: 1.25M x 1024 rows, the full 4096-query batch (strong scaling)."""
+    n, dim, nq, k = 1_250_000, 1024, 4096, 50
+    _, tf, _ = peaks()
+    X, Q = unit_bf16(n, dim, 1234, dev), unit_bf16(nq, dim, 5678, dev)
+    idx = engine.VectorIndex(X)
+    idx.set_profiling(True)
+    ms = timed(lambda: idx.topk(Q, k, mode="bf16"), steps=10, warmup=3)
+    prof = idx.get_profile()
+    k1 = prof["k1_ms_total"] / max(1, prof["k1_launches"])
+    print(json.dumps({"workload": "c3 shard at 8 GPUs: 1.25M x 1024 bf16, Q=4096, k=50", "ms": round(ms, 4), "k1_ms": round(k1, 4),
+                      "n_slabs": prof["n_slabs"], "tflops": round(2.0 * nq * n * dim / (k1 * 1e-3) / 1e12, 1),
+                      "frac_of_sustained_peak": round(2.0 * nq * n * dim / (k1 * 1e-3) / 1e12 / tf, 3)}), flush=True)
+    del idx, X, Q
+
+
+def run_adv(dev):
+    """Adversarial row order: 1.25M x 1024 rows sorted by ascending similarity to the centre of a tight query cluster, so
+    for every query almost every row beats everything seen before it (worst case for the epilogue's lists)."""
+    n, dim, nq, k = 1_250_000, 1024, 4096, 50
+    X = unit_bf16(n, dim, 1234, dev)
+    g = torch.Generator(device=dev).manual_seed(77)
+    c = torch.randn((dim,), generator=g, device=dev)
+    c /= c.norm()
+    Q = c[None, :] + 0.02 * torch.randn((nq, dim), generator=g, device=dev)
+    Q = (Q / Q.norm(dim=1, keepdim=True)).to(torch.bfloat16).contiguous()
+    order = torch.argsort(X.float() @ c)
+    Xs = X[order].contiguous()
+    del X
+    for stride in ("0", "64"):
+        os.environ["AHR_TC_SEED_STRIDE"] = stride
+        idx = engine.VectorIndex(Xs)
+        ms = timed(lambda: idx.topk(Q, k, mode="bf16"), steps=5, warmup=2)
+        print(json.dumps({"workload": "adversarial order: 1.25M x 1024 bf16 sorted by similarity to the query cluster, Q=4096, k=50",
+                          "seed_stride": int(stride), "ms": round(ms, 3)}), flush=True)
+        del idx
+    os.environ.pop("AHR_TC_SEED_STRIDE", None)
+
+
 def make_c5_graph(dev, scale=1.0, seed=42):
     """CSR arrays on the device: [entities | L1 | L2 | hyperedges]; ~25 directed edges per node at scale 1."""
     g = torch.Generator(device=dev).manual_seed(seed)
@@ -288,6 +352,12 @@ def main():
             run_c5(dev, float(os.environ.get("AHR_C5_SCALE", "1.0")))
         elif w == "c2":
             run_c2(dev)
+        elif w == "shard8":
+            run_shard8(dev)
+        elif w == "adv":
+            run_adv(dev)
+        elif w == "qsweep":
+            run_qsweep(dev)
         torch.cuda.empty_cache()
 
 

@@ -108,10 +108,43 @@ def test_single_cta_variant_matches(engine, monkeypatch):
     X = torch.from_numpy(synth.unit_rows(n, dim, 51)).cuda().to(torch.bfloat16).contiguous()
     Q = torch.from_numpy(synth.unit_rows(nq, dim, 52)).cuda().to(torch.bfloat16).contiguous()
     idx = engine.VectorIndex(X)  # reads the variant at creation
-    monkeypatch.delenv("AHR_TC_VARIANT")
+    monkeypatch.setenv("AHR_TC_VARIANT", "2")
     ref = engine.VectorIndex(X)
+    monkeypatch.delenv("AHR_TC_VARIANT")
     a, b = idx.topk(Q, k, mode="bf16"), ref.topk(Q, k, mode="bf16")
     assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+
+
+@pytest.mark.parametrize("nq", [1, 100, 129, 300])
+def test_variant_dispatch_and_sample_seeded_thresholds(engine, monkeypatch, nq):
+    """Batch-size dispatch (one CTA per tile up to 128 queries, CTA pairs above) and the sample pass that seeds the
+    admission thresholds must not change a single bit of the answer: every (variant, stride) combination returns the
+    same scores and ids, on a corpus full of exact ties (duplicated rows) in adversarial order."""
+    n, dim, k = 40_000 + 77, 64, 50
+    base = synth.unit_rows(1500, dim, 61, clustered=6)
+    Qn = synth.unit_rows(nq, dim, 62, clustered=6)
+    Xn = base[np.arange(n) % 1500]                     # every row appears ~27 times: ties at every rank
+    order = np.argsort(Xn @ Qn[0], kind="stable")      # ascending similarity to query 0
+    Xn = np.ascontiguousarray(Xn[order])
+    X = torch.from_numpy(Xn).cuda().to(torch.bfloat16).contiguous()
+    Q = torch.from_numpy(Qn).cuda().to(torch.bfloat16).contiguous()
+    bits = lambda t: t.view(torch.int16).cpu().numpy().view(np.uint16)
+    rs, ri = exact.exact_topk(bits(X), bits(Q), k)
+    outs = {}
+    for variant in ("0", "1", "2"):
+        for stride in ("0", "4", "64"):
+            monkeypatch.setenv("AHR_TC_VARIANT", variant)
+            monkeypatch.setenv("AHR_TC_SEED_STRIDE", stride)
+            idx = engine.VectorIndex(X)
+            s, i = idx.topk(Q, k, mode="bf16")
+            outs[(variant, stride)] = (s.cpu().numpy(), i.cpu().numpy())
+            es, ei = idx.topk(Q, k, mode="exact")
+            assert np.array_equal(ei.cpu().numpy(), ri), (variant, stride)
+            assert np.array_equal(es.cpu().numpy().view(np.uint32), rs.view(np.uint32)), (variant, stride)
+    s0, i0 = outs[("2", "0")]
+    assert np.allclose(s0, rs, rtol=1e-2, atol=1e-4)
+    for key, (s, i) in outs.items():
+        assert np.array_equal(s.view(np.uint32), s0.view(np.uint32)) and np.array_equal(i, i0), key
 
 
 def test_csr_graph_at_scale_vs_array_oracle(engine):
