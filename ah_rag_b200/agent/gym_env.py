@@ -182,43 +182,11 @@ class DeviceVecAHRAGGymEnv:
 
     def __init__(self, hg: HierarchicalGraph, n_envs: int, max_steps: int = 6, repeat_penalty: float = 0.02,
                  cap_selection: Optional[int] = None, cap_frontier: Optional[int] = None) -> None:
-        import ctypes
-        import torch
-        from .. import _lib
-        self._torch, self._ctypes, self._libmod = torch, ctypes, _lib
+        from ..engine import EnvBatchState
         self.hg = hg
-        self.n_envs = int(n_envs)
-        self.max_steps = max(1, int(max_steps))
-        self.repeat_penalty = float(repeat_penalty)
         self.csr = hg._device_graph()["csr"]
-        dev = self.csr.device
-        B = self.n_envs
-        # an episode adds at most 3 selected and 10 frontier nodes per step (gym_env.py:94-100)
-        self.cap_sel = int(cap_selection or max(3 * (self.max_steps + 2), 32))
-        self.cap_fr = int(cap_frontier or (10 + 10 * (self.max_steps + 2)))
-        i32 = dict(dtype=torch.int32, device=dev)
-        self.state = {
-            "sel_ids": torch.zeros((B, self.cap_sel), **i32), "sel_cnt": torch.zeros((B,), **i32),
-            "fr_ids": torch.zeros((B, self.cap_fr), **i32), "fr_cnt": torch.zeros((B,), **i32),
-            "shown_ids": torch.full((B, 10), -1, **i32),
-            "shown_score": torch.zeros((B, 10), dtype=torch.float64, device=dev),
-            "shown_sem": torch.zeros((B, 10), dtype=torch.float64, device=dev),
-            "shown_cnt": torch.zeros((B,), **i32), "n_seeds": torch.zeros((B,), **i32),
-            "obs_step": torch.zeros((B,), **i32), "obs_sel": torch.zeros((B,), **i32),
-            "obs_fr": torch.zeros((B,), **i32), "env_steps": torch.zeros((B,), **i32),
-            "gym_steps": torch.zeros((B,), **i32), "last_action": torch.full((B,), -1, **i32),
-            "done": torch.zeros((B,), dtype=torch.uint8, device=dev), "overflow": torch.zeros((1,), **i32),
-        }
-        self.features = torch.zeros((B, self.FEATS), dtype=torch.float32, device=dev)
-        self.mask = torch.zeros((B, N_ACTIONS), dtype=torch.uint8, device=dev)
-        self.rewards = torch.zeros((B,), dtype=torch.float64, device=dev)
-        self.done = torch.zeros((B,), dtype=torch.uint8, device=dev)
-        eb = _lib.EnvBatch()
-        eb.n_env, eb.cap_sel, eb.cap_fr, eb.reserved = B, self.cap_sel, self.cap_fr, 0
-        for name, t in self.state.items():
-            setattr(eb, name, t.data_ptr())
-        self._eb = eb
-        self._ready = False
+        self.batch = EnvBatchState(self.csr, n_envs, max_steps, repeat_penalty, cap_selection, cap_frontier)
+        self.n_envs, self.max_steps, self.repeat_penalty = self.batch.n_envs, self.batch.max_steps, self.batch.repeat_penalty
 
     def __len__(self) -> int:
         return self.n_envs
@@ -227,12 +195,13 @@ class DeviceVecAHRAGGymEnv:
     def action_size(self) -> int:
         return N_ACTIONS
 
-    def _stream(self) -> int:
-        return self._torch.cuda.current_stream(self.csr.device).cuda_stream
+    @property
+    def state(self):
+        return self.batch.state
 
     def reset(self, query_embeddings):
         """``query_embeddings`` [B, d] -> (features [B, 84] float32, action mask [B, 6] uint8), device tensors."""
-        torch, ct = self._torch, self._ctypes
+        import torch
         if len(query_embeddings) != self.n_envs:
             raise ValueError(f"expected {self.n_envs} query embeddings, got {len(query_embeddings)}")
         hg = self.hg
@@ -242,7 +211,7 @@ class DeviceVecAHRAGGymEnv:
         n_index = len(hg._device_index(db_path)["store"].ids)
         top_k = 5
         dev = self.csr.device
-        if n_index == 0:
+        if n_index == 0:  # un-built index: empty anchor, as the reference's empty collection returns
             out = {"nodes": torch.full((self.n_envs, top_k), -1, dtype=torch.int32, device=dev),
                    "semantic": torch.zeros((self.n_envs, top_k), dtype=torch.float64, device=dev),
                    "score": torch.zeros((self.n_envs, top_k), dtype=torch.float64, device=dev),
@@ -251,49 +220,31 @@ class DeviceVecAHRAGGymEnv:
         else:
             out, rows = hg._device_search(query_embeddings, top_k, params, False, db_path)
             n_seeds = int(rows.shape[1])
-        if self.n_envs:
-            with torch.cuda.device(dev):
-                self._libmod.check(self.csr.lib.ahr_env_reset(
-                    self.csr._h, ct.byref(self._eb), out["nodes"].data_ptr(), out["semantic"].data_ptr(),
-                    out["score"].data_ptr(), out["count"].data_ptr(), top_k, n_seeds, self.features.data_ptr(),
-                    self.mask.data_ptr(), self._stream()), "ahr_env_reset")
-        self._ready = True
-        return self.features, self.mask
+        return self.batch.reset(out, n_seeds)
 
     def action_masks(self):
-        return self.mask
+        return self.batch.mask
 
     def step(self, actions):
         """``actions`` [B] ints in 0..5 (device int32 tensor preferred) ->
         (features [B, 84], rewards [B] f64, done [B] u8, mask [B, 6] u8) -- device tensors, overwritten every step."""
-        torch, ct = self._torch, self._ctypes
-        if not self._ready:
-            raise RuntimeError("Call reset() first")
-        dev = self.csr.device
+        import torch
         a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions, dtype=np.int32))
-        a = a.to(device=dev, dtype=torch.int32).contiguous()
-        if a.shape != (self.n_envs,):
+        if tuple(a.shape) != (self.n_envs,):
             raise ValueError(f"actions must have shape ({self.n_envs},)")
-        if self.n_envs:
-            with torch.cuda.device(dev):
-                self._libmod.check(self.csr.lib.ahr_env_step(
-                    self.csr._h, ct.byref(self._eb), a.data_ptr(), self.max_steps, self.repeat_penalty,
-                    self.features.data_ptr(), self.rewards.data_ptr(), self.done.data_ptr(), self.mask.data_ptr(),
-                    self._stream()), "ahr_env_step")
-        return self.features, self.rewards, self.done, self.mask
+        return self.batch.step(a.to(device=self.csr.device, dtype=torch.int32).contiguous())
 
     def check_overflow(self) -> None:
-        """Raises if a selection / frontier list outgrew its capacity (synchronises)."""
-        if int(self.state["overflow"].item()):
-            raise RuntimeError("DeviceVecAHRAGGymEnv: selection/frontier capacity exceeded; raise cap_selection/cap_frontier")
+        self.batch.check_overflow()
+
+    def _sets(self, ids_key: str, cnt_key: str) -> List[List[str]]:
+        names = self.hg._device_graph()["arrays"]["node_ids"]
+        ids, cnt = self.batch.state[ids_key].cpu().numpy(), self.batch.state[cnt_key].cpu().numpy()
+        return [sorted(names[int(v)] for v in ids[b, :int(cnt[b])]) for b in range(self.n_envs)]
 
     def selection_sets(self) -> List[List[str]]:
         """Selected node ids per environment (host copy; what `end_episode` hands to the evaluator)."""
-        ids = self.hg._device_graph()["arrays"]["node_ids"]
-        sel, cnt = self.state["sel_ids"].cpu().numpy(), self.state["sel_cnt"].cpu().numpy()
-        return [sorted(ids[int(v)] for v in sel[b, :int(cnt[b])]) for b in range(self.n_envs)]
+        return self._sets("sel_ids", "sel_cnt")
 
     def frontier_sets(self) -> List[List[str]]:
-        ids = self.hg._device_graph()["arrays"]["node_ids"]
-        fr, cnt = self.state["fr_ids"].cpu().numpy(), self.state["fr_cnt"].cpu().numpy()
-        return [sorted(ids[int(v)] for v in fr[b, :int(cnt[b])]) for b in range(self.n_envs)]
+        return self._sets("fr_ids", "fr_cnt")

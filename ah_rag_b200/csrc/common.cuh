@@ -199,8 +199,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
+// Remote arrive WITHOUT release semantics: used by the epilogue to hand a TMEM accumulator back to the MMA issuer.
+// Nothing the epilogue wrote is read by the waiter; the only hazard is the MMA overwriting TMEM columns still being
+// read, and tcgen05.wait::ld (+ tcgen05.fence::before_thread_sync) has retired those reads before this instruction.
+// The .release.cluster form compiles to ERRBAR + a cluster-scope membar: ~1.6 k cycles per tile on the accumulator's
+// critical path (17 % of the epilogue warps' samples in profiles/r1_c4_pairs_v6_ncu.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair: data lands in the issuing CTA's smem, completion bytes are
 // credited to the mbarrier at `cluster_bar_addr` (the leader CTA's full barrier)

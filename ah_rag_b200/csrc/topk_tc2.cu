@@ -40,8 +40,10 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const __grid_constant__ CUtensorMap map_q_lo, const __grid_constant__ CUtensorMap map_x_lo, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  static_assert(NB >= NA && NA >= 1, "the corpus ring is at least as deep as the query ring");
-  constexpr int LAG = NB - NA;  // the producer issues A(t - LAG) right after B(t)
+  static_assert(NA >= 1 && NB >= 1, "ring depths");
+  constexpr bool B_LEADS = NB >= NA;
+  constexpr int ND = B_LEADS ? NB : NA;         // slots of the `done` ring = depth of the deeper operand ring
+  constexpr int LAG = B_LEADS ? NB - NA : NA - NB;  // the producer issues block t - LAG of the shallower ring right after block t
   uint8_t *a_tiles = smem;                                // [NA][16 KB]
   uint8_t *b_tiles = smem + NA * T2_A_BYTES;              // [NB][16 KB]
   unsigned long long *lists = reinterpret_cast<unsigned long long *>(b_tiles + NB * T2_B_BYTES);  // [128][KLIST] keys
@@ -49,10 +51,10 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 4 * 32 * 32);
   uint64_t *full_a = bars;               // [NA] leader's copy is the live one (bytes of both CTAs)
   uint64_t *full_b = full_a + NA;        // [NB]
-  uint64_t *done = full_b + NB;          // [NB] per CTA: the MMA finished k-block t (slot t mod NB): frees B slot t mod NB
+  uint64_t *done = full_b + NB;          // [ND] per CTA: the MMA finished k-block t (slot t mod ND): frees B slot t mod NB
                                          //      and A slot t mod NA -- ONE commit per k-block (a second one per
                                          //      k-block cost 30 % on the tensor-bound workload)
-  uint64_t *tfull = done + NB;           // [2] per CTA: accumulator stage complete
+  uint64_t *tfull = done + ND;           // [2] per CTA: accumulator stage complete
   uint64_t *tempty = tfull + 2;          // [2] leader's copy: both epilogues drained the stage
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
@@ -75,10 +77,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < NA; ++s) mbar_init(&full_a[s], 1);  // the leader's arrive.expect_tx; TMA bytes of both CTAs
-      for (int s = 0; s < NB; ++s) {
-        mbar_init(&full_b[s], 1);
-        mbar_init(&done[s], 1);  // one multicast commit
-      }
+      for (int s = 0; s < NB; ++s) mbar_init(&full_b[s], 1);
+      for (int s = 0; s < ND; ++s) mbar_init(&done[s], 1);  // one multicast commit
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);   // one multicast commit
         mbar_init(&tempty[a], 8);  // 4 epilogue warps x 2 CTAs
@@ -130,10 +130,9 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       Cursor ca{cluster_id, 0, 0, 0, 0, 0, false}, cb{cluster_id, 0, 0, 0, 0, 0, false};
       open_item(ca);
       open_item(cb);
-      int sa = 0, sb = 0;
-      uint32_t pb = 0;
+      int sa = 0, sb = 0, sd = 0;
+      uint32_t pd = 0;
       const uint32_t full_a0 = mapa_u32(smem_u32(&full_a[0]), 0), full_b0 = mapa_u32(smem_u32(&full_b[0]), 0);  // leader's
-      // A(j) needs "k-block j - NA finished" = the event B(j + LAG) waits for: the caller has just waited for it
       auto issue_a = [&]() {
         const CUtensorMap *mq = ca.seg == 1 ? &map_q_lo : &map_q;  // (q_hi,x_hi) (q_lo,x_hi) (q_hi,x_lo)
         if (leader) mbar_arrive_expect_tx(&full_a[sa], 2 * T2_A_BYTES);
@@ -142,21 +141,31 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (++sa == NA) sa = 0;
         advance(ca);
       };
-      int lead = 0;
-      while (!cb.done) {
+      auto issue_b = [&]() {
         const CUtensorMap *mx = cb.seg == 2 ? &map_x_lo : &map_x;
         const int32_t x_row0 = (int32_t)cb.ct * (p.tile_stride * T2_BN) + (int32_t)rank * T2_BN_HALF;
-        mbar_wait_acct(&done[sb], pb ^ 1, acct);  // k-block t - NB finished
         if (leader) mbar_arrive_expect_tx(&full_b[sb], 2 * T2_B_BYTES);
         tma_load_2d_2sm(b_tiles + sb * T2_B_BYTES, mx, full_b0 + sb * 8, cb.kb * TC_BK, x_row0, kEvictNormal);  // streams through
-        if (++sb == NB) { sb = 0; pb ^= 1; }
+        if (++sb == NB) sb = 0;
         advance(cb);
-        if (lead < LAG) ++lead; else issue_a();
+      };
+      // The deeper ring leads.  Its block t waits for "k-block t - ND finished" (done[t mod ND]); the block t - LAG of
+      // the other ring needs "k-block t - LAG - (ND - LAG) finished" -- the same event, so it is issued right behind
+      // without a wait of its own.
+      Cursor &cl = B_LEADS ? cb : ca, &ct_ = B_LEADS ? ca : cb;
+      int lead = 0;
+      while (!cl.done) {
+        mbar_wait_acct(&done[sd], pd ^ 1, acct);
+        if (++sd == ND) { sd = 0; pd ^= 1; }
+        if (B_LEADS) issue_b(); else issue_a();
+        if (lead < LAG) ++lead;
+        else if (B_LEADS) issue_a();
+        else issue_b();
       }
-      while (!ca.done) {  // the last LAG query blocks: keep walking the `done` ring as if B blocks followed
-        mbar_wait_acct(&done[sb], pb ^ 1, acct);
-        if (++sb == NB) { sb = 0; pb ^= 1; }
-        issue_a();
+      while (!ct_.done) {  // the last LAG blocks of the trailing ring: keep walking the `done` ring
+        mbar_wait_acct(&done[sd], pd ^ 1, acct);
+        if (++sd == ND) { sd = 0; pd ^= 1; }
+        if (B_LEADS) issue_a(); else issue_b();
       }
       if (p.stats) p.stats[blockIdx.x * 8 + 0] = w_empty;
     }
@@ -165,7 +174,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * T2_BM, T2_BN);  // M = 256 across the pair, N = 256
-      int sa = 0, sb = 0;
+      int sa = 0, sb = 0, sd = 0;
       uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
@@ -189,7 +198,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             for (int k4 = 0; k4 < TC_BK / 16; ++k4)
               umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), idesc,
                                (kb | k4) != 0 ? 1u : 0u);
-            umma_commit_2sm(&done[sb], 0x3);  // frees A slot sa and B slot sb in both CTAs
+            umma_commit_2sm(&done[sd], 0x3);  // frees A slot sa and B slot sb in both CTAs
+            if (++sd == ND) sd = 0;
             if (++sa == NA) { sa = 0; pa ^= 1; }
             if (++sb == NB) { sb = 0; pb ^= 1; }
           }
@@ -332,10 +342,11 @@ int tc2_topk_partials(const CUtensorMap &map_x, const CUtensorMap *map_x_lo, con
   }
   if (k <= 56) {  // the list needs room beyond k: KLIST - k appends amortise one compaction
     // rings: 4 x 16 KB of queries + 4 x 16 KB of corpus (128 KB), next to 64 KB of lists and 16 KB of chunk scratch;
-    // the rest of the SM's 228 KB stays L1.  AHR_TC_RING = "35" | "36" select deeper corpus rings (experiments).
+    // the rest of the SM's 228 KB stays L1.  Measured alternatives (profiles/r1_k1_epilogue_history.md, "rings"):
+    // 3+5 / 3+6 starve the tensor-bound workload (-18 %), 4+5 and 5+4 change nothing on either regime.
+    // AHR_TC_RING=45 keeps the 4+5 build for experiments.
     static const int ring = getenv("AHR_TC_RING") ? atoi(getenv("AHR_TC_RING")) : 44;
-    if (ring == 35) return tc2_launch_t<64, 3, 5, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
-    if (ring == 36) return tc2_launch_t<64, 3, 6, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
+    if (ring == 45) return tc2_launch_t<64, 4, 5, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
     return tc2_launch_t<64, 4, 4, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
   }
   return tc2_launch_t<128, 2, 2, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);

@@ -5,6 +5,8 @@ computation is a call into libahrag_b200.so with raw device pointers.  No CPU fa
                                                                                hierarchical_graph.py:605-611, :714)
   GraphCSR     -- device-resident typed CSR + node attributes               (replaces the NetworkX adjacency
                                                                                reads, hierarchical_graph.py:441-462)
+  EnvBatchState -- device-resident state of B gym environments + reset/step  (replaces B sequential AHRAGGymEnv
+                                                                               objects, gym_env.py:41-125)
 """
 from __future__ import annotations
 
@@ -16,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import RerankParams, check
+from ._lib import EnvBatch, RerankParams, check
 
 _NT_BITS = {"entity": 1 << 0, "summary": 1 << 1, "hyperedge": 1 << 2}
 
@@ -318,3 +320,86 @@ class GraphCSR:
                                       in_offsets.data_ptr(), int(limit), out_ids.data_ptr(), out_cnt.data_ptr(),
                                       _stream_ptr(self.device)), "ahr_expand")
         return out_ids, out_cnt
+
+
+class EnvBatchState:
+    """Device-resident state of ``n_envs`` gym environments over one ``GraphCSR`` (``ahr_env_reset`` /
+    ``ahr_env_step``): selection and frontier sets, the current observation, step counters.  Outputs are
+    preallocated CUDA tensors overwritten by every call: ``features`` [B, 84] fp32, ``mask`` [B, 6] u8,
+    ``rewards`` [B] fp64, ``done`` [B] u8.  Nothing here synchronises with the host."""
+
+    FEATS = 84
+    N_ACTIONS = 6
+
+    def __init__(self, csr: GraphCSR, n_envs: int, max_steps: int = 6, repeat_penalty: float = 0.02,
+                 cap_selection: Optional[int] = None, cap_frontier: Optional[int] = None) -> None:
+        self.csr = csr
+        self.n_envs = int(n_envs)
+        self.max_steps = max(1, int(max_steps))
+        self.repeat_penalty = float(repeat_penalty)
+        dev = csr.device
+        B = self.n_envs
+        # an episode adds at most 3 selected and 10 frontier nodes per step (gym_env.py:94-100)
+        self.cap_sel = int(cap_selection or max(3 * (self.max_steps + 2), 32))
+        self.cap_fr = int(cap_frontier or (10 + 10 * (self.max_steps + 2)))
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.state = {
+            "sel_ids": torch.zeros((B, self.cap_sel), **i32), "sel_cnt": torch.zeros((B,), **i32),
+            "fr_ids": torch.zeros((B, self.cap_fr), **i32), "fr_cnt": torch.zeros((B,), **i32),
+            "shown_ids": torch.full((B, 10), -1, **i32),
+            "shown_score": torch.zeros((B, 10), dtype=torch.float64, device=dev),
+            "shown_sem": torch.zeros((B, 10), dtype=torch.float64, device=dev),
+            "shown_cnt": torch.zeros((B,), **i32), "n_seeds": torch.zeros((B,), **i32),
+            "obs_step": torch.zeros((B,), **i32), "obs_sel": torch.zeros((B,), **i32),
+            "obs_fr": torch.zeros((B,), **i32), "env_steps": torch.zeros((B,), **i32),
+            "gym_steps": torch.zeros((B,), **i32), "last_action": torch.full((B,), -1, **i32),
+            "done": torch.zeros((B,), dtype=torch.uint8, device=dev), "overflow": torch.zeros((1,), **i32),
+        }
+        self.features = torch.zeros((B, self.FEATS), dtype=torch.float32, device=dev)
+        self.mask = torch.zeros((B, self.N_ACTIONS), dtype=torch.uint8, device=dev)
+        self.rewards = torch.zeros((B,), dtype=torch.float64, device=dev)
+        self.done = torch.zeros((B,), dtype=torch.uint8, device=dev)
+        eb = EnvBatch()
+        eb.n_env, eb.cap_sel, eb.cap_fr, eb.reserved = B, self.cap_sel, self.cap_fr, 0
+        for name, t in self.state.items():
+            setattr(eb, name, t.data_ptr())
+        self._eb = eb
+        self._ready = False
+
+    def reset(self, rerank: Dict[str, torch.Tensor], n_seeds: int):
+        """``rerank`` = output of ``GraphCSR.anchor_rerank`` for one query per environment (top_k <= 10)."""
+        nodes, sem, score, count = rerank["nodes"], rerank["semantic"], rerank["score"], rerank["count"]
+        if int(nodes.shape[0]) != self.n_envs:
+            raise ValueError(f"expected {self.n_envs} reranked lists, got {int(nodes.shape[0])}")
+        for t, name in ((nodes, "nodes"), (sem, "semantic"), (score, "score"), (count, "count")):
+            _require_cuda(t, name)
+        dev = self.csr.device
+        if self.n_envs:
+            with torch.cuda.device(dev):
+                check(self.csr.lib.ahr_env_reset(self.csr._h, ctypes.byref(self._eb), nodes.data_ptr(), sem.data_ptr(),
+                                                 score.data_ptr(), count.data_ptr(), int(nodes.shape[1]), int(n_seeds),
+                                                 self.features.data_ptr(), self.mask.data_ptr(), _stream_ptr(dev)),
+                      "ahr_env_reset")
+        self._ready = True
+        return self.features, self.mask
+
+    def step(self, actions: torch.Tensor):
+        """``actions`` int32 [B] on the device, values 0..5 (gym_env.py:14-20)."""
+        if not self._ready:
+            raise RuntimeError("Call reset() first")
+        _require_cuda(actions, "actions")
+        if actions.dtype != torch.int32 or tuple(actions.shape) != (self.n_envs,):
+            raise ValueError(f"actions must be int32 of shape ({self.n_envs},)")
+        dev = self.csr.device
+        if self.n_envs:
+            with torch.cuda.device(dev):
+                check(self.csr.lib.ahr_env_step(self.csr._h, ctypes.byref(self._eb), actions.data_ptr(), self.max_steps,
+                                                self.repeat_penalty, self.features.data_ptr(), self.rewards.data_ptr(),
+                                                self.done.data_ptr(), self.mask.data_ptr(), _stream_ptr(dev)),
+                      "ahr_env_step")
+        return self.features, self.rewards, self.done, self.mask
+
+    def check_overflow(self) -> None:
+        """Raises if a selection / frontier list outgrew its capacity (synchronises)."""
+        if int(self.state["overflow"].item()):
+            raise RuntimeError("EnvBatchState: selection/frontier capacity exceeded; raise cap_selection/cap_frontier")

@@ -294,11 +294,38 @@ def run_c5(dev, scale=1.0):
                     array_graph.expand(host, int(opsh[e]), flath[offh[e]:offh[e + 1]], 2048) == list(oi2h[e, :oc2h[e]])
                     for e in sample)
     emitted = int(oc2.sum().item())
+    # bandwidth view of the hop kernel: 65536 frontier nodes (L1 summaries, 260 out + ~260 in related_to neighbours each),
+    # limit 512 so the walk reads both neighbour lists in full
+    nb = 65536
+    big_in = torch.randint(l_lo, l_hi, (nb,), generator=gen, device=dev).to(torch.int32)
+    big_ops = torch.full((nb,), 2, dtype=torch.int32, device=dev)
+    big_off = torch.arange(nb + 1, dtype=torch.int32, device=dev)
+    g.expand(big_ops, big_in, big_off, 512)
+    ms_bw = timed(lambda: g.expand(big_ops, big_in, big_off, 512), steps=10)
+    rp_o, rp_i = a["row_ptr"][4], a["row_ptr"][5]
+    bi = big_in.long()
+    deg = (rp_o[bi + 1] - rp_o[bi]) + (rp_i[bi + 1] - rp_i[bi])
+    bw_bytes = int(deg.sum().item()) * 4 + nb * (2 * 16 + 4) + nb * 512 * 4  # col_idx + row_ptr pairs + ids in + ids out
+    # device-resident gym rollout: 1024 environments, reset from a top-5 anchor, 6 random steps (one launch per step)
+    envb = engine.EnvBatchState(g, n_env, max_steps=6)
+    rr5 = g.anchor_rerank(seeds[:, :5].contiguous(), scores[:, :5].contiguous(), prm, 5, want_cluster=False)
+    acts = [torch.randint(0, 5, (n_env,), generator=gen, device=dev).to(torch.int32) for _ in range(6)]
+
+    def rollout():
+        envb.reset(rr5, 5)
+        for t in range(6):
+            envb.step(acts[t])
+
+    ms_roll = timed(rollout, steps=20)
+    envb.check_overflow()
     print(json.dumps({"workload": f"c5: synthetic hierarchical graph {n} nodes / {a['n_edges']} edges (scale {scale}), 1024 envs x 50 seeds",
                       "graph_bytes": g.nbytes(), "build_s": round(time.time() - t0, 1),
                       "hop1_anchor_rerank_ms": ms_anchor, "hop1_envs_per_s": n_env / ms_anchor * 1e3,
                       "hop2_expand_limit10_ms": ms_expand, "hop2_envs_per_s": n_env / ms_expand * 1e3,
                       "hop2_expand_limit2048_ms": ms_expand_big, "hop2_nodes_emitted": emitted,
+                      "hop_bw_65536_nodes_ms": ms_bw, "hop_bw_algorithmic_bytes": bw_bytes,
+                      "hop_bw_gbs": bw_bytes / (ms_bw * 1e-3) / 1e9, "hop_bw_frac_of_hbm": bw_bytes / (ms_bw * 1e-3) / 1e9 / hbm,
+                      "gym_rollout_reset_plus_6_steps_ms": ms_roll, "gym_env_steps_per_s": n_env * 6 / ms_roll * 1e3,
                       "parity_sample_envs": len(sample), "anchor_rerank_bit_exact": bool(ok_anchor),
                       "expand_bit_exact": bool(ok_expand), "hbm_peak_gbs": hbm, "peak_source": src}))
 
