@@ -71,7 +71,8 @@ struct AnchorArgs {
 
 __host__ __device__ inline size_t anchor_ws_per_query(int cap) { return ((size_t)cap * 22 + 15) & ~(size_t)15; }
 
-__global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a) {
+// General version: any capacity (the expanded map lives in the global workspace when it outgrows shared memory).
+__global__ void __launch_bounds__(AR_THREADS) anchor_rerank_big_kernel(AnchorArgs a) {
   __shared__ double sm_sem[AR_SMEM_CAP];
   __shared__ double sm_rs[AR_SMEM_CAP];
   __shared__ int32_t sm_node[AR_SMEM_CAP];
@@ -230,6 +231,223 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
   }
 }
 
+// Block-wide exclusive prefix sum of one int per thread (AR_THREADS = 4 warps); returns the block total in `total`.
+__device__ __forceinline__ int block_exclusive_scan(int v, int *sm_warp /*[4]*/, int &total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  __syncthreads();  // sm_warp may still be read from a previous scan
+  if (lane == 31) sm_warp[w] = x;
+  __syncthreads();
+  int base = 0;
+  total = 0;
+#pragma unroll
+  for (int i = 0; i < AR_THREADS / 32; ++i) {
+    const int t = sm_warp[i];
+    if (i < w) base += t;
+    total += t;
+  }
+  return base + x - v;
+}
+
+// Fast path (expanded map fits shared memory: cap <= AR_SMEM_CAP, i.e. every configuration the reference's callers
+// use).  Same results as anchor_rerank_big_kernel, O(cap) work for the map instead of O(cap^2):
+//   dedup        open-addressing hash table in shared memory: first occurrence = atomicMin of the entry index,
+//                "a seed owns its node's value" = atomicMax over the seed entries carrying the node
+//   positions    block prefix sums (insertion order of the expanded map, order of the filtered list)
+//   stable sort  rank counting over the COMPACTED filtered list (the only O(n^2) step left, n <= cap)
+// The O(cap^2) dedup/position loops of the first version made the kernel instruction-bound: 117 k warp instructions per
+// query at 50 seeds (profiles/r1_k2_c5_ncu.md).
+__global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a) {
+  constexpr int HASH_MAX = 2 * AR_SMEM_CAP;
+  __shared__ double sm_sem[AR_SMEM_CAP];
+  __shared__ double sm_rs[AR_SMEM_CAP];
+  __shared__ int32_t sm_node[AR_SMEM_CAP];
+  __shared__ uint8_t sm_kind[AR_SMEM_CAP];
+  __shared__ uint8_t sm_flag[AR_SMEM_CAP];
+  __shared__ int32_t h_key[HASH_MAX];                       // node id, -1 = free
+  __shared__ __align__(8) int32_t h_val[2 * HASH_MAX];      // [0, HASH_MAX): first entry, [HASH_MAX, ..): last seed entry
+  __shared__ int sm_warp[AR_THREADS / 32];
+  // after the dedup the hash values are dead: the compacted filtered list lives there
+  double *c_rs = reinterpret_cast<double *>(h_val);         // [AR_SMEM_CAP] rounded scores, 8 KB
+  int32_t *c_e = h_val + 2 * AR_SMEM_CAP;                   // [AR_SMEM_CAP] entry index, 4 KB
+  int32_t *h_first = h_val, *h_seed = h_val + HASH_MAX;
+
+  const int q = blockIdx.x;
+  const int cap = a.cap, fan = a.fan, per = 1 + fan;
+  double *e_sem = sm_sem, *e_rs = sm_rs;
+  int32_t *e_node = sm_node;
+  uint8_t *e_kind = sm_kind, *e_flag = sm_flag;
+  const GraphView &g = a.g;
+  const int32_t *seeds = a.seed_nodes + (int64_t)q * a.n_seeds;
+  const float *sscore = a.seed_scores + (int64_t)q * a.n_seeds;
+  int hsize = 64;
+  while (hsize < 2 * cap) hsize <<= 1;  // <= HASH_MAX because cap <= AR_SMEM_CAP
+  const int hmask = hsize - 1;
+  for (int i = threadIdx.x; i < hsize; i += AR_THREADS) {
+    h_key[i] = -1;
+    h_first[i] = 0x7fffffff;
+    h_seed[i] = -1;
+  }
+
+  // ---- A. generate the candidate list in reference order: seed r, then its expansions ----
+  for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
+    const int r = e / per, j = e % per;
+    int32_t v = seeds[r];
+    if (v >= g.n_nodes) v = -1;
+    int32_t node = -1;
+    double sem = 0.0;
+    uint8_t kind = EK_ABSENT;
+    if (v >= 0) {
+      // hnswlib's cosine space reports dist = 1.0f - <q,x> (fp32); the reference then takes
+      // semantic = 1.0 - float(dist) in fp64 (hierarchical_graph.py:723)
+      const double sem_r = 1.0 - (double)__fsub_rn(1.0f, sscore[r]);
+      if (j == 0) {
+        node = v; sem = sem_r; kind = EK_SEED;
+        if (a.seed_sem) a.seed_sem[(int64_t)q * a.n_seeds + r] = sem_r;
+      } else {
+        const uint8_t t = g.node_type[v];
+        if (t == AHR_NT_ENTITY && j - 1 < a.prm.parent_cap) {  // first 2 out-belongs_to parents, x0.9 (:733-736)
+          const int64_t p0 = g.row_ptr[AHR_CSR_BEL_OUT][v], p1 = g.row_ptr[AHR_CSR_BEL_OUT][v + 1];
+          if (p0 + (j - 1) < p1) {
+            node = g.col_idx[AHR_CSR_BEL_OUT][p0 + (j - 1)];
+            sem = __dmul_rn(sem_r, 0.9);
+            kind = EK_PARENT;
+          }
+        } else if (t == AHR_NT_SUMMARY && j - 1 < a.prm.member_top_m) {  // first m in-belongs_to members, x0.85 (:737-740)
+          const int64_t p0 = g.row_ptr[AHR_CSR_BEL_IN][v], p1 = g.row_ptr[AHR_CSR_BEL_IN][v + 1];
+          if (p0 + (j - 1) < p1) {
+            node = g.col_idx[AHR_CSR_BEL_IN][p0 + (j - 1)];
+            sem = __dmul_rn(sem_r, 0.85);
+            kind = EK_MEMBER;
+          }
+        }
+      }
+    } else if (j == 0 && a.seed_sem) {
+      a.seed_sem[(int64_t)q * a.n_seeds + r] = 0.0;
+    }
+    e_node[e] = node; e_sem[e] = sem; e_kind[e] = kind; e_flag[e] = 0;
+  }
+  __syncthreads();
+
+  // ---- B. first-writer-wins dedup; a seed always owns the value of its node (:732) ----
+  auto probe = [&](int32_t node, bool insert) {
+    int slot = (int)(((uint32_t)node * 2654435761u) >> 7) & hmask;
+    for (;;) {
+      const int32_t k = insert ? atomicCAS(&h_key[slot], -1, node) : h_key[slot];
+      if (k == node || (insert && k == -1)) return slot;
+      slot = (slot + 1) & hmask;
+    }
+  };
+  for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
+    const int32_t node = e_node[e];
+    if (node < 0) continue;
+    const int slot = probe(node, true);
+    atomicMin(&h_first[slot], e);
+    if (e % per == 0) atomicMax(&h_seed[slot], e);  // the LAST seed entry carrying this node overwrites the value
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
+    const int32_t node = e_node[e];
+    if (node < 0) continue;
+    const int slot = probe(node, false);
+    if (h_first[slot] != e) continue;
+    const int seed_e = h_seed[slot];
+    e_flag[e] = 1 | (seed_e >= 0 ? 4 : 0);
+    e_rs[e] = seed_e >= 0 ? e_sem[seed_e] : e_sem[e];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < cap; e += AR_THREADS)
+    if (e_flag[e] & 1) {
+      e_sem[e] = e_rs[e];
+      if (e_flag[e] & 4) e_kind[e] = EK_SEED;
+    }
+  __syncthreads();
+
+  // each thread owns a contiguous run of entries for the two order-preserving compactions below
+  const int chunk = (cap + AR_THREADS - 1) / AR_THREADS;
+  const int e_lo = min(cap, (int)threadIdx.x * chunk), e_hi = min(cap, e_lo + chunk);
+
+  // ---- expanded map in insertion order (return_cluster=True) ----
+  if (a.exp_nodes) {
+    int mine = 0, total;
+    for (int e = e_lo; e < e_hi; ++e) mine += e_flag[e] & 1;
+    int pos = block_exclusive_scan(mine, sm_warp, total);
+    for (int e = e_lo; e < e_hi; ++e) {
+      if (!(e_flag[e] & 1)) continue;
+      a.exp_nodes[(int64_t)q * cap + pos] = e_node[e];
+      a.exp_sem[(int64_t)q * cap + pos] = e_sem[e];
+      if (a.exp_kind) a.exp_kind[(int64_t)q * cap + pos] = e_kind[e];
+      ++pos;
+    }
+    if (threadIdx.x == 0 && a.exp_count) a.exp_count[q] = total;
+  } else if (threadIdx.x == 0 && a.exp_count) {
+    a.exp_count[q] = 0;
+  }
+
+  // ---- C. filters + linear rerank in fp64, same operation order as :764-768, no FMA contraction ----
+  const ahr_rerank_params &P = a.prm;
+  for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
+    if (!(e_flag[e] & 1)) continue;
+    const int32_t node = e_node[e];
+    const uint8_t t = g.node_type[node];
+    const double judge = g.judge[node], conf = g.conf[node];
+    const bool has_j = judge == judge, has_c = conf == conf;  // NaN encodes None
+    bool ok = true;
+    if (P.type_mask != 0 && !((P.type_mask >> t) & 1)) ok = false;                       // :756-757
+    if (P.has_judge_min && (!has_j || judge < P.judge_min)) ok = false;                  // :759-760
+    if (P.has_conf_min && (!has_c || conf < P.conf_min)) ok = false;                     // :761-762
+    if (!ok) continue;
+    const double jt = has_j ? g.judge_term[node] : 0.0;
+    const double ct = has_c ? __ddiv_rn(conf, 10.0) : 0.0;
+    double score = __dmul_rn(P.alpha, e_sem[e]);
+    score = __dadd_rn(score, __dmul_rn(P.beta, jt));
+    score = __dadd_rn(score, __dmul_rn(P.gamma, ct));
+    score = __dadd_rn(score, __dmul_rn(P.delta, P.boost[t & 3]));
+    e_rs[e] = round4_py(score);
+    e_flag[e] |= 2;
+  }
+  __syncthreads();
+
+  // ---- D. stable descending sort on the ROUNDED score (:781), keep top_k ----
+  int mine = 0, n_valid;
+  for (int e = e_lo; e < e_hi; ++e) mine += (e_flag[e] >> 1) & 1;
+  int pos = block_exclusive_scan(mine, sm_warp, n_valid);  // its barriers also retire the last reads of the hash
+  for (int e = e_lo; e < e_hi; ++e) {
+    if (!(e_flag[e] & 2)) continue;
+    c_rs[pos] = e_rs[e];
+    c_e[pos] = e;
+    ++pos;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_valid; i += AR_THREADS) {
+    const double rs = c_rs[i];
+    int rank = 0;
+#pragma unroll 4
+    for (int t = 0; t < n_valid; ++t) {
+      const double o = c_rs[t];
+      rank += (o > rs || (o == rs && t < i)) ? 1 : 0;  // list order = entry order: ties keep insertion order
+    }
+    if (rank < a.top_k) {
+      const int e = c_e[i];
+      const int64_t o = (int64_t)q * a.top_k + rank;
+      a.out_nodes[o] = e_node[e];
+      a.out_sem[o] = round4_py(e_sem[e]);
+      a.out_score[o] = rs;
+    }
+  }
+  const int n_out = n_valid < a.top_k ? n_valid : a.top_k;
+  for (int j = n_out + threadIdx.x; j < a.top_k; j += AR_THREADS) {
+    const int64_t o = (int64_t)q * a.top_k + j;
+    a.out_nodes[o] = -1; a.out_sem[o] = 0.0; a.out_score[o] = 0.0;
+  }
+  if (threadIdx.x == 0) a.out_count[q] = n_out;
+}
+
 size_t graph_anchor_workspace_bytes(int32_t nq, int32_t n_seeds, const ahr_rerank_params &prm) {
   const int fan = std::max(prm.parent_cap, prm.member_top_m);
   const int64_t cap = (int64_t)n_seeds * (1 + std::max(fan, 0));
@@ -260,7 +478,8 @@ int graph_anchor_rerank(const GraphView &g, int32_t nq, int32_t n_seeds, const i
   a.workspace = reinterpret_cast<uint8_t *>(workspace);
   if (cap > AR_SMEM_CAP)
     AHR_REQUIRE(workspace && workspace_bytes >= (size_t)nq * anchor_ws_per_query((int)cap), "anchor_rerank: workspace too small");
-  anchor_rerank_kernel<<<nq, AR_THREADS, 0, stream>>>(a);
+  if (cap <= AR_SMEM_CAP) anchor_rerank_kernel<<<nq, AR_THREADS, 0, stream>>>(a);
+  else anchor_rerank_big_kernel<<<nq, AR_THREADS, 0, stream>>>(a);
   AHR_KERNEL_CHECK();
   return AHR_OK;
 }
