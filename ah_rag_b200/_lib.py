@@ -20,11 +20,14 @@ EK_SEED, EK_PARENT, EK_MEMBER = 1, 2, 3
 OP_PARENTS, OP_CHILDREN, OP_RELATED = 0, 1, 2
 
 # every symbol include/ahrag_b200.h declares (tests/test_abi.py checks the header against this list)
+AHR_IPC_HANDLE_BYTES = 64
+
 EXPORTS = [
     "ahr_last_error", "ahr_version", "ahr_launch_count", "ahr_index_create", "ahr_index_destroy", "ahr_topk",
     "ahr_topk_host", "ahr_merge_topk", "ahr_merge_topk_packed", "ahr_graph_create", "ahr_graph_destroy", "ahr_anchor_rerank", "ahr_expand",
     "ahr_debug_tc_scores", "ahr_rescore", "ahr_debug_round4", "ahr_exact_stats", "ahr_set_profiling",
-    "ahr_get_profile", "ahr_env_reset", "ahr_env_step",
+    "ahr_get_profile", "ahr_env_reset", "ahr_env_step", "ahr_comm_create", "ahr_comm_export", "ahr_comm_connect",
+    "ahr_comm_destroy", "ahr_comm_begin", "ahr_comm_exchange_merge",
 ]
 
 
@@ -71,6 +74,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.ahr_set_profiling.argtypes = [vp, c_int]
     lib.ahr_get_profile.argtypes = [vp, POINTER(c_double), POINTER(c_int64), POINTER(c_int32)]
     lib.ahr_env_reset.argtypes = [vp, POINTER(EnvBatch), vp, vp, vp, vp, c_int32, c_int32, vp, vp, vp]
+    lib.ahr_comm_create.argtypes = [POINTER(vp), c_int, c_int, c_int, c_int64]
+    lib.ahr_comm_export.argtypes = [vp, vp]
+    lib.ahr_comm_connect.argtypes = [vp, vp]
+    lib.ahr_comm_destroy.argtypes = [vp]
+    lib.ahr_comm_begin.argtypes = [vp, c_int32, c_int32, POINTER(vp), POINTER(vp)]
+    lib.ahr_comm_exchange_merge.argtypes = [vp, c_int32, c_int32, vp, vp, vp]
     lib.ahr_env_step.argtypes = [vp, POINTER(EnvBatch), vp, c_int32, c_double, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)

@@ -1,0 +1,208 @@
+// exchange.cu -- K3: the cross-GPU candidate exchange of the sharded index, over NVLink peer memory.
+//
+// The reference has no multi-GPU path; the shape of the exchange comes from the north star:
+// every rank computes a local top-k over its node range, the [nq, k] candidate lists of all ranks meet, a device
+// k-way merge with the total order (score desc, id asc) produces the same answer on every rank.
+//
+// Instead of a collective library call the lists travel by plain stores into the PEERS' memory:
+//
+//   buffer (one cudaMalloc per rank, exported with cudaIpcGetMemHandle, opened by every peer):
+//     flags [2][world]  uint64   epoch of the last record rank `src` delivered into half `h`
+//     slots [2][world][record]   record = [nq*k fp32 scores | nq*k int64 ids], slot `src` is written by rank src
+//
+//   push_kernel   copies this rank's record (already sitting in its own slot: ahr_topk wrote it there) into slot
+//                 `rank` of every peer with 16-byte stores over NVLink, fences at system scope, and the LAST block to
+//                 finish publishes the epoch into the peers' flags (st.release.sys).
+//   wait + merge  one warp acquires the world flags (ld.acquire.sys spin), then select_topk_kernel merges the local
+//                 slots in stream order.  No host synchronisation, no collective library call.
+//
+// Two halves alternate by epoch parity: a rank can run at most one exchange ahead of a peer (its merge of call n
+// needs the peer's record of call n), so the half a fast rank overwrites in call n+1 is one the slow rank finished
+// reading in call n-1.
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ahr {
+
+constexpr int PUSH_THREADS = 256;
+constexpr int PUSH_BLOCKS = 32;
+constexpr int MAX_WORLD = 16;
+
+struct PeerTable {
+  uint8_t *base[MAX_WORLD];  // peer allocations (base[rank] = own)
+};
+
+__device__ __forceinline__ void st_release_sys_u64(uint64_t *p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(PUSH_THREADS)
+push_kernel(PeerTable peers, int rank, int world, size_t slot_off, size_t rec_bytes, size_t flag_off, uint64_t epoch,
+            unsigned int *done_counter) {
+  const uint8_t *src = peers.base[rank] + slot_off;
+  const size_t n16 = rec_bytes / 16;
+  const size_t total = n16 * (size_t)(world - 1);
+  for (size_t i = (size_t)blockIdx.x * PUSH_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * PUSH_THREADS) {
+    const int pi = (int)(i / n16);
+    const int peer = pi < rank ? pi : pi + 1;
+    const size_t at = i - (size_t)pi * n16;
+    const uint4 v = reinterpret_cast<const uint4 *>(src)[at];
+    reinterpret_cast<uint4 *>(peers.base[peer] + slot_off)[at] = v;  // NVLink store into the peer's slot `rank`
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  if (threadIdx.x < world && (int)threadIdx.x != rank)
+    st_release_sys_u64(reinterpret_cast<uint64_t *>(peers.base[threadIdx.x] + flag_off) + rank, epoch);
+  if (threadIdx.x == 0) *done_counter = 0;  // ready for the next launch (stream-ordered)
+}
+
+// Blocks until every peer's record of this epoch has landed (one acquire per peer, by the first `world` threads).
+__global__ void wait_flags_kernel(const uint64_t *flags, int rank, int world, uint64_t epoch) {
+  if ((int)threadIdx.x < world && (int)threadIdx.x != rank)
+    while (ld_acquire_sys_u64(flags + threadIdx.x) < epoch) __nanosleep(64);
+}
+
+}  // namespace ahr
+
+using namespace ahr;
+
+struct ahr_comm {
+  int device = 0, rank = 0, world = 1;
+  size_t max_record = 0, flags_bytes = 0, total_bytes = 0;
+  uint8_t *base = nullptr;               // own allocation
+  std::vector<uint8_t *> peer;           // opened peer allocations (peer[rank] = base)
+  std::vector<bool> opened;
+  unsigned int *done_counter = nullptr;
+  uint64_t epoch = 0;
+  bool connected = false;
+  size_t slot_offset(int half, int src) const { return flags_bytes + ((size_t)half * world + src) * max_record; }
+  size_t flag_offset(int half) const { return (size_t)half * world * sizeof(uint64_t); }
+};
+
+extern "C" {
+
+int ahr_comm_create(ahr_comm **out, int device, int rank, int world, int64_t max_record_bytes) {
+  AHR_REQUIRE(out != nullptr, "ahr_comm_create: out is NULL");
+  AHR_REQUIRE(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world, "ahr_comm_create: bad rank %d / world %d", rank, world);
+  AHR_REQUIRE(max_record_bytes >= 16, "ahr_comm_create: record too small");
+  DeviceGuard guard(device);
+  AHR_REQUIRE(guard.ok, "ahr_comm_create: cannot select CUDA device %d", device);
+  ahr_comm *c = new ahr_comm();
+  c->device = device; c->rank = rank; c->world = world;
+  c->max_record = ((size_t)max_record_bytes + 255) & ~(size_t)255;
+  c->flags_bytes = ((size_t)2 * world * sizeof(uint64_t) + 255) & ~(size_t)255;
+  c->total_bytes = c->flags_bytes + (size_t)2 * world * c->max_record;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&c->base), c->total_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&c->done_counter), sizeof(unsigned int));
+  if (e != cudaSuccess) {
+    set_error("ahr_comm_create: cudaMalloc(%zu) failed: %s", c->total_bytes, cudaGetErrorString(e));
+    if (c->base) cudaFree(c->base);
+    delete c;
+    return AHR_E_NOMEM;
+  }
+  AHR_CUDA_CHECK(cudaMemset(c->base, 0, c->flags_bytes));
+  AHR_CUDA_CHECK(cudaMemset(c->done_counter, 0, sizeof(unsigned int)));
+  AHR_CUDA_CHECK(cudaDeviceSynchronize());
+  c->peer.assign(world, nullptr);
+  c->opened.assign(world, false);
+  c->peer[rank] = c->base;
+  c->connected = world == 1;
+  *out = c;
+  return AHR_OK;
+}
+
+int ahr_comm_export(ahr_comm *c, void *handle_out) {
+  AHR_REQUIRE(c && handle_out, "ahr_comm_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == AHR_IPC_HANDLE_BYTES, "IPC handle size");
+  DeviceGuard guard(c->device);
+  cudaIpcMemHandle_t h;
+  AHR_CUDA_CHECK(cudaIpcGetMemHandle(&h, c->base));
+  memcpy(handle_out, &h, sizeof h);
+  return AHR_OK;
+}
+
+int ahr_comm_connect(ahr_comm *c, const void *all_handles) {
+  AHR_REQUIRE(c && all_handles, "ahr_comm_connect: NULL argument");
+  DeviceGuard guard(c->device);
+  for (int p = 0; p < c->world; ++p) {
+    if (p == c->rank || c->opened[p]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, reinterpret_cast<const uint8_t *>(all_handles) + (size_t)p * AHR_IPC_HANDLE_BYTES, sizeof h);
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_error("ahr_comm_connect: cudaIpcOpenMemHandle for rank %d failed: %s", p, cudaGetErrorString(e));
+      cudaGetLastError();
+      return AHR_E_CUDA;
+    }
+    c->peer[p] = reinterpret_cast<uint8_t *>(ptr);
+    c->opened[p] = true;
+  }
+  c->connected = true;
+  return AHR_OK;
+}
+
+int ahr_comm_destroy(ahr_comm *c) {
+  if (!c) return AHR_OK;
+  DeviceGuard guard(c->device);
+  cudaDeviceSynchronize();
+  for (int p = 0; p < c->world; ++p)
+    if (c->opened[p]) cudaIpcCloseMemHandle(c->peer[p]);
+  if (c->base) cudaFree(c->base);
+  if (c->done_counter) cudaFree(c->done_counter);
+  delete c;
+  return AHR_OK;
+}
+
+int ahr_comm_begin(ahr_comm *c, int32_t nq, int32_t k, float **dev_slot_scores, int64_t **dev_slot_ids) {
+  AHR_REQUIRE(c && dev_slot_scores && dev_slot_ids, "ahr_comm_begin: NULL argument");
+  AHR_REQUIRE(c->connected, "ahr_comm_begin: peers are not connected (ahr_comm_connect)");
+  AHR_REQUIRE(nq >= 1 && k >= 1, "ahr_comm_begin: bad sizes nq=%d k=%d", nq, k);
+  const size_t sb = (size_t)nq * k * 4, rec = sb * 3;
+  AHR_REQUIRE(sb % 16 == 0, "ahr_comm_begin: nq * k must be a multiple of 4 (16-byte peer stores)");
+  AHR_REQUIRE(rec <= c->max_record, "ahr_comm_begin: record of %zu bytes exceeds the buffer's %zu", rec, c->max_record);
+  c->epoch += 1;
+  const int half = (int)(c->epoch & 1);
+  uint8_t *slot = c->base + c->slot_offset(half, c->rank);
+  *dev_slot_scores = reinterpret_cast<float *>(slot);
+  *dev_slot_ids = reinterpret_cast<int64_t *>(slot + sb);
+  return AHR_OK;
+}
+
+int ahr_comm_exchange_merge(ahr_comm *c, int32_t nq, int32_t k, float *dev_out_scores, int64_t *dev_out_ids, void *stream) {
+  AHR_REQUIRE(c && dev_out_scores && dev_out_ids, "ahr_comm_exchange_merge: NULL argument");
+  AHR_REQUIRE(c->connected && c->epoch > 0, "ahr_comm_exchange_merge: call ahr_comm_begin first");
+  DeviceGuard guard(c->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t sb = (size_t)nq * k * 4, rec = sb * 3;
+  const int half = (int)(c->epoch & 1);
+  if (c->world > 1) {
+    PeerTable t;
+    for (int p = 0; p < MAX_WORLD; ++p) t.base[p] = p < c->world ? c->peer[p] : nullptr;
+    push_kernel<<<PUSH_BLOCKS, PUSH_THREADS, 0, st>>>(t, c->rank, c->world, c->slot_offset(half, c->rank), rec,
+                                                      c->flag_offset(half), c->epoch, c->done_counter);
+    AHR_KERNEL_CHECK();
+    wait_flags_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const uint64_t *>(c->base + c->flag_offset(half)), c->rank,
+                                        c->world, c->epoch);
+    AHR_KERNEL_CHECK();
+  }
+  // k-way merge over the world slots of this half: part p at + p * max_record
+  const float *scores = reinterpret_cast<const float *>(c->base + c->slot_offset(half, 0));
+  const int64_t *ids = reinterpret_cast<const int64_t *>(c->base + c->slot_offset(half, 0) + sb);
+  return select_topk_strided2(scores, nullptr, ids, k, (int64_t)c->world * k, k, (int64_t)(c->max_record / 4),
+                              (int64_t)(c->max_record / 8), nq, k, 0, false, dev_out_scores, dev_out_ids, st);
+}
+
+}  // extern "C"

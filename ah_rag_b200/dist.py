@@ -1,8 +1,9 @@
 """Node-range sharding of the embedding index across the GPUs of one box (one process per GPU).
 
 Each rank holds rows [lo, hi) of the corpus, computes its local top-k with the fused kernel, and the
-candidate lists meet through ONE all-gather (NCCL over NVLink; gloo in the CPU tests) followed by a
-device-side k-way merge with the total order (score desc, id asc) -- so fp32-exact results are identical
+candidate lists meet through ONE exchange -- stores straight into the peers' memory over NVLink
+(``engine.PeerExchange`` / csrc/exchange.cu) on a GPU box, an all-gather (NCCL, or gloo in the CPU tests) otherwise
+or when ``AHR_EXCHANGE=nccl`` -- followed by a device-side k-way merge with the total order (score desc, id asc) -- so fp32-exact results are identical
 for every shard count.  Queries are replicated (every rank receives the same batch).
 
 The reference has no distributed path at all; this is the B200-native scaling of
@@ -57,10 +58,32 @@ class ShardedIndex:
         obj.merge_packed = engine.merge_topk_packed
         return obj
 
+    def enable_peer_exchange(self, max_queries: int, max_k: int) -> bool:
+        """Switch the exchange to peer-memory stores (one-time rendezvous of CUDA IPC handles over the process group).
+        Returns False and keeps the all-gather when ``AHR_EXCHANGE=nccl`` is set or the world has one rank."""
+        import os
+        from . import engine
+        if self.world == 1 or os.environ.get("AHR_EXCHANGE", "peer") == "nccl":
+            return False
+
+        def swap(mine: bytes):
+            out = [None] * self.world
+            dist.all_gather_object(out, mine, group=self.group)
+            return out
+
+        self.peer = engine.PeerExchange(self.index.device, self.rank, self.world, max_queries * max_k * 12, swap)
+        return True
+
     def topk(self, q: torch.Tensor, k: int, mode: str = "bf16") -> Tuple[torch.Tensor, torch.Tensor]:
         if self.world == 1:
             return self.local_topk(q, k, mode)
         nq = int(q.shape[0])
+        peer = getattr(self, "peer", None)
+        if peer is not None and (nq * k) % 4 == 0 and nq * k * 12 <= peer.max_record_bytes:
+            # the local top-k writes straight into this rank's slot; the slot is stored into every peer's buffer
+            ps, pi = peer.begin(nq, k)
+            self.index.topk_raw(q, k, mode, ps, pi)
+            return peer.exchange_merge(nq, k)
         if self.merge_packed is not None and (nq * k * 4) % 8 == 0:
             # the local top-k writes straight into this rank's record of the exchange buffer
             rec = nq * k * 12

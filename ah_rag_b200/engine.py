@@ -98,6 +98,15 @@ class VectorIndex:
                                     ids.data_ptr(), _stream_ptr(self.device)), "ahr_topk")
         return scores, ids
 
+    def topk_raw(self, q: torch.Tensor, k: int, mode: str, scores_ptr: int, ids_ptr: int) -> None:
+        """Top-k written to raw device pointers ([nq, k] fp32 / int64), e.g. a slot of the peer exchange buffer."""
+        _require_cuda(q, "q")
+        if q.dim() != 2 or q.shape[1] != self.dim or q.dtype != self.dtype:
+            raise ValueError(f"q must be [nq, {self.dim}] {self.dtype}")
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_topk(self._h, q.data_ptr(), int(q.shape[0]), int(k), self._mode(mode), scores_ptr, ids_ptr,
+                                    _stream_ptr(self.device)), "ahr_topk")
+
     def topk_host(self, q_host: torch.Tensor, k: int, mode: str = "bf16",
                   out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """End-to-end call with HOST buffers (H2D copy of the queries, top-k, D2H copy of the results)."""
@@ -403,3 +412,53 @@ class EnvBatchState:
         """Raises if a selection / frontier list outgrew its capacity (synchronises)."""
         if int(self.state["overflow"].item()):
             raise RuntimeError("EnvBatchState: selection/frontier capacity exceeded; raise cap_selection/cap_frontier")
+
+
+class PeerExchange:
+    """Handle over ``ahr_comm``: the cross-GPU candidate exchange through NVLink peer memory (csrc/exchange.cu).
+    ``swap_handles(my_handle: bytes) -> list[bytes]`` is any all-gather of 64-byte blobs in rank order (the one-time
+    rendezvous; ``torch.distributed.all_gather_object`` in ``dist.ShardedIndex``)."""
+
+    def __init__(self, device: torch.device, rank: int, world: int, max_record_bytes: int, swap_handles) -> None:
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.rank, self.world = int(rank), int(world)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_comm_create(ctypes.byref(self._h), self.device.index or 0, self.rank, self.world,
+                                           int(max_record_bytes)), "ahr_comm_create")
+            mine = ctypes.create_string_buffer(_lib.AHR_IPC_HANDLE_BYTES)
+            check(self.lib.ahr_comm_export(self._h, mine), "ahr_comm_export")
+            if self.world > 1:
+                handles = swap_handles(bytes(mine.raw))
+                if len(handles) != self.world or any(len(h) != _lib.AHR_IPC_HANDLE_BYTES for h in handles):
+                    raise RuntimeError("swap_handles must return one 64-byte handle per rank")
+                blob = ctypes.create_string_buffer(b"".join(handles), self.world * _lib.AHR_IPC_HANDLE_BYTES)
+                check(self.lib.ahr_comm_connect(self._h, blob), "ahr_comm_connect")
+        self.max_record_bytes = int(max_record_bytes)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.ahr_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def begin(self, nq: int, k: int) -> Tuple[int, int]:
+        """Start an exchange: raw device pointers (scores, ids) of this rank's slot."""
+        ps, pi = ctypes.c_void_p(), ctypes.c_void_p()
+        check(self.lib.ahr_comm_begin(self._h, int(nq), int(k), ctypes.byref(ps), ctypes.byref(pi)), "ahr_comm_begin")
+        return int(ps.value), int(pi.value)
+
+    def exchange_merge(self, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Push this rank's slot to the peers, wait for theirs, merge: [nq, k] results, identical on every rank."""
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_comm_exchange_merge(self._h, int(nq), int(k), out_s.data_ptr(), out_i.data_ptr(),
+                                                   _stream_ptr(self.device)), "ahr_comm_exchange_merge")
+        return out_s, out_i

@@ -221,6 +221,22 @@ def main() -> int:
     rows = make_corpus_shard(torch, device, lo, hi, DIM)
     sharded = ShardedIndex.from_rows(rows, id_base=lo)
     index = sharded.index
+    exchange = "none (one shard)"
+    if world > 1:
+        # candidate exchange: stores into the peers' memory over NVLink (csrc/exchange.cu); AHR_EXCHANGE=nccl keeps the
+        # all-gather.  The choice is made by every rank together (a failed IPC mapping on one rank falls back on all).
+        ok = 0
+        try:
+            ok = 1 if sharded.enable_peer_exchange(N_QUERIES, TOP_K) else 0
+        except RuntimeError as e:  # e.g. CUDA IPC not permitted in this container
+            print(f"bench.py[rank {rank}]: peer exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            exchange = "peer-memory stores over NVLink + epoch flags (csrc/exchange.cu), device k-way merge"
+        else:
+            sharded.peer = None
+            exchange = "single NCCL all-gather + device k-way merge"
     q_dev = make_queries(torch, device, N_QUERIES, DIM)
     q_host = q_dev.cpu().pin_memory()
     out_host = (torch.empty((N_QUERIES, TOP_K), dtype=torch.float32).pin_memory(),
@@ -293,7 +309,7 @@ def main() -> int:
             "config": {"workload": f"c3: synthetic {N_ROWS}x{DIM} bf16 corpus (seeded N(0,1), L2-normalised), "
                                    f"{N_QUERIES}-query batch, top-k={TOP_K}, mode={args.mode}",
                        "sharding": f"node-range, {world} shard(s) of {hi - lo} rows; queries replicated; "
-                                   + ("single NCCL all-gather + device k-way merge" if world > 1 else "no collective"),
+                                   + (exchange if world > 1 else "no collective"),
                        "l2": "inputs larger than L2 (corpus shard %.1f GB vs 126 MB)" % ((hi - lo) * DIM * 2 / 1e9),
                        "n_slabs": prof["n_slabs"]},
             "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": N_QUERIES * DIM * 2,

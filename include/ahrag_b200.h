@@ -221,6 +221,28 @@ int ahr_env_step(ahr_graph *g, const ahr_env_batch *env, const int32_t *dev_acti
                  double repeat_penalty, float *dev_features, double *dev_rewards, uint8_t *dev_done, uint8_t *dev_mask,
                  void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Cross-GPU candidate exchange over NVLink peer memory (one process per GPU, one box).
+ * The reference has no multi-GPU path; this is the scaling of the Collection.query seam
+ * (src/ah_rag/graph/hierarchical_graph.py:714) over an index sharded by node range: every rank's
+ * [nq, k] candidate list is stored directly into the peers' exchange buffers, a flag per (half, source) carries
+ * the epoch, and the k-way merge runs on every rank.  No collective library call on the data path.
+ *
+ *   create  -> export (64-byte CUDA IPC handle) -> all ranks swap handles (any transport) -> connect
+ *   per batch: ahr_comm_begin gives this rank's slot; run ahr_topk with the slot as its output (global ids);
+ *              ahr_comm_exchange_merge pushes the slot to the peers, waits for theirs, merges into out.
+ * ---------------------------------------------------------------------------------------------- */
+#define AHR_IPC_HANDLE_BYTES 64
+typedef struct ahr_comm ahr_comm;
+int ahr_comm_create(ahr_comm **out, int device, int rank, int world, int64_t max_record_bytes /* >= nq*k*12 */);
+int ahr_comm_export(ahr_comm *c, void *handle_out /* AHR_IPC_HANDLE_BYTES */);
+int ahr_comm_connect(ahr_comm *c, const void *all_handles /* world x AHR_IPC_HANDLE_BYTES, rank order */);
+int ahr_comm_destroy(ahr_comm *c);
+/* start an exchange of [nq, k] lists (nq*k %% 4 == 0): returns device pointers to this rank's slot */
+int ahr_comm_begin(ahr_comm *c, int32_t nq, int32_t k, float **dev_slot_scores, int64_t **dev_slot_ids);
+/* push the slot to every peer, wait for every peer's slot of this exchange, merge: out [nq, k] identical on all ranks */
+int ahr_comm_exchange_merge(ahr_comm *c, int32_t nq, int32_t k, float *dev_out_scores, int64_t *dev_out_ids, void *stream);
+
 /* ---- diagnostics used by the parity tests (not part of the reference seam) ---------------------- */
 /* full [nq, n_rows] score matrix of the tensor-core path (small inputs only) */
 int ahr_debug_tc_scores(ahr_index *idx, const void *dev_q, int32_t nq, float *dev_out, void *stream);

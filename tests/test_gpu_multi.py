@@ -1,0 +1,93 @@
+"""Multi-GPU parity of the sharded index (needs >= 2 GPUs on the box; skipped otherwise): node-range shards, the
+peer-memory exchange of csrc/exchange.cu (stores into the peers' buffers over NVLink + epoch flags) and the NCCL
+all-gather path must both return, on every rank, exactly what one index over the whole corpus returns."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from ah_rag_b200 import engine, synth
+        from ah_rag_b200.dist import ShardedIndex, shard_bounds
+        n, dim, k = 60_000 + 13, 128, 50
+        X = torch.from_numpy(synth.unit_rows(n, dim, 31, clustered=8)).to(dev).to(torch.bfloat16).contiguous()
+        lo, hi = shard_bounds(n, world, rank)
+        full = engine.VectorIndex(X)
+        sh = ShardedIndex.from_rows(X[lo:hi].contiguous(), id_base=lo)
+        problems = []
+        for use_peer in (False, True):
+            if use_peer and not sh.enable_peer_exchange(512, k):
+                problems.append("peer exchange not enabled")
+                break
+            # several exchanges back to back without host synchronisation: exercises the two buffer halves / epochs
+            outs, wants = [], []
+            for it, nq in enumerate((64, 300, 8, 512, 128, 4)):
+                Q = torch.from_numpy(synth.unit_rows(nq, dim, 40 + it, clustered=8)).to(dev).to(torch.bfloat16).contiguous()
+                for mode in ("bf16", "exact"):
+                    outs.append(sh.topk(Q, k, mode))
+                    wants.append(full.topk(Q, k, mode))
+            torch.cuda.synchronize()
+            for j, ((s, i), (ws, wi)) in enumerate(zip(outs, wants)):
+                if not (torch.equal(i, wi) and torch.equal(s.view(torch.int32), ws.view(torch.int32))):
+                    problems.append(f"peer={use_peer} case {j} differs")
+        q.put((rank, problems))
+    except Exception as e:  # report instead of leaving the parent waiting
+        q.put((rank, [repr(e)]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_topk_peer_exchange_and_nccl(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=280) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+    assert res == [(r, []) for r in range(world)]
+
+
+def test_peer_exchange_single_rank():
+    """world = 1: the exchange degenerates to a merge of this rank's own slot (API / addressing check on one GPU)."""
+    from ah_rag_b200 import engine, synth
+    n, dim, nq, k = 9000, 64, 96, 50
+    X = torch.from_numpy(synth.unit_rows(n, dim, 51)).cuda().to(torch.bfloat16).contiguous()
+    Q = torch.from_numpy(synth.unit_rows(nq, dim, 52)).cuda().to(torch.bfloat16).contiguous()
+    idx = engine.VectorIndex(X, id_base=1000)
+    ex = engine.PeerExchange(torch.device("cuda", 0), 0, 1, nq * k * 12, lambda h: [h])
+    for _ in range(3):  # both halves
+        ps, pi = ex.begin(nq, k)
+        idx.topk_raw(Q, k, "bf16", ps, pi)
+        s, i = ex.exchange_merge(nq, k)
+        ws, wi = idx.topk(Q, k, "bf16")
+        assert torch.equal(i, wi) and torch.equal(s, ws)
+    with pytest.raises(RuntimeError):
+        ex.begin(nq * 4, k)  # record larger than the buffer
+    with pytest.raises(RuntimeError):
+        ex.begin(3, 3)  # 16-byte store granularity
