@@ -84,6 +84,103 @@ def csr_from_networkx(G) -> Dict[str, Any]:
             "node_type": node_type, "level": level, "judge": judge, "judge_term": judge_term, "conf": conf}
 
 
+_ABSENT = object()
+
+
+def _node_attr_arrays(node_ids: List[Any], attrs: List[Dict[str, Any]]) -> Dict[str, np.ndarray]:
+    n = len(node_ids)
+    node_type = np.full(n, 3, dtype=np.uint8)
+    level = np.zeros(n, dtype=np.uint8)
+    judge = np.full(n, np.nan, dtype=np.float64)
+    judge_term = np.zeros(n, dtype=np.float64)
+    conf = np.full(n, np.nan, dtype=np.float64)
+    for i, d in enumerate(attrs):
+        node_type[i] = NODE_TYPE_CODE.get(d.get("node_type"), 3)
+        lv = d.get("level")
+        if isinstance(lv, (int, float)) and not isinstance(lv, bool) and 0 <= lv < 256:
+            level[i] = int(lv)
+        j = judge_overall(d)
+        if j is not None:
+            judge[i] = j
+            # same expression, same library call as hierarchical_graph.py:766 (np.exp on a Python float)
+            judge_term[i] = 1.0 / (1.0 + np.exp(-((j or 0.0) / 10.0)))
+        c = d.get("confidence")
+        if c is not None:
+            conf[i] = float(c)
+    return {"node_type": node_type, "level": level, "judge": judge, "judge_term": judge_term, "conf": conf}
+
+
+def csr_from_node_link(data: Dict[str, Any], edges: str = "links") -> Dict[str, Any]:
+    """CSR export straight from the on-disk node-link document (``structure.json``, hierarchical_graph.py:175-218),
+    without walking a NetworkX graph: equal, array for array, to
+    ``csr_from_networkx(nx.node_link_graph(data, directed=True, edges="links"))`` (tests/test_host.py), in vectorised
+    numpy -- the per-edge Python loop of the NetworkX route is what dominates start-up on large graphs.
+
+    Rules of ``node_link_graph`` / ``DiGraph.add_edge`` reproduced here: nodes in document order, a repeated node id
+    merges its attributes into the first entry; a link naming an unknown node appends it (source before target); a
+    repeated (source, target) pair keeps the adjacency slot of its first link and takes the ``edge_type`` of the last
+    link that carries that key.
+    """
+    node_ids: List[Any] = []
+    dense: Dict[Any, int] = {}
+    attrs: List[Dict[str, Any]] = []
+    for d in data.get("nodes", []):
+        nid = d["id"]
+        rest = {k: v for k, v in d.items() if k != "id"}
+        if nid in dense:
+            attrs[dense[nid]].update(rest)
+        else:
+            dense[nid] = len(node_ids)
+            node_ids.append(nid)
+            attrs.append(rest)
+    links = data.get(edges, [])
+    m = len(links)
+    tcode = {t: i for i, t in enumerate(EDGE_TYPES)}
+    src_l = [l["source"] for l in links]
+    dst_l = [l["target"] for l in links]
+    # -2: the link has no edge_type key (keeps whatever an earlier duplicate set); -1: key present, not a known type
+    et = np.fromiter((-2 if (t := l.get("edge_type", _ABSENT)) is _ABSENT else tcode.get(t, -1) if isinstance(t, str) else -1
+                      for l in links), dtype=np.int64, count=m)
+    src = np.fromiter((dense.get(u, -1) for u in src_l), dtype=np.int64, count=m)
+    dst = np.fromiter((dense.get(v, -1) for v in dst_l), dtype=np.int64, count=m)
+    if m and (src.min() < 0 or dst.min() < 0):  # rare: endpoints missing from "nodes" are appended in link order
+        for i in np.flatnonzero((src < 0) | (dst < 0)):
+            for arr, name in ((src, src_l[i]), (dst, dst_l[i])):
+                if name not in dense:
+                    dense[name] = len(node_ids)
+                    node_ids.append(name)
+                    attrs.append({})
+                arr[i] = dense[name]
+    n = len(node_ids)
+    if m:
+        key = src * n + dst
+        _, first, inv = np.unique(key, return_index=True, return_inverse=True)
+        n_pairs = first.shape[0]
+        last_typed = np.full(n_pairs, -1, dtype=np.int64)
+        typed = np.flatnonzero(et != -2)
+        np.maximum.at(last_typed, inv[typed], typed)
+        pair_type = np.where(last_typed >= 0, et[np.maximum(last_typed, 0)], -1)
+        order = np.argsort(first, kind="stable")          # pairs in the order of their first link
+        p_src, p_dst, p_type = src[first][order], dst[first][order], pair_type[order]
+    else:
+        p_src = p_dst = p_type = np.zeros(0, dtype=np.int64)
+    # in-adjacency order of DiGraph: _pred[v] gets u when the pair (u, v) is first added -> also first-link order
+    row_ptr, col_idx = [], []
+    for t in range(3):
+        sel = p_type == t
+        s_, d_ = p_src[sel], p_dst[sel]
+        for direction in (0, 1):
+            k_, v_ = (s_, d_) if direction == 0 else (d_, s_)
+            o = np.argsort(k_, kind="stable")
+            rp = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(np.bincount(k_, minlength=n), out=rp[1:])
+            row_ptr.append(rp)
+            col_idx.append(v_[o].astype(np.int32))
+    out = {"n_nodes": n, "node_ids": node_ids, "dense": dense, "row_ptr": row_ptr, "col_idx": col_idx}
+    out.update(_node_attr_arrays(node_ids, attrs))
+    return out
+
+
 def csr_from_edges(n_nodes: int, src: np.ndarray, dst: np.ndarray, etype: np.ndarray, node_type: np.ndarray,
                    level: Optional[np.ndarray] = None, judge: Optional[np.ndarray] = None,
                    conf: Optional[np.ndarray] = None) -> Dict[str, Any]:

@@ -53,6 +53,7 @@ class HierarchicalGraph:
         self.device: str = "cuda"
         self._dev_graph: Optional[Dict[str, Any]] = None
         self._dev_index: Optional[Dict[str, Any]] = None
+        self._source: Optional[Dict[str, Any]] = None  # set by load(): lets the device export skip the NetworkX walk
         self._st_model = None
         self._st_name: Optional[str] = None
 
@@ -77,6 +78,7 @@ class HierarchicalGraph:
     def _touch(self) -> None:
         self.G.graph["dirty"] = True
         self._dev_graph = None
+        self._source = None  # the graph no longer is the document it was loaded from
 
     def add_entity(self, name: str, description: Optional[str] = None, entity_type: Optional[str] = None,
                    embedding_ref: Optional[Tuple[str, int]] = None,
@@ -170,11 +172,17 @@ class HierarchicalGraph:
 
     @classmethod
     def load(cls, directory: str = GRAPH_DIR) -> "HierarchicalGraph":
-        with open(os.path.join(directory, "structure.json"), "r", encoding="utf-8") as f:
-            data = json.load(f)
+        with open(os.path.join(directory, "structure.json"), "rb") as f:
+            raw = f.read()
+        data = json.loads(raw.decode("utf-8"))
         hg = cls()
         key = "links" if "links" in data else "edges"
+        from . import snapshot
+        # what the device export needs later (csr.csr_from_node_link, or the binary snapshot keyed by these bytes);
+        # node_link_graph copies the attribute dicts it reads and leaves the document untouched
+        hg._source = {"dir": directory, "key": snapshot.key_of(raw), "doc": data, "edges": key}
         hg.G = nx.node_link_graph(data, directed=True, edges=key)
+        hg._source["sig"] = (hg.G.number_of_nodes(), hg.G.number_of_edges())
         for nid, attr in hg.G.nodes(data=True):
             if attr.get("node_type") == "entity" and attr.get("name"):
                 hg.name_to_entity_id[attr["name"]] = nid
@@ -322,12 +330,28 @@ class HierarchicalGraph:
     def _device_graph(self) -> Dict[str, Any]:
         sig = (id(self.G), self.G.number_of_nodes(), self.G.number_of_edges())
         if self._dev_graph is None or self._dev_graph["sig"] != sig:
-            from .. import csr as csr_mod
             from .. import engine
-            arrays = csr_mod.csr_from_networkx(self.G)
+            arrays = self._export_arrays()
             self._dev_graph = {"sig": sig, "arrays": arrays, "csr": engine.GraphCSR(arrays, self.device)}
             self._dev_index = None  # row -> node map depends on dense ids
         return self._dev_graph
+
+    def _export_arrays(self) -> Dict[str, Any]:
+        """CSR + attribute arrays of the current graph.  A graph that still is the document ``load`` read comes from
+        the binary snapshot beside it (written on first use) or, failing that, from the vectorised node-link export;
+        anything built or edited in memory is walked through NetworkX."""
+        from .. import csr as csr_mod
+        from . import snapshot
+        src = self._source
+        if src is not None and src.get("sig") == (self.G.number_of_nodes(), self.G.number_of_edges()):
+            arrays = snapshot.load(src["dir"], src["key"])
+            if arrays is None and src.get("doc") is not None:
+                arrays = csr_mod.csr_from_node_link(src["doc"], edges=src["edges"])
+                if os.environ.get("AHR_SNAPSHOT", "1") != "0" and snapshot.save(src["dir"], src["key"], arrays):
+                    src["doc"] = None  # the snapshot replaces the parsed document from here on
+            if arrays is not None and arrays["node_ids"] == list(self.G.nodes):
+                return arrays
+        return csr_mod.csr_from_networkx(self.G)
 
     def _device_index(self, db_path: str) -> Dict[str, Any]:
         import torch

@@ -138,3 +138,89 @@ def test_featurizer_and_reward_match_oracle():
             assert v.shape == (84,) and np.array_equal(v, ref_search.featurize(st["obs"]))
             assert step_reward(prev, st["obs"]) == ref_search.step_reward(prev, st["obs"])
             prev = st["obs"]
+
+
+# ---------------------------------------------------------------------------------------------
+# on-disk -> device loader (vectorised node-link export + binary snapshot)
+# ---------------------------------------------------------------------------------------------
+def _same_arrays(a, b):
+    assert a["n_nodes"] == b["n_nodes"] and a["node_ids"] == b["node_ids"]
+    for s in range(6):
+        assert np.array_equal(a["row_ptr"][s], b["row_ptr"][s]), s
+        assert np.array_equal(a["col_idx"][s], b["col_idx"][s]), s
+    for k in ("node_type", "level", "judge", "judge_term", "conf"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_csr_from_node_link_equals_networkx_walk():
+    """The vectorised export of structure.json must equal the walk over the graph NetworkX loads from it, including
+    what DiGraph does with repeated links (slot of the first, edge_type of the last that has the key), links without
+    an edge_type, unknown edge types, links naming nodes absent from "nodes", and repeated node entries."""
+    import copy
+    import random
+    import networkx as nx
+    from ah_rag_b200 import csr, synth
+    from tests import golden_util as gu
+    for name in gu.fixture_names():
+        nl = gu.load(name)["node_link"]
+        _same_arrays(csr.csr_from_node_link(nl),
+                     csr.csr_from_networkx(nx.node_link_graph(copy.deepcopy(nl), directed=True, edges="links")))
+    rng = random.Random(3)
+    for trial in range(12):
+        nl = synth.make_graph(seed=100 + trial, n_entities=30, n_l1=4, n_l2=2, n_hyperedges=10)
+        links, ids = nl["links"], [d["id"] for d in nl["nodes"]]
+        extra = []
+        for _ in range(40):
+            l, r = dict(rng.choice(links)), rng.random()
+            if r < 0.3:
+                l["edge_type"] = rng.choice(["belongs_to", "related_to", "participates_in", "weird", None])
+            elif r < 0.5:
+                l.pop("edge_type", None)
+            elif r < 0.7:
+                l["source"], l["target"] = l["target"], l["source"]
+            elif r < 0.85:
+                l["target"] = "ghost:%d" % rng.randrange(5)
+            else:
+                l["source"], l["target"] = "ghost:%d" % rng.randrange(5), rng.choice(ids)
+            extra.append(l)
+        for p, l in zip(reversed(sorted(rng.sample(range(len(links) + 1), len(extra)))), reversed(extra)):
+            links.insert(p, l)
+        nl["nodes"].append({"id": ids[3], "confidence": 7.5, "level": 2})
+        _same_arrays(csr.csr_from_node_link(nl),
+                     csr.csr_from_networkx(nx.node_link_graph(copy.deepcopy(nl), directed=True, edges="links")))
+
+
+def test_device_snapshot_round_trip_and_invalidation(tmp_path):
+    import json
+    from ah_rag_b200 import csr, synth
+    from ah_rag_b200.graph import snapshot
+    from ah_rag_b200.graph.hierarchical_graph import HierarchicalGraph
+    d = str(tmp_path / "graph")
+    nl = synth.make_graph(seed=4, n_entities=120, n_l1=6, n_l2=2, n_hyperedges=40)
+    synth.write_graph_dir(d, nl)
+    hg = HierarchicalGraph.load(d)
+    want = csr.csr_from_networkx(hg.G)
+    _same_arrays(hg._export_arrays(), want)            # built from the document, snapshot written
+    assert os.path.exists(snapshot.path_in(d))
+    hg2 = HierarchicalGraph.load(d)
+    hg2._source["doc"] = None                           # force the snapshot route
+    _same_arrays(hg2._export_arrays(), want)
+    # a changed structure.json makes the snapshot stale: ignored, rebuilt
+    with open(os.path.join(d, "structure.json"), "r", encoding="utf-8") as f:
+        doc = json.load(f)
+    doc["links"] = doc["links"][:-3]
+    with open(os.path.join(d, "structure.json"), "w", encoding="utf-8") as f:
+        json.dump(doc, f)
+    hg3 = HierarchicalGraph.load(d)
+    assert snapshot.load(d, hg3._source["key"]) is None
+    _same_arrays(hg3._export_arrays(), csr.csr_from_networkx(hg3.G))
+    assert snapshot.load(d, hg3._source["key"]) is not None
+    # an edited graph is no longer its document: NetworkX walk
+    hg3.add_entity("Somebody New")
+    assert hg3._source is None
+    _same_arrays(hg3._export_arrays(), csr.csr_from_networkx(hg3.G))
+    # a corrupt snapshot is ignored, not an error
+    with open(snapshot.path_in(d), "wb") as f:
+        f.write(b"not a zip")
+    hg4 = HierarchicalGraph.load(d)
+    _same_arrays(hg4._export_arrays(), csr.csr_from_networkx(hg4.G))
