@@ -54,6 +54,7 @@ class HierarchicalGraph:
         self._dev_graph: Optional[Dict[str, Any]] = None
         self._dev_index: Optional[Dict[str, Any]] = None
         self._source: Optional[Dict[str, Any]] = None  # set by load(): lets the device export skip the NetworkX walk
+        self._host_arrays: Optional[Tuple[Any, Dict[str, Any]]] = None
         self._st_model = None
         self._st_name: Optional[str] = None
 
@@ -78,6 +79,7 @@ class HierarchicalGraph:
     def _touch(self) -> None:
         self.G.graph["dirty"] = True
         self._dev_graph = None
+        self._host_arrays = None
         self._source = None  # the graph no longer is the document it was loaded from
 
     def add_entity(self, name: str, description: Optional[str] = None, entity_type: Optional[str] = None,
@@ -327,11 +329,18 @@ class HierarchicalGraph:
         self._dev_index = None
 
     # ------------------------------------------------------------------ device residency
+    def _graph_arrays(self) -> Dict[str, Any]:
+        """Host copy of the CSR + attribute arrays of the current graph (cached until the graph changes)."""
+        sig = (id(self.G), self.G.number_of_nodes(), self.G.number_of_edges())
+        if self._host_arrays is None or self._host_arrays[0] != sig:
+            self._host_arrays = (sig, self._export_arrays())
+        return self._host_arrays[1]
+
     def _device_graph(self) -> Dict[str, Any]:
         sig = (id(self.G), self.G.number_of_nodes(), self.G.number_of_edges())
         if self._dev_graph is None or self._dev_graph["sig"] != sig:
             from .. import engine
-            arrays = self._export_arrays()
+            arrays = self._graph_arrays()
             self._dev_graph = {"sig": sig, "arrays": arrays, "csr": engine.GraphCSR(arrays, self.device)}
             self._dev_index = None  # row -> node map depends on dense ids
         return self._dev_graph
@@ -378,6 +387,7 @@ class HierarchicalGraph:
 
     def invalidate_device_cache(self) -> None:
         self._dev_graph = None
+        self._host_arrays = None
         self._dev_index = None
 
     # ------------------------------------------------------------------ search (:675-789)

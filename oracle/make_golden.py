@@ -52,7 +52,7 @@ def main() -> None:
         queries = [f"golden query {i}" for i in range(6)]
         qvecs = np.stack([stubs.hash_embed(q) for q in queries])
         fixture = {"name": spec["name"], "make_graph_kwargs": spec["kw"], "node_link": g,
-                   "index_ids": rs.index_ids, "queries": queries, "search": [], "env": [], "gym": []}
+                   "index_ids": rs.index_ids, "queries": queries, "search": [], "env": [], "gym": [], "lca": []}
         for qi, q in enumerate(queries):
             for case in SEARCH_CASES:
                 out = ref_runner.strip_search(rs.search(q, **case))
@@ -75,6 +75,22 @@ def main() -> None:
             o, i = env.expand_related(ids[:2])
             trace.append({"call": "expand_related", "args": {"node_ids": ids[:2], "limit": 10}, "obs": o, "info": i})
             fixture["env"].append(trace)
+        # expand_to_lca (environment.py:243-299): summaries, entities, mixed sets, a node without belongs_to edges
+        lenv = rs.make_env()
+        G = rs.hg.G
+        by_type = {t: [n for n, d in G.nodes(data=True) if d.get("node_type") == t] for t in ("entity", "summary", "hyperedge")}
+        ents, sums = by_type["entity"], by_type["summary"]
+        parent_of = lambda n: [v for _, v, d in G.out_edges(n, data=True) if d.get("edge_type") == "belongs_to"]
+        cases = [[s_] for s_ in sums[:3]] + [sums[:2], sums[-2:], ents[:1], ents[:2], [ents[0]] + parent_of(ents[0])[:1],
+                                             parent_of(ents[1])[:1] + [ents[1]], [], by_type["hyperedge"][:1], ["not-a-node"]]
+        for ids in cases:
+            for mr in (5, 1):
+                try:
+                    o, i = lenv.expand_to_lca(list(ids), max_results=mr)
+                    i = {k: v for k, v in i.items() if k != "time_s"}
+                    fixture["lca"].append({"node_ids": list(ids), "max_results": mr, "obs": o, "info": i})
+                except Exception as e:  # nx.ancestors on a node outside the belongs_to subgraph
+                    fixture["lca"].append({"node_ids": list(ids), "max_results": mr, "raises": type(e).__name__})
         for si, seq in enumerate(GYM_ACTION_SEQS):
             gym = rs.make_gym(max_steps=6)
             qi = si % len(queries)
