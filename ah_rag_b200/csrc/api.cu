@@ -315,6 +315,10 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
   }
 
   // ---- exact mode ----
+  // Tiers: (1) tensor-core candidates with a small slack (kc = 56 for k <= 50: the fast 64-slot lists), canonical
+  // rescoring, certification; (2) the queries that could not be certified (near-ties, duplicated rows around rank k) again
+  // with kc = 112; (3) what still fails through the brute-force scan.  Every tier returns the exact answer or hands the
+  // query on, so the result does not depend on which tier served it.
   idx->n_certified = 0;
   idx->n_fallback = 0;
   const bool use_tc = idx->has_map && k <= 96 && idx->n_rows > 4096 && (reinterpret_cast<uintptr_t>(dev_q) & 15) == 0;
@@ -322,14 +326,19 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
     idx->n_fallback = nq;
     return exact_bruteforce(idx, dev_q, nullptr, nq, k, dev_scores, dev_ids, idx->ws, st);
   }
-  const int32_t kc = k <= 40 ? 56 : 112;  // candidates per query: k plus slack for the tensor-core rounding error
-  // scratch: cand scores/ids [nq,kc], exact scores [nq,kc], eps [nq], flags [nq], list [nq], count
-  const size_t nc = (size_t)nq * kc;
+  const int32_t kc_small = 56, kc_big = 112;
+  const int32_t kc1 = k <= 50 ? kc_small : kc_big;
+  const size_t esz = idx->dtype == AHR_DTYPE_F32 ? 4 : 2;
+  const size_t row_bytes = (size_t)idx->dim * esz;
+  // scratch: cand scores/ids [nq,kc], exact scores [nq,kc], eps [nq], flags [nq], list [nq], count,
+  //          final (scores, ids) [nq,k] of a sub-batch, the gathered queries of tier 2, its failure list
+  const size_t nc = (size_t)nq * kc_big;
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
   const size_t o_cs = carve(nc * 4), o_ci = carve(nc * 8), o_ex = carve(nc * 4), o_eps = carve((size_t)nq * 4),
                o_flag = carve((size_t)nq * 4), o_list = carve((size_t)nq * 4), o_cnt = carve(4),
-               o_fs = carve((size_t)nq * k * 4), o_fi = carve((size_t)nq * k * 8);
+               o_fs = carve((size_t)nq * k * 4), o_fi = carve((size_t)nq * k * 8), o_list2 = carve((size_t)nq * 4),
+               o_qsub = carve(kc1 == kc_small ? (size_t)nq * row_bytes : 0);
   int rc = idx->ws2.reserve(off);
   if (rc != AHR_OK) return rc;
   uint8_t *w = reinterpret_cast<uint8_t *>(idx->ws2.ptr);
@@ -339,14 +348,11 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
   float *eps = reinterpret_cast<float *>(w + o_eps);
   int32_t *flags = reinterpret_cast<int32_t *>(w + o_flag);
   int32_t *flist = reinterpret_cast<int32_t *>(w + o_list);
+  int32_t *flist2 = reinterpret_cast<int32_t *>(w + o_list2);
   int32_t *fcnt = reinterpret_cast<int32_t *>(w + o_cnt);
   float *fs = reinterpret_cast<float *>(w + o_fs);
   int64_t *fi = reinterpret_cast<int64_t *>(w + o_fi);
-
-  rc = tc_topk(idx, dev_q, nq, kc, cs, ci, nullptr, st);
-  if (rc != AHR_OK) return rc;
-  rc = exact_rescore(idx->rows, dev_q, idx->dtype, idx->dim, nq, kc, ci, idx->id_base, ex, st);
-  if (rc != AHR_OK) return rc;
+  void *qsub = w + o_qsub;
   // |tensor - canonical| <= eps_rel * ||q|| * ||x||: fp32 accumulation over dim/16 MMA steps plus the in-step
   // alignment of 16 exact products; 2^-23 per accumulation step with generous headroom
   // fp32 rows go through the hi/lo split: 3x the accumulation steps plus the dropped lo*lo and residual terms
@@ -354,14 +360,43 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
   const float eps_rel = idx->dtype == AHR_DTYPE_F32
                             ? (float)((3 * idx->dim / 8 + 32) * std::ldexp(1.0, -23) + std::ldexp(1.0, -16))
                             : (float)((idx->dim / 8 + 32) * std::ldexp(1.0, -23));
-  rc = query_eps(dev_q, idx->dtype, nq, idx->dim, idx->d_max_norm, eps_rel, eps, st);
-  if (rc != AHR_OK) return rc;
-  AHR_CUDA_CHECK(cudaMemsetAsync(fcnt, 0, 4, st));
-  rc = exact_certify(cs, ci, ex, nq, kc, k, eps, dev_scores, dev_ids, flags, fcnt, flist, st);
-  if (rc != AHR_OK) return rc;
+  // one tier over `n` queries at `q`: results into out_* [n, k], uncertified query indices into `fail_list`
+  auto tier = [&](const void *q, int32_t n, int32_t kc, float *out_s, int64_t *out_i, int32_t *fail_list, int32_t *n_fail) {
+    int r = tc_topk(idx, q, n, kc, cs, ci, nullptr, st);
+    if (r == AHR_OK) r = exact_rescore(idx->rows, q, idx->dtype, idx->dim, n, kc, ci, idx->id_base, ex, st);
+    if (r == AHR_OK) r = query_eps(q, idx->dtype, n, idx->dim, idx->d_max_norm, eps_rel, eps, st);
+    if (r != AHR_OK) return r;
+    AHR_CUDA_CHECK(cudaMemsetAsync(fcnt, 0, 4, st));
+    r = exact_certify(cs, ci, ex, n, kc, k, eps, out_s, out_i, flags, fcnt, fail_list, st);
+    if (r != AHR_OK) return r;
+    AHR_CUDA_CHECK(cudaMemcpyAsync(n_fail, fcnt, 4, cudaMemcpyDeviceToHost, st));
+    AHR_CUDA_CHECK(cudaStreamSynchronize(st));
+    return (int)AHR_OK;
+  };
   int32_t n_fail = 0;
-  AHR_CUDA_CHECK(cudaMemcpyAsync(&n_fail, fcnt, 4, cudaMemcpyDeviceToHost, st));
-  AHR_CUDA_CHECK(cudaStreamSynchronize(st));
+  rc = tier(dev_q, nq, kc1, dev_scores, dev_ids, flist, &n_fail);
+  if (rc != AHR_OK) return rc;
+  if (n_fail > 0 && kc1 == kc_small) {
+    // tier 2 on the sub-batch of uncertified queries
+    const int32_t n1 = n_fail;
+    rc = gather_query_rows(dev_q, (int64_t)row_bytes, flist, n1, qsub, st);
+    if (rc != AHR_OK) return rc;
+    int32_t n2 = 0;
+    rc = tier(qsub, n1, kc_big, fs, fi, flist2, &n2);
+    if (rc != AHR_OK) return rc;
+    rc = gather_rows_i64(fs, fi, flist, n1, k, dev_scores, dev_ids, /*scatter=*/true, st);  // rows of tier-2 failures are
+    if (rc != AHR_OK) return rc;                                                          // overwritten by tier 3 below
+    if (n2 > 0) {  // compose the failure list: positions in the sub-batch -> original query indices
+      std::vector<int32_t> h1(n1), h2(n2);
+      AHR_CUDA_CHECK(cudaMemcpyAsync(h1.data(), flist, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+      AHR_CUDA_CHECK(cudaMemcpyAsync(h2.data(), flist2, (size_t)n2 * 4, cudaMemcpyDeviceToHost, st));
+      AHR_CUDA_CHECK(cudaStreamSynchronize(st));
+      for (int32_t i = 0; i < n2; ++i) h2[i] = h1[h2[i]];
+      AHR_CUDA_CHECK(cudaMemcpyAsync(flist, h2.data(), (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
+      AHR_CUDA_CHECK(cudaStreamSynchronize(st));  // h2 goes out of scope
+    }
+    n_fail = n2;
+  }
   idx->n_certified = nq - n_fail;
   idx->n_fallback = n_fail;
   if (n_fail > 0) {

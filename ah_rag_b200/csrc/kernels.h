@@ -63,6 +63,8 @@ int query_eps(const void *dev_q, int dtype, int32_t nq, int32_t dim, const float
 int gather_rows_i64(const float *src_s, const int64_t *src_i, const int32_t *sel, int32_t n_sel, int32_t k,
                     float *dst_s, int64_t *dst_i, bool scatter, cudaStream_t stream);
 
+int gather_query_rows(const void *src, int64_t row_bytes, const int32_t *sel, int32_t n_sel, void *out, cudaStream_t stream);
+
 // ---- graph.cu (K2) ----
 struct GraphView {
   int64_t n_nodes;

@@ -314,4 +314,23 @@ int gather_rows_i64(const float *src_s, const int64_t *src_i, const int32_t *sel
   return AHR_OK;
 }
 
+// out[i] = src[sel[i]] for rows of row_words 32-bit words (query sub-batches of the tiered exact mode)
+__global__ void gather_words_kernel(const uint32_t *__restrict__ src, int64_t row_words, const int32_t *__restrict__ sel,
+                                    int32_t n_sel, uint32_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_sel * row_words) return;
+  const int64_t r = i / row_words, c = i - r * row_words;
+  out[i] = src[(int64_t)sel[r] * row_words + c];
+}
+
+int gather_query_rows(const void *src, int64_t row_bytes, const int32_t *sel, int32_t n_sel, void *out, cudaStream_t stream) {
+  AHR_REQUIRE(row_bytes % 4 == 0, "gather_query_rows: rows must be a whole number of 32-bit words");
+  const int64_t total = (int64_t)n_sel * (row_bytes / 4);
+  if (total <= 0) return AHR_OK;
+  gather_words_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint32_t *>(src), row_bytes / 4,
+                                                                           sel, n_sel, reinterpret_cast<uint32_t *>(out));
+  AHR_KERNEL_CHECK();
+  return AHR_OK;
+}
+
 }  // namespace ahr

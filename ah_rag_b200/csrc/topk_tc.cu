@@ -245,13 +245,15 @@ static constexpr size_t tc_smem_bytes() {
 template <int KLIST, int STAGES, bool DBG>
 static int tc_launch_t(const CUtensorMap &map_q, const CUtensorMap &map_x, const TcParams &p, int grid,
                        cudaStream_t stream) {
-  static bool configured = false;
+  static std::atomic<uint64_t> configured{0};  // bit d: attribute set on device d (function attributes are per device)
   constexpr size_t smem = tc_smem_bytes<KLIST, STAGES>();
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
-  if (!configured) {
+  int dev = 0;
+  AHR_CUDA_CHECK(cudaGetDevice(&dev));
+  if (!((configured.load(std::memory_order_relaxed) >> (dev & 63)) & 1)) {
     AHR_CUDA_CHECK(cudaFuncSetAttribute(topk_tc_kernel<KLIST, STAGES, DBG>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
   }
   topk_tc_kernel<KLIST, STAGES, DBG><<<grid, TC_THREADS, smem, stream>>>(map_q, map_x, p);
   AHR_KERNEL_CHECK();

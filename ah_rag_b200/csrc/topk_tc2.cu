@@ -284,13 +284,15 @@ template <int KLIST, int NA, int NB, bool DBG>
 static int tc2_launch_t(const CUtensorMap &map_q, const CUtensorMap &map_x, const CUtensorMap &map_q_lo,
                         const CUtensorMap &map_x_lo, const TcParams &p, int n_clusters,
                         cudaStream_t stream) {
-  static bool configured = false;
+  static std::atomic<uint64_t> configured{0};  // bit d: attribute set on device d (function attributes are per device)
   constexpr size_t smem = tc2_smem_bytes<KLIST, NA, NB>();
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
-  if (!configured) {
+  int dev = 0;
+  AHR_CUDA_CHECK(cudaGetDevice(&dev));
+  if (!((configured.load(std::memory_order_relaxed) >> (dev & 63)) & 1)) {
     AHR_CUDA_CHECK(cudaFuncSetAttribute(topk_tc2_kernel<KLIST, NA, NB, DBG>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
   }
   topk_tc2_kernel<KLIST, NA, NB, DBG><<<2 * n_clusters, TC_THREADS, smem, stream>>>(map_q, map_x, map_q_lo, map_x_lo, p);
   AHR_KERNEL_CHECK();

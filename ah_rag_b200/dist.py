@@ -60,19 +60,37 @@ class ShardedIndex:
 
     def enable_peer_exchange(self, max_queries: int, max_k: int) -> bool:
         """Switch the exchange to peer-memory stores (one-time rendezvous of CUDA IPC handles over the process group).
-        Returns False and keeps the all-gather when ``AHR_EXCHANGE=nccl`` is set or the world has one rank."""
+        Collective: every rank must call it.  Returns True on every rank or False on every rank -- a rank that cannot
+        allocate, export or map a buffer (e.g. CUDA IPC not permitted in the container) still takes part in the two
+        collectives below, so nobody is left waiting, and all ranks keep the all-gather.  ``AHR_EXCHANGE=nccl`` opts out."""
         import os
         from . import engine
+        self.peer = None
         if self.world == 1 or os.environ.get("AHR_EXCHANGE", "peer") == "nccl":
             return False
-
-        def swap(mine: bytes):
-            out = [None] * self.world
-            dist.all_gather_object(out, mine, group=self.group)
-            return out
-
-        self.peer = engine.PeerExchange(self.index.device, self.rank, self.world, max_queries * max_k * 12, swap)
-        return True
+        peer, handle, why = None, None, ""
+        try:
+            peer = engine.PeerExchange(self.index.device, self.rank, self.world, max_queries * max_k * 12)
+            handle = peer.export_handle()
+        except Exception as e:  # noqa: BLE001 -- reported below, the collectives must still run
+            why = repr(e)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=self.group)
+        ok = all(h is not None for h in handles)
+        if ok:
+            try:
+                peer.connect(handles)
+            except Exception as e:  # noqa: BLE001
+                ok, why = False, repr(e)
+        flags = [None] * self.world
+        dist.all_gather_object(flags, (ok, why), group=self.group)
+        if all(f[0] for f in flags):
+            self.peer = peer
+            return True
+        self.peer_failure = "; ".join(f"rank {r}: {f[1]}" for r, f in enumerate(flags) if f[1])
+        if peer is not None:
+            peer.close()
+        return False
 
     def topk(self, q: torch.Tensor, k: int, mode: str = "bf16") -> Tuple[torch.Tensor, torch.Tensor]:
         if self.world == 1:

@@ -416,26 +416,34 @@ class EnvBatchState:
 
 class PeerExchange:
     """Handle over ``ahr_comm``: the cross-GPU candidate exchange through NVLink peer memory (csrc/exchange.cu).
-    ``swap_handles(my_handle: bytes) -> list[bytes]`` is any all-gather of 64-byte blobs in rank order (the one-time
-    rendezvous; ``torch.distributed.all_gather_object`` in ``dist.ShardedIndex``)."""
+    Rendezvous (once): every rank creates its buffer and ``export_handle()``s 64 bytes, the ranks swap them over any
+    transport, every rank ``connect(handles)``s.  ``dist.ShardedIndex.enable_peer_exchange`` does this over the process
+    group with collective-safe error handling."""
 
-    def __init__(self, device: torch.device, rank: int, world: int, max_record_bytes: int, swap_handles) -> None:
+    def __init__(self, device: torch.device, rank: int, world: int, max_record_bytes: int, swap_handles=None) -> None:
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.rank, self.world = int(rank), int(world)
+        self.max_record_bytes = int(max_record_bytes)
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             check(self.lib.ahr_comm_create(ctypes.byref(self._h), self.device.index or 0, self.rank, self.world,
-                                           int(max_record_bytes)), "ahr_comm_create")
-            mine = ctypes.create_string_buffer(_lib.AHR_IPC_HANDLE_BYTES)
+                                           self.max_record_bytes), "ahr_comm_create")
+        if swap_handles is not None and self.world > 1:
+            self.connect(swap_handles(self.export_handle()))
+
+    def export_handle(self) -> bytes:
+        mine = ctypes.create_string_buffer(_lib.AHR_IPC_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
             check(self.lib.ahr_comm_export(self._h, mine), "ahr_comm_export")
-            if self.world > 1:
-                handles = swap_handles(bytes(mine.raw))
-                if len(handles) != self.world or any(len(h) != _lib.AHR_IPC_HANDLE_BYTES for h in handles):
-                    raise RuntimeError("swap_handles must return one 64-byte handle per rank")
-                blob = ctypes.create_string_buffer(b"".join(handles), self.world * _lib.AHR_IPC_HANDLE_BYTES)
-                check(self.lib.ahr_comm_connect(self._h, blob), "ahr_comm_connect")
-        self.max_record_bytes = int(max_record_bytes)
+        return bytes(mine.raw)
+
+    def connect(self, handles: Sequence[bytes]) -> None:
+        if len(handles) != self.world or any(h is None or len(h) != _lib.AHR_IPC_HANDLE_BYTES for h in handles):
+            raise RuntimeError("connect needs one 64-byte handle per rank, in rank order")
+        blob = ctypes.create_string_buffer(b"".join(handles), self.world * _lib.AHR_IPC_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_comm_connect(self._h, blob), "ahr_comm_connect")
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:

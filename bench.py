@@ -225,17 +225,12 @@ def main() -> int:
     if world > 1:
         # candidate exchange: stores into the peers' memory over NVLink (csrc/exchange.cu); AHR_EXCHANGE=nccl keeps the
         # all-gather.  The choice is made by every rank together (a failed IPC mapping on one rank falls back on all).
-        ok = 0
-        try:
-            ok = 1 if sharded.enable_peer_exchange(N_QUERIES, TOP_K) else 0
-        except RuntimeError as e:  # e.g. CUDA IPC not permitted in this container
-            print(f"bench.py[rank {rank}]: peer exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
-        flag = torch.tensor([ok], device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 1:
+        if sharded.enable_peer_exchange(N_QUERIES, TOP_K):  # collective; True on all ranks or False on all ranks
             exchange = "peer-memory stores over NVLink + epoch flags (csrc/exchange.cu), device k-way merge"
         else:
-            sharded.peer = None
+            why = getattr(sharded, "peer_failure", "") or os.environ.get("AHR_EXCHANGE", "")
+            if rank == 0 and why:
+                print(f"bench.py: peer exchange not used ({why}); NCCL all-gather instead", file=sys.stderr)
             exchange = "single NCCL all-gather + device k-way merge"
     q_dev = make_queries(torch, device, N_QUERIES, DIM)
     q_host = q_dev.cpu().pin_memory()

@@ -38,6 +38,9 @@ def _worker(rank, world, port, n, dim, nq, k, q):
 
         sh = ShardedIndex(local_topk, merge)
         assert sh.world == world and sh.rank == rank
+        # no GPU here: the peer-memory rendezvous must fail on every rank TOGETHER (collective-safe) and leave the
+        # all-gather path in place
+        assert sh.enable_peer_exchange(16, kk_max := 32) is False and sh.peer is None and kk_max
         s, i = sh.topk(torch.from_numpy(Q), k, "exact")
         ws, wi = exact.exact_topk(X, Q, k)
         ok = np.array_equal(i.numpy(), wi) and np.array_equal(s.numpy().view(np.uint32), ws.view(np.uint32))

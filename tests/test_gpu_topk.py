@@ -102,6 +102,27 @@ def test_exact_mode_fallback_on_near_ties(engine):
     assert list(i[0].cpu().numpy()) == list(range(999, 999 + k))
 
 
+def test_exact_mode_second_tier_resolves_moderate_tie_groups(engine):
+    """A group of identical rows straddling rank k defeats the first tier (6 spare candidates) but not the second
+    (62 spare): certified there, no brute-force scan, ties still broken by the lower id."""
+    n, dim, nq, k = 20000, 128, 5, 50
+    Xn = synth.unit_rows(n, dim, 13)
+    Qn = synth.unit_rows(nq, dim, 14)
+    near = Qn[0] + 0.05 * synth.unit_rows(1, dim, 15)[0]
+    near /= np.linalg.norm(near)
+    Xn[3000:3040] = Qn[0]          # ranks 1..40 of query 0
+    Xn[7000:7030] = near           # ranks 41..70: rank 50 falls inside this group of equal scores
+    X, Q = _bf16(Xn), _bf16(Qn)
+    idx = engine.VectorIndex(X)
+    s, i = idx.topk(Q, k, mode="exact")
+    cert, fb = idx.exact_stats()
+    assert (cert, fb) == (nq, 0)
+    rs, ri = exact.exact_topk(_bits(X), _bits(Q), k)
+    assert np.array_equal(i.cpu().numpy(), ri)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), rs.view(np.uint32))
+    assert list(i[0, 40:].cpu().numpy()) == list(range(7000, 7010))
+
+
 def test_topk_host_entry_point(engine):
     n, dim, nq, k = 3000, 128, 33, 20
     X = _bf16(synth.unit_rows(n, dim, 11))
