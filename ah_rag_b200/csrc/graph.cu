@@ -489,7 +489,7 @@ int graph_anchor_rerank(const GraphView &g, int32_t nq, int32_t n_seeds, const i
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EXP_WARPS * 32)
 expand_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const int32_t *__restrict__ in_ids,
-              const int32_t *__restrict__ in_offsets, int32_t limit, int32_t *__restrict__ out_ids,
+              const int32_t *__restrict__ in_offsets, int32_t limit, int hash_slots, int32_t *__restrict__ out_ids,
               int32_t *__restrict__ out_counts) {
   extern __shared__ int32_t sm_out[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -498,6 +498,12 @@ expand_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const
   ExpandState st;
   st.out = sm_out + (size_t)w * limit;
   st.count = 0; st.raw = 0; st.limit = limit;
+  if (hash_slots > 0) {  // large limits: a hash set instead of scanning the list for every candidate
+    st.hash = sm_out + (size_t)EXP_WARPS * limit + (size_t)w * hash_slots;
+    st.hmask = hash_slots - 1;
+    for (int j = lane; j < hash_slots; j += 32) st.hash[j] = -1;
+    __syncwarp();
+  }
   expand_walk(st, g, ops[env], in_ids + in_offsets[env], in_offsets[env + 1] - in_offsets[env], lane);
   for (int j = lane; j < limit; j += 32) out_ids[(int64_t)env * limit + j] = j < st.count ? st.out[j] : -1;
   if (lane == 0) out_counts[env] = st.count;
@@ -507,9 +513,24 @@ int graph_expand(const GraphView &g, int32_t n_env, const int32_t *ops, const in
                  const int32_t *in_offsets, int32_t limit, int32_t *out_ids, int32_t *out_counts, cudaStream_t stream) {
   AHR_REQUIRE(limit >= 1 && limit <= 2048, "expand: limit must be in [1, 2048] (got %d)", limit);
   if (n_env <= 0) return AHR_OK;
-  const size_t smem = (size_t)EXP_WARPS * limit * sizeof(int32_t);
+  // the list can hold `limit` values but a batch of up to 32 is inserted before the cut: 2 * (limit + 32) slots, power of 2
+  int hash_slots = 0;
+  if (limit > 64) {
+    hash_slots = 128;
+    while (hash_slots < 2 * (limit + 32)) hash_slots <<= 1;
+  }
+  const size_t smem = (size_t)EXP_WARPS * (limit + hash_slots) * sizeof(int32_t);
+  if (smem > 48 * 1024) {
+    static std::atomic<uint64_t> configured{0};
+    int dev = 0;
+    AHR_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!((configured.load(std::memory_order_relaxed) >> (dev & 63)) & 1)) {
+      AHR_CUDA_CHECK(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024));
+      configured.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
+    }
+  }
   expand_kernel<<<(n_env + EXP_WARPS - 1) / EXP_WARPS, EXP_WARPS * 32, smem, stream>>>(g, n_env, ops, in_ids, in_offsets,
-                                                                                      limit, out_ids, out_counts);
+                                                                                      limit, hash_slots, out_ids, out_counts);
   AHR_KERNEL_CHECK();
   return AHR_OK;
 }

@@ -13,19 +13,32 @@ struct ExpandState {
   int count;
   int raw;
   int limit;
+  int32_t *hash = nullptr;  // optional open-addressing set of the values in `out` (-1 = free), hmask + 1 slots
+  int hmask = 0;            // used for large limits, where scanning `out` per candidate would be O(limit)
 };
 
 // append values to the order-preserving unique list; returns true once the list is full
 __device__ __forceinline__ bool expand_push(ExpandState &st, int32_t val, bool valid, int lane) {
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   st.raw += __popc(vmask);
-  bool dup = false;
-  if (valid) {
-    for (int t = 0; t < st.count; ++t) dup |= (st.out[t] == val);
-  }
   // duplicates inside this batch of 32: the lowest lane carrying the value is the first occurrence
   const unsigned peers = __match_any_sync(0xffffffffu, valid ? val : (int32_t)(-2 - lane));
   const bool first_in_batch = (__ffs(peers & vmask) - 1) == lane;
+  bool dup = false;
+  if (st.hash != nullptr) {
+    // only the batch's representative of a value probes / inserts, so lane order still decides the list order
+    if (valid && first_in_batch) {
+      int slot = (int)(((uint32_t)val * 2654435761u) >> 8) & st.hmask;
+      for (;;) {
+        const int32_t k = atomicCAS(&st.hash[slot], -1, val);
+        if (k == -1) break;
+        if (k == val) { dup = true; break; }
+        slot = (slot + 1) & st.hmask;
+      }
+    }
+  } else if (valid) {
+    for (int t = 0; t < st.count; ++t) dup |= (st.out[t] == val);
+  }
   const bool fresh = valid && !dup && first_in_batch;
   const unsigned nmask = __ballot_sync(0xffffffffu, fresh);
   const int pos = st.count + __popc(nmask & ((1u << lane) - 1u));

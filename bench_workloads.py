@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench_workloads.py -- the BASELINE.json configurations other than the headline (which is bench.py's job).
 
-    python bench_workloads.py [c3x] [c4] [c5] [c2]        (default: all; one GPU; a few minutes)
+    python bench_workloads.py [c3x] [c4] [c5] [c2] [qsweep] [shard8] [adv]     (default: c3x c4 c5 c2; one GPU)
+    torchrun --nproc-per-node N bench_workloads.py c4dist c5dist            (the sharded configurations, N = 2/4/8)
 
   c3x  c3 in fp32-EXACT mode: bit-exact ids at tensor-core speed (candidates + canonical rescoring + certification)
   c4   one shard of the 100M x 768 corpus at 8 GPUs (12.5M rows), 256-query batch: the HBM-bound regime of K1
@@ -365,11 +366,115 @@ def run_c2(dev):
                       "bf16_ms": msb, "bf16_queries_per_s": nq / msb * 1e3}))
 
 
+def _dist_setup():
+    import torch.distributed as dist
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    return dist, world, rank, dev
+
+
+def _timed_dist(dist, world, dev, fn, steps, warmup=3):
+    """bench.py's timing: barrier + synchronize on both sides, CUDA events, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def run_c4dist():
+    """configs[3]: 100M x 768 bf16 sharded by node range over the ranks of `torchrun`, 256-query batch, k = 50
+    (strong scaling on the fixed corpus; run with 2, 4 or 8 ranks -- one GPU cannot hold the 153.6 GB)."""
+    from ah_rag_b200.dist import ShardedIndex, shard_bounds
+    dist, world, rank, dev = _dist_setup()
+    n_total, dim, nq, k = 100_000_000, 768, 256, 50
+    hbm, tf, src = peaks()
+    lo, hi = shard_bounds(n_total, world, rank)
+    assert (hi - lo) * dim * 2 < 150e9, "shard does not fit one GPU: use more ranks"
+    X = unit_bf16(hi - lo, dim, 1234 + 1000 * rank, dev)
+    Q = unit_bf16(nq, dim, 5678, dev)
+    sh = ShardedIndex.from_rows(X, id_base=lo)
+    peer = sh.enable_peer_exchange(nq, k) if world > 1 else False
+    sh.index.set_profiling(True)
+    ms = _timed_dist(dist, world, dev, lambda: sh.topk(Q, k, mode="bf16"), steps=20)
+    prof = sh.index.get_profile()
+    k1 = prof["k1_ms_total"] / max(1, prof["k1_launches"])
+    t_mem = 2.0 * (hi - lo) * dim / (hbm * 1e9) * 1e3
+    t_mma = 2.0 * nq * (hi - lo) * dim / (tf * 1e12) * 1e3
+    if rank == 0:
+        print(json.dumps({"workload": f"c4: 100M x 768 bf16 over {world} GPUs (shards of {hi - lo} rows), Q=256, k=50, bf16 mode",
+                          "n_gpus": world, "ms_per_batch": round(ms, 4), "queries_per_s": round(nq / ms * 1e3, 1),
+                          "k1_ms_rank0": round(k1, 4), "exchange": "peer-memory stores" if peer else ("nccl all-gather" if world > 1 else "none"),
+                          "roofline_rank0": {"t_mem_ms": round(t_mem, 3), "t_mma_ms": round(t_mma, 3),
+                                             "binding": "tensor" if t_mma > t_mem else "hbm",
+                                             "frac": round(max(t_mem, t_mma) / k1, 3),
+                                             "hbm_gbs": round(2.0 * (hi - lo) * dim / (k1 * 1e-3) / 1e9, 1), "peak_source": src}}), flush=True)
+    del sh, X
+
+
+def run_c5dist():
+    """configs[4] at N GPUs: the graph is replicated on every GPU, the 1024 environments are sharded across the ranks
+    (no exchange on the hop path); per batch: anchor expansion + rerank (hop 1, 50 seeds) and one frontier expansion
+    (hop 2) per environment.  Value = environments per second over all ranks."""
+    dist, world, rank, dev = _dist_setup()
+    a = make_c5_graph(dev, float(os.environ.get("AHR_C5_SCALE", "1.0")))
+    g = DeviceGraph(a, dev)
+    n_env_total, n_seeds, top_k, m = 1024, 50, 50, 5
+    n_env = n_env_total // world
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    e_lo, e_hi = a["ranges"]["entity"]
+    l_lo, l_hi = a["ranges"]["l1"]
+    seeds = torch.where(torch.rand((n_env, n_seeds), generator=gen, device=dev) < 0.8,
+                        torch.randint(e_lo, e_hi, (n_env, n_seeds), generator=gen, device=dev),
+                        torch.randint(l_lo, l_hi, (n_env, n_seeds), generator=gen, device=dev)).to(torch.int32)
+    scores = torch.sort(torch.rand((n_env, n_seeds), generator=gen, device=dev) * 0.9 + 0.05, dim=1, descending=True).values
+    scores = scores.to(torch.float32).contiguous()
+    prm = engine.SearchParams(member_top_m=m)
+    ops = torch.randint(0, 3, (n_env,), generator=gen, device=dev).to(torch.int32)
+    offs = (torch.arange(n_env + 1, device=dev) * 2).to(torch.int32)
+
+    def step():
+        out = g.anchor_rerank(seeds, scores, prm, top_k, want_cluster=False)
+        return g.expand(ops, out["nodes"][:, :2].contiguous().view(-1), offs, 10)
+
+    ms = _timed_dist(dist, world, dev, step, steps=50)
+    if rank == 0:
+        print(json.dumps({"workload": f"c5: 20M nodes / {a['n_edges']} edges replicated on {world} GPU(s), {n_env_total} environments "
+                                      f"sharded {n_env} per GPU, hop 1 (50 seeds, rerank) + hop 2 (expand, limit 10)",
+                          "n_gpus": world, "ms_per_batch": round(ms, 4), "envs_per_s": round(n_env_total / ms * 1e3, 1),
+                          "scaling": "environments sharded, graph replicated, no collective"}), flush=True)
+
+
 def main():
     assert torch.cuda.is_available(), "no CUDA device: the engine has no CPU fallback"
+    which = sys.argv[1:] or ["c3x", "c4", "c5", "c2"]
+    if any(w in ("c4dist", "c5dist") for w in which):  # torchrun workloads
+        for w in which:
+            {"c4dist": run_c4dist, "c5dist": run_c5dist}[w]()
+            torch.cuda.empty_cache()
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    which = sys.argv[1:] or ["c3x", "c4", "c5", "c2"]
     for w in which:
         if w == "c3x":
             run_c3x(dev)
