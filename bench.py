@@ -198,6 +198,12 @@ def main() -> int:
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line: everything else any library prints there (NCCL's version banner is a C-level
+    # write to fd 1) is sent to stderr; the line itself goes to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -209,6 +215,7 @@ def main() -> int:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the ONE JSON line, nothing else
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank)
@@ -237,6 +244,8 @@ def main() -> int:
     out_host = (torch.empty((N_QUERIES, TOP_K), dtype=torch.float32).pin_memory(),
                 torch.empty((N_QUERIES, TOP_K), dtype=torch.int64).pin_memory())
 
+    q_stage = torch.empty_like(q_dev)  # device staging of the end-to-end path (multi-GPU)
+
     def sync_all():
         if world > 1:
             dist.barrier()
@@ -248,9 +257,9 @@ def main() -> int:
     def step_e2e():
         if world == 1:
             return index.topk_host(q_host, TOP_K, mode=args.mode, out=out_host)
-        # multi-GPU: host queries -> device, sharded top-k (+ all-gather + merge), result back to the host
-        qd = q_host.to(device, non_blocking=True)
-        s, i = sharded.topk(qd, TOP_K, mode=args.mode)
+        # multi-GPU: host queries -> device, sharded top-k (+ exchange + merge), result back to the host
+        q_stage.copy_(q_host, non_blocking=True)
+        s, i = sharded.topk(q_stage, TOP_K, mode=args.mode)
         out_host[0].copy_(s, non_blocking=True)
         out_host[1].copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -325,7 +334,8 @@ def main() -> int:
             line["cpu_baseline"] = {k: v for k, v in cpu_retrieval.time_sample(
                 N_ROWS, DIM, TOP_K, int(os.environ.get("AHR_BENCH_CPU_ROWS", 500_000)),
                 int(os.environ.get("AHR_BENCH_CPU_QUERIES", 128))).items() if k != "seconds"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -373,6 +373,7 @@ def _dist_setup():
     torch.cuda.set_device(dev)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     return dist, world, rank, dev
 
