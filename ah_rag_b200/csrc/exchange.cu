@@ -27,7 +27,7 @@
 namespace ahr {
 
 constexpr int PUSH_THREADS = 256;
-constexpr int PUSH_BLOCKS = 32;
+constexpr int PUSH_BLOCKS = 64;
 constexpr int MAX_WORLD = 16;
 
 struct PeerTable {
@@ -49,12 +49,18 @@ push_kernel(PeerTable peers, int rank, int world, size_t slot_off, size_t rec_by
   const uint8_t *src = peers.base[rank] + slot_off;
   const size_t n16 = rec_bytes / 16;
   const size_t total = n16 * (size_t)(world - 1);
-  for (size_t i = (size_t)blockIdx.x * PUSH_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * PUSH_THREADS) {
-    const int pi = (int)(i / n16);
+  (void)total;
+  const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
+  const size_t stride = (size_t)gridDim.x * PUSH_THREADS;
+  for (int pi = 0; pi < world - 1; ++pi) {
     const int peer = pi < rank ? pi : pi + 1;
-    const size_t at = i - (size_t)pi * n16;
-    const uint4 v = reinterpret_cast<const uint4 *>(src)[at];
-    reinterpret_cast<uint4 *>(peers.base[peer] + slot_off)[at] = v;  // NVLink store into the peer's slot `rank`
+    uint4 *dst4 = reinterpret_cast<uint4 *>(peers.base[peer] + slot_off);  // the peer's slot `rank`, over NVLink
+    size_t i = (size_t)blockIdx.x * PUSH_THREADS + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {  // four independent loads in flight per thread
+      const uint4 v0 = src4[i], v1 = src4[i + stride], v2 = src4[i + 2 * stride], v3 = src4[i + 3 * stride];
+      dst4[i] = v0; dst4[i + stride] = v1; dst4[i + 2 * stride] = v2; dst4[i + 3 * stride] = v3;
+    }
+    for (; i < n16; i += stride) dst4[i] = src4[i];
   }
   __threadfence_system();
   __syncthreads();
@@ -188,21 +194,42 @@ int ahr_comm_exchange_merge(ahr_comm *c, int32_t nq, int32_t k, float *dev_out_s
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t sb = (size_t)nq * k * 4, rec = sb * 3;
   const int half = (int)(c->epoch & 1);
+  static const bool stats = getenv("AHR_COMM_STATS") != nullptr;  // debug: per-phase device times on stderr (synchronises)
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (stats)
+    for (auto &e : ev) AHR_CUDA_CHECK(cudaEventCreate(&e));
+  if (stats) AHR_CUDA_CHECK(cudaEventRecord(ev[0], st));
   if (c->world > 1) {
     PeerTable t;
     for (int p = 0; p < MAX_WORLD; ++p) t.base[p] = p < c->world ? c->peer[p] : nullptr;
     push_kernel<<<PUSH_BLOCKS, PUSH_THREADS, 0, st>>>(t, c->rank, c->world, c->slot_offset(half, c->rank), rec,
                                                       c->flag_offset(half), c->epoch, c->done_counter);
     AHR_KERNEL_CHECK();
+    if (stats) AHR_CUDA_CHECK(cudaEventRecord(ev[1], st));
     wait_flags_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const uint64_t *>(c->base + c->flag_offset(half)), c->rank,
                                         c->world, c->epoch);
     AHR_KERNEL_CHECK();
+  } else if (stats) {
+    AHR_CUDA_CHECK(cudaEventRecord(ev[1], st));
   }
+  if (stats) AHR_CUDA_CHECK(cudaEventRecord(ev[2], st));
   // k-way merge over the world slots of this half: part p at + p * max_record
   const float *scores = reinterpret_cast<const float *>(c->base + c->slot_offset(half, 0));
   const int64_t *ids = reinterpret_cast<const int64_t *>(c->base + c->slot_offset(half, 0) + sb);
-  return select_topk_strided2(scores, nullptr, ids, k, (int64_t)c->world * k, k, (int64_t)(c->max_record / 4),
-                              (int64_t)(c->max_record / 8), nq, k, 0, false, dev_out_scores, dev_out_ids, st);
+  int rc = select_topk_strided2(scores, nullptr, ids, k, (int64_t)c->world * k, k, (int64_t)(c->max_record / 4),
+                                (int64_t)(c->max_record / 8), nq, k, 0, false, dev_out_scores, dev_out_ids, st);
+  if (stats && rc == AHR_OK) {
+    AHR_CUDA_CHECK(cudaEventRecord(ev[3], st));
+    AHR_CUDA_CHECK(cudaEventSynchronize(ev[3]));
+    float t_push = 0, t_wait = 0, t_merge = 0;
+    cudaEventElapsedTime(&t_push, ev[0], ev[1]);
+    cudaEventElapsedTime(&t_wait, ev[1], ev[2]);
+    cudaEventElapsedTime(&t_merge, ev[2], ev[3]);
+    fprintf(stderr, "[ahr comm stats] rank %d epoch %llu: push %.1f us (%.1f MB to %d peers), wait %.1f us, merge %.1f us\n",
+            c->rank, (unsigned long long)c->epoch, t_push * 1e3, rec / 1e6, c->world - 1, t_wait * 1e3, t_merge * 1e3);
+    for (auto &e : ev) cudaEventDestroy(e);
+  }
+  return rc;
 }
 
 }  // extern "C"
