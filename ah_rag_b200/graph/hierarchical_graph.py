@@ -471,41 +471,47 @@ class HierarchicalGraph:
             return [dict(empty) if return_cluster else [] for _ in range(B)]
         k_eff = min(int(top_k), n_index)  # Chroma returns at most the collection size
         out, rows = self._device_search(query_embeddings, int(top_k), params, return_cluster, db_path)
-        host = {k: v.cpu().numpy() for k, v in out.items()}
-        rows_h = rows.cpu().numpy() if return_cluster else None
-        node_ids, G = arrays["node_ids"], self.G
-        from ..csr import judge_overall
+        # one device -> host copy per output, then plain Python lists (numpy scalar indexing would dominate the loop)
+        host = {k: v.cpu().numpy().tolist() for k, v in out.items()}
+        rows_h = rows.cpu().numpy().tolist() if return_cluster else None
+        node_ids, nodes_view = arrays["node_ids"], self.G.nodes
+        judge_arr = arrays["judge"]  # float(js["overall"]) per node, NaN = None: the value `search` re-parses per result
         results: List[Any] = []
         for b in range(B):
             reranked = []
-            for j in range(int(host["count"][b])):
-                nid = node_ids[int(host["nodes"][b, j])]
-                d = G.nodes.get(nid, {})
+            h_nodes, h_sem, h_score = host["nodes"][b], host["semantic"][b], host["score"][b]
+            for j in range(host["count"][b]):
+                v = h_nodes[j]
+                nid = node_ids[v]
+                d = nodes_view.get(nid, {})
                 nt = d.get("node_type")
+                ju = judge_arr[v]
                 reranked.append({"node_id": nid, "node_type": nt, "layer": 1 if nt == "summary" else 0,
-                                 "semantic": float(host["semantic"][b, j]), "judge_overall": judge_overall(d),
-                                 "confidence": d.get("confidence"), "score": float(host["score"][b, j]),
+                                 "semantic": h_sem[j], "judge_overall": None if ju != ju else float(ju),
+                                 "confidence": d.get("confidence"), "score": h_score[j],
                                  "name": d.get("name"), "title": d.get("title")})
             if not return_cluster:
                 results.append(reranked)
                 continue
             seeds, seed_meta = [], {}
+            seed_sem = host["seed_semantic"][b]
             for r in range(k_eff):
-                row = int(rows_h[b, r])
+                row = rows_h[b][r]
                 if row < 0:
                     continue
                 nid = store.ids[row]
-                seeds.append({"node_id": nid, "semantic": float(host["seed_semantic"][b, r]), "meta": store.metas[row]})
+                seeds.append({"node_id": nid, "semantic": seed_sem[r], "meta": store.metas[row]})
                 seed_meta[nid] = store.metas[row]
             expanded = []
-            for j in range(int(host["exp_count"][b])):
-                nid = node_ids[int(host["exp_nodes"][b, j])]
-                kind = int(host["exp_kind"][b, j])
+            e_nodes, e_sem, e_kind = host["exp_nodes"][b], host["exp_semantic"][b], host["exp_kind"][b]
+            for j in range(host["exp_count"][b]):
+                nid = node_ids[e_nodes[j]]
+                kind = e_kind[j]
                 if kind == 1:
-                    expanded.append({"node_id": nid, "semantic": float(host["exp_semantic"][b, j]),
-                                     "meta": seed_meta.get(nid), "node_type": G.nodes.get(nid, {}).get("node_type")})
+                    expanded.append({"node_id": nid, "semantic": e_sem[j], "meta": seed_meta.get(nid),
+                                     "node_type": nodes_view.get(nid, {}).get("node_type")})
                 else:
-                    expanded.append({"node_id": nid, "semantic": float(host["exp_semantic"][b, j]),
-                                     "meta": {"expanded": True}, "node_type": "summary" if kind == 2 else "entity"})
+                    expanded.append({"node_id": nid, "semantic": e_sem[j], "meta": {"expanded": True},
+                                     "node_type": "summary" if kind == 2 else "entity"})
             results.append({"seeds": seeds, "expanded": expanded, "reranked": reranked})
         return results
