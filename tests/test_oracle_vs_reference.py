@@ -79,3 +79,53 @@ def test_expand_to_lca_against_reference_on_random_graphs(seed, tmp_path):
         strip = lambda i: {k: v for k, v in i.items() if k != "time_s"}
         assert json.dumps(want[0], sort_keys=True) == json.dumps(got[0], sort_keys=True), ids
         assert strip(want[1]) == strip(got[1]), ids
+
+
+def test_featurizer_and_reward_equal_the_reference_functions():
+    """The drop-in featurizer / reward (own structure) against the reference's functions, bit for bit, on the golden
+    observations and on random observation dicts (missing keys, None values, observations without "state")."""
+    import importlib.util
+    import random
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    rf = load("_ref_featurizer", "/root/reference/src/ah_rag/agent/featurizer.py")
+    rr = load("_ref_reward", "/root/reference/src/ah_rag/agent/reward.py")
+    from ah_rag_b200.agent import featurizer as mf, reward as mr
+    from tests import golden_util as gu
+    rng = random.Random(1)
+    observations = []
+    for name in gu.fixture_names():
+        fx = gu.load(name)
+        observations += [st["obs"] for tr in fx["env"] for st in tr] + [c["obs"] for c in fx["lca"] if "obs" in c]
+
+    def random_obs():
+        o = {"step": rng.choice([None, 0, 3, 7.5]), "seeds": [{}] * rng.randrange(4), "selection": []}
+        if rng.random() < 0.8:
+            o["state"] = {"selection_ids": [str(rng.randrange(6)) for _ in range(rng.randrange(5))],
+                          "frontier_ids": [str(rng.randrange(9)) for _ in range(rng.randrange(14))]}
+        for _ in range(rng.randrange(13)):
+            o["selection"].append({"node_id": rng.choice(["a", "b", None]),
+                                   "node_type": rng.choice(["entity", "summary", "hyperedge", None]),
+                                   "layer": rng.choice([0, 1, 2, None]), "score": rng.choice([None, 0.1234, 1.0, 0]),
+                                   "semantic": rng.choice([None, 0.5, 0.33333]),
+                                   "judge_overall": rng.choice([None, 7.5, 0.0]), "confidence": rng.choice([None, 3, 8.25])})
+        return o
+
+    observations += [random_obs() for _ in range(300)]
+    for o in observations:
+        a, ia = rf.featurize_observation(o)
+        b, ib = mf.featurize_observation(o)
+        assert a.dtype == b.dtype and np.array_equal(a.view(np.uint32), b.view(np.uint32)) and ia == ib
+    assert np.array_equal(mf.featurize_batch(observations[:40]),
+                          np.stack([rf.featurize_observation(o)[0] for o in observations[:40]]))
+    for _ in range(1000):
+        p, c = rng.choice(observations + [None]), rng.choice(observations)
+        assert rr.step_reward(p, c) == mr.step_reward(p, c)
+    for _ in range(100):
+        m = {k: rng.random() for k in rng.sample(["f1", "faithfulness", "answer_relevancy", "contextual_recall", "x"], rng.randrange(5))}
+        assert rr.final_reward(m) == mr.final_reward(m)
