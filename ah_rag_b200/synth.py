@@ -210,3 +210,23 @@ def make_csr_graph(n_entities: int, n_l1: int, n_l2: int, n_hyperedges: int, see
     judge[s1:h0][rng.uniform(size=ns) < 0.2] = np.nan
     return {"n_nodes": np.int64(n_nodes), "src": src, "dst": dst, "etype": typ, "node_type": node_type,
             "level": level, "judge": judge, "conf": conf}
+
+
+def make_l1_nodes(seed: int, n_topics: int = 30, dim: int = 16, n_entities: int = 60) -> List[Dict[str, Any]]:
+    """Synthetic L1 topic records (topic_id, members, centroid, confidence) for ``generate_l1_relations``: clustered
+    centroids (so cosines spread over [-1, 1]), overlapping member sets, and the irregularities the reference tolerates
+    (missing / null centroid, missing confidence, permuted and duplicated topic ids)."""
+    rng = np.random.default_rng(seed)
+    base = rng.normal(size=(4, dim))
+    nodes: List[Dict[str, Any]] = []
+    for t in range(n_topics):
+        node: Dict[str, Any] = {"topic_id": int(t * 3 % n_topics) if seed % 2 else t,
+                                "members": [f"e{int(x)}" for x in rng.integers(0, n_entities, size=int(rng.integers(0, 12)))],
+                                "confidence": float(np.round(rng.uniform(1, 9), 2))}
+        centroid = (base[t % 4] + 0.6 * rng.normal(size=dim)).tolist() if rng.random() > 0.1 else None
+        if centroid is not None or rng.random() > 0.5:
+            node["centroid"] = centroid
+        if rng.random() < 0.1:
+            node.pop("confidence")
+        nodes.append(node)
+    return nodes

@@ -110,6 +110,21 @@ def main() -> None:
         print(spec["name"], "nodes", rs.hg.G.number_of_nodes(), "edges", rs.hg.G.number_of_edges(),
               "index", len(rs.index_ids), "search cases", len(fixture["search"]))
 
+    # generate_l1_relations (semantic_aggregator.py:594-680): inputs + the reference's edges and neighbour lists
+    import copy
+    l1_cases = []
+    for seed in range(5):
+        for kw in (dict(), dict(min_overlap=1, min_jaccard=0.05, min_cosine=0.3), dict(top_k=7),
+                   dict(min_cosine=0.9, min_overlap=99, min_jaccard=0.99)):
+            nodes = synth.make_l1_nodes(seed, n_topics=30 if seed < 4 else 60, dim=16 if seed < 4 else 24)
+            inp = copy.deepcopy(nodes)
+            edges = ref_runner.reference_l1_relations(nodes, **kw)
+            l1_cases.append({"seed": seed, "kwargs": kw, "l1_nodes": inp, "edges": edges,
+                             "neighbors": [n["neighbors"] for n in nodes]})
+    with open(os.path.join(GOLDEN_DIR, "l1_relations.json"), "w", encoding="utf-8") as f:
+        json.dump(l1_cases, f)
+    print("l1 relation cases", len(l1_cases), "edges", sum(len(c["edges"]) for c in l1_cases))
+
     # known answers held by the reference's own tests / shipped data
     HG = rs.HG
     known = {

@@ -73,3 +73,17 @@ def strip_search(out: Dict[str, Any]) -> Dict[str, Any]:
                      for e in out["expanded"]],
         "reranked": out["reranked"],
     }
+
+
+def reference_l1_relations(l1_nodes: List[Dict[str, Any]], **kw) -> List[Dict[str, Any]]:
+    """``SemanticAggregator.generate_l1_relations`` of the unmodified reference (no model is loaded: the method does
+    not touch ``self``).  Runs in a scratch directory because it writes ``artifacts/l1_*.json``; mutates ``l1_nodes``
+    (``neighbors``) exactly as the reference does."""
+    cls = stubs.import_reference_aggregator(REF_ROOT)
+    agg = cls.__new__(cls)
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp(prefix="ahrag_ref_l1_"))
+    try:
+        return agg.generate_l1_relations(l1_nodes, **kw)
+    finally:
+        os.chdir(cwd)

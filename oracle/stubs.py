@@ -162,3 +162,22 @@ def import_reference(ref_root: str = "/root/reference"):
     gym = importlib.import_module("ah_rag.agent.gym_env")
     nr = importlib.import_module("baselines.naive_rag")
     return hg.HierarchicalGraph, env.GraphEnvironment, gym.AHRAGGymEnv, nr.NaiveRAG
+
+
+def import_reference_aggregator(ref_root: str = "/root/reference"):
+    """``SemanticAggregator`` of the unmodified reference (semantic_aggregator.py) for the one method that is pure
+    numpy / Python, ``generate_l1_relations`` (:594-680).  The clustering libraries the module imports at the top
+    (bertopic, umap, hdbscan) are absent here and not needed by that method: empty stand-ins."""
+    import importlib
+    import os
+
+    install()
+    for name, attr in (("bertopic", "BERTopic"), ("umap", "UMAP"), ("hdbscan", "HDBSCAN")):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            setattr(m, attr, type(attr, (), {}))
+            sys.modules[name] = m
+    src = os.path.join(ref_root, "src")
+    if src not in sys.path:
+        sys.path.insert(0, src)
+    return importlib.import_module("ah_rag.aggregate.semantic_aggregator").SemanticAggregator

@@ -247,3 +247,33 @@ def test_expand_to_lca_matches_reference_golden(name, tmp_path):
         info = {k: v for k, v in info.items() if k != "time_s"}
         assert gu.canon(obs) == gu.canon(case["obs"]), case["node_ids"]
         assert gu.canon(info) == gu.canon(case["info"]), case["node_ids"]
+
+
+def _pairwise_np_dot(mat):
+    """fp32 ``np.dot`` per pair, i.e. what the reference evaluates (semantic_aggregator.py:634)."""
+    t = mat.shape[0]
+    out = np.zeros((t, t), dtype=np.float32)
+    for i in range(t):
+        for j in range(t):
+            out[i, j] = np.dot(mat[i], mat[j])
+    return out
+
+
+def test_l1_relations_host_logic_matches_reference_golden(tmp_path):
+    """generate_l1_relations against the edges / neighbour lists the unmodified reference produced
+    (tests/golden/l1_relations.json).  The cosine matrix is injected (fp32 np.dot per pair, the reference's own
+    arithmetic), so everything else -- overlap, Jaccard, rules, rounding, ordering, top-k pruning, neighbours, the two
+    artifact files -- must be identical."""
+    from ah_rag_b200.aggregate.l1_relations import generate_l1_relations
+    with open(os.path.join(gu.GOLDEN_DIR, "l1_relations.json"), "r", encoding="utf-8") as f:
+        cases = json.load(f)
+    assert sum(len(c["edges"]) for c in cases) > 1000
+    for c in cases:
+        nodes = copy.deepcopy(c["l1_nodes"])
+        art = str(tmp_path / "artifacts")
+        edges = generate_l1_relations(nodes, cosine_fn=_pairwise_np_dot, artifact_dir=art, **c["kwargs"])
+        assert json.dumps(edges) == json.dumps(c["edges"]), (c["seed"], c["kwargs"])
+        assert [n["neighbors"] for n in nodes] == c["neighbors"]
+        with open(os.path.join(art, "l1_edges.json"), "r", encoding="utf-8") as f:
+            assert json.load(f) == c["edges"]
+    assert generate_l1_relations([], artifact_dir=None) == []

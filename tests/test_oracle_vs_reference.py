@@ -129,3 +129,17 @@ def test_featurizer_and_reward_equal_the_reference_functions():
     for _ in range(100):
         m = {k: rng.random() for k in rng.sample(["f1", "faithfulness", "answer_relevancy", "contextual_recall", "x"], rng.randrange(5))}
         assert rr.final_reward(m) == mr.final_reward(m)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_l1_relations_against_reference(seed, tmp_path):
+    """generate_l1_relations (host logic, cosines injected as the reference's fp32 np.dot) against
+    ``SemanticAggregator.generate_l1_relations`` of the unmodified reference, files included."""
+    from ah_rag_b200.aggregate.l1_relations import generate_l1_relations
+    from tests.test_host import _pairwise_np_dot
+    for kw in (dict(), dict(min_overlap=1, min_jaccard=0.05, min_cosine=0.3), dict(top_k=5)):
+        a = synth.make_l1_nodes(seed, n_topics=40, dim=12)
+        b = copy.deepcopy(a)
+        want = ref_runner.reference_l1_relations(a, **kw)
+        got = generate_l1_relations(b, cosine_fn=_pairwise_np_dot, artifact_dir=str(tmp_path / "art"), **kw)
+        assert json.dumps(want) == json.dumps(got) and json.dumps(a) == json.dumps(b)
