@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libahrag_b200.so")
-SOURCES = ["api.cu", "topk_tc.cu", "topk_tc2.cu", "topk_exact.cu", "select.cu", "graph.cu", "env.cu", "exchange.cu"]
+SOURCES = ["api.cu", "topk_tc.cu", "topk_tc2.cu", "topk_exact.cu", "select.cu", "graph.cu", "env.cu", "exchange.cu", "lca.cu"]
 HEADERS = ["common.cuh", "kernels.h", "tc_shared.cuh", "graph_shared.cuh", os.path.join("..", "..", "include", "ahrag_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

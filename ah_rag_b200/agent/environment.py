@@ -155,58 +155,48 @@ class GraphEnvironment:
         cluster = self.hg.search(query=query, return_cluster=True, **kw)
         return self._finish_anchor(query, cluster, top_k, time.perf_counter() - t0)
 
-    def _belongs_to_is_dag(self, arrays: Dict[str, Any]) -> bool:
-        """``nx.is_directed_acyclic_graph`` of the belongs_to subgraph (Kahn's algorithm on the CSR, level by level)."""
-        rp_out, ci_out = arrays["row_ptr"][2], arrays["col_idx"][2]
-        indeg = np.diff(arrays["row_ptr"][3]).astype(np.int64)
-        alive = np.ones(arrays["n_nodes"], dtype=bool)
-        frontier = np.flatnonzero(indeg == 0)
-        while frontier.size:
-            alive[frontier] = False
-            starts, ends = rp_out[frontier], rp_out[frontier + 1]
-            if int((ends - starts).sum()) == 0:
-                break
-            tgt = np.concatenate([ci_out[a:b] for a, b in zip(starts, ends) if b > a])
-            np.subtract.at(indeg, tgt, 1)
-            cand = np.unique(tgt)
-            frontier = cand[(indeg[cand] == 0) & alive[cand]]
-        return not bool(alive.any())
+    @staticmethod
+    def _belongs_to_is_dag(arrays: Dict[str, Any]) -> bool:
+        """``nx.is_directed_acyclic_graph`` of the belongs_to subgraph: a property of the loaded graph, evaluated once
+        per export on the host arrays (Kahn's algorithm, level by level) and cached with them."""
+        if "bel_is_dag" not in arrays:
+            rp_out, ci_out = arrays["row_ptr"][2], arrays["col_idx"][2]
+            indeg = np.diff(arrays["row_ptr"][3]).astype(np.int64)
+            alive = np.ones(arrays["n_nodes"], dtype=bool)
+            frontier = np.flatnonzero(indeg == 0)
+            while frontier.size:
+                alive[frontier] = False
+                starts, ends = rp_out[frontier], rp_out[frontier + 1]
+                if int((ends - starts).sum()) == 0:
+                    break
+                tgt = np.concatenate([ci_out[a:b] for a, b in zip(starts, ends) if b > a])
+                np.subtract.at(indeg, tgt, 1)
+                cand = np.unique(tgt)
+                frontier = cand[(indeg[cand] == 0) & alive[cand]]
+            arrays["bel_is_dag"] = not bool(alive.any())
+        return arrays["bel_is_dag"]
 
     def expand_to_lca(self, node_ids: List[str], max_results: int = 5):
-        """environment.py:243-299 over the exported CSR instead of a DiGraph rebuilt per call.
-        As in the reference, "ancestors" are taken with ``nx.ancestors`` on child -> parent edges, i.e. the nodes BELOW
-        each input (its transitive members) plus the input itself; the result is the set of nodes common to all inputs
-        that have no belongs_to parent inside that common set, ordered by ``(level or 1, node id)``.  For distinct
-        entities that set is empty -- the reference's behaviour, kept.  An input that has no belongs_to edge at all
-        raises ``networkx.NetworkXError`` like ``nx.ancestors`` does."""
+        """environment.py:243-299 over the device-resident CSR instead of a DiGraph rebuilt per
+        call (``ahr_lca_closure``, csrc/lca.cu).  As in the reference, "ancestors" are taken with ``nx.ancestors`` on
+        child -> parent edges, i.e. the nodes BELOW each input (its transitive members) plus the input itself; the
+        result is the set of nodes common to all inputs that have no belongs_to parent inside that common set, ordered
+        by ``(level or 1, node id)``.  For distinct entities that set is empty -- the reference's behaviour, kept.  An
+        input that has no belongs_to edge at all raises ``networkx.NetworkXError`` like ``nx.ancestors`` does."""
         import networkx as nx
         self._ensure_graph_loaded()
         self.step_count += 1
-        arrays = self.hg._graph_arrays()
+        dg = self.hg._device_graph()
+        arrays = dg["arrays"]
         dense, names = arrays["dense"], arrays["node_ids"]
-        rp_in, ci_in = arrays["row_ptr"][3], arrays["col_idx"][3]
-        rp_out, ci_out = arrays["row_ptr"][2], arrays["col_idx"][2]
-        common: Optional[np.ndarray] = None
-        for nid in node_ids:
+        rp_in, rp_out = arrays["row_ptr"][3], arrays["row_ptr"][2]
+        ids: List[int] = []
+        for nid in node_ids:  # membership in the belongs_to subgraph, checked in input order like the reference's loop
             v = dense.get(nid, -1)
             if v < 0 or (rp_in[v + 1] == rp_in[v] and rp_out[v + 1] == rp_out[v]):
                 raise nx.NetworkXError(f"The node {nid} is not in the graph.")
-            seen = np.zeros(arrays["n_nodes"], dtype=bool)
-            seen[v] = True
-            frontier = np.asarray([v], dtype=np.int64)
-            while frontier.size:  # members of members ...: walk the in-belongs_to lists
-                nxt = [ci_in[rp_in[u]:rp_in[u + 1]] for u in frontier]
-                nxt = np.unique(np.concatenate(nxt)) if nxt else np.zeros(0, dtype=np.int64)
-                nxt = nxt[~seen[nxt]]
-                seen[nxt] = True
-                frontier = nxt
-            common = seen if common is None else (common & seen)
-        lcas = []
-        if common is not None:
-            for v in np.flatnonzero(common):
-                parents = ci_out[rp_out[v]:rp_out[v + 1]]
-                if not common[parents].any():
-                    lcas.append(names[int(v)])
+            ids.append(v)
+        lcas = [names[v] for v in dg["csr"].lca_closure(ids).cpu().tolist()]
         t0 = time.perf_counter()
         G = self.hg.G
         lcas = sorted(lcas, key=lambda x: (G.nodes[x].get("level") or 1, x))[:max_results]

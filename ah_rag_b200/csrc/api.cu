@@ -593,6 +593,25 @@ int ahr_expand(ahr_graph *g, int32_t n_env, const int32_t *dev_ops, const int32_
                       reinterpret_cast<cudaStream_t>(stream));
 }
 
+int ahr_lca_closure(ahr_graph *g, const int32_t *host_ids, int32_t n_ids, uint8_t *dev_out_flags, int64_t *n_result,
+                    void *stream) {
+  AHR_REQUIRE(g && dev_out_flags && n_result, "ahr_lca_closure: NULL argument");
+  AHR_REQUIRE(n_ids >= 0 && (n_ids == 0 || host_ids != nullptr), "ahr_lca_closure: bad input list");
+  for (int32_t i = 0; i < n_ids; ++i)
+    AHR_REQUIRE(host_ids[i] >= 0 && host_ids[i] < g->view.n_nodes, "ahr_lca_closure: node id %d out of range", host_ids[i]);
+  DeviceGuard guard(g->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  *n_result = 0;
+  if (g->view.n_nodes == 0) return AHR_OK;
+  if (n_ids == 0) {  // set.intersection() of nothing: the reference returns no node (environment.py:276)
+    AHR_CUDA_CHECK(cudaMemsetAsync(dev_out_flags, 0, (size_t)g->view.n_nodes, st));
+    return AHR_OK;
+  }
+  int rc = g->ws.reserve(graph_lca_workspace_bytes(g->view.n_nodes));
+  if (rc != AHR_OK) return rc;
+  return graph_lca_closure(g->view, host_ids, n_ids, dev_out_flags, n_result, g->ws.ptr, st);
+}
+
 int ahr_env_reset(ahr_graph *g, const ahr_env_batch *env, const int32_t *dev_nodes, const double *dev_semantic,
                   const double *dev_score, const int32_t *dev_count, int32_t top_k, int32_t n_seeds, float *dev_features,
                   uint8_t *dev_mask, void *stream) {

@@ -86,6 +86,11 @@ int graph_expand(const GraphView &g, int32_t n_env, const int32_t *ops, const in
                  const int32_t *in_offsets, int32_t limit, int32_t *out_ids, int32_t *out_counts, cudaStream_t stream);
 int debug_round4(const double *x, int64_t n, double *out, cudaStream_t stream);
 
+// ---- lca.cu ----
+size_t graph_lca_workspace_bytes(int64_t n_nodes);
+int graph_lca_closure(const GraphView &g, const int32_t *host_ids, int32_t n_ids, uint8_t *out_flags, int64_t *n_result,
+                      void *workspace, cudaStream_t stream);
+
 // ---- env.cu ----
 int env_reset(const GraphView &g, const ahr_env_batch &b, const int32_t *nodes, const double *sem, const double *score,
               const int32_t *count, int32_t top_k, int32_t n_seeds, float *feat, uint8_t *mask, cudaStream_t stream);

@@ -312,6 +312,19 @@ class GraphCSR:
                 _stream_ptr(dev)), "ahr_anchor_rerank")
         return out
 
+    def lca_closure(self, node_ids: Sequence[int]) -> torch.Tensor:
+        """environment.py:243-299, closure step: dense ids (int64, ascending) of the nodes that lie below every input
+        over belongs_to and have no belongs_to parent with the same property (``ahr_lca_closure``)."""
+        ids = (ctypes.c_int32 * max(1, len(node_ids)))(*[int(v) for v in node_ids])
+        flags = torch.empty((self.n_nodes,), dtype=torch.uint8, device=self.device)
+        n = ctypes.c_int64()
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_lca_closure(self._h, ids, len(node_ids), flags.data_ptr(), ctypes.byref(n),
+                                           _stream_ptr(self.device)), "ahr_lca_closure")
+        if n.value == 0:
+            return torch.empty((0,), dtype=torch.int64, device=self.device)
+        return torch.nonzero(flags, as_tuple=False).view(-1)
+
     def expand(self, ops: torch.Tensor, in_ids: torch.Tensor, in_offsets: torch.Tensor, limit: int = 10
                ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Batched environment.py:393-480.  ops int32 [n_env]; in_ids int32 (CSR by in_offsets int32 [n_env+1])."""

@@ -186,6 +186,18 @@ int ahr_expand(ahr_graph *g, int32_t n_env, const int32_t *dev_ops, const int32_
                const int32_t *dev_in_offsets, int32_t limit, int32_t *dev_out_ids, int32_t *dev_out_counts,
                void *stream);
 
+/*
+ * Closure step of GraphEnvironment.expand_to_lca (src/ah_rag/agent/environment.py:243-299) over the belongs_to CSRs:
+ * for every input node the set of nodes below it (transitive members, itself included -- what nx.ancestors yields on
+ * child -> parent edges), the intersection of those sets, and of it the nodes without a belongs_to parent inside it.
+ * host_ids [n_ids]: dense node ids on the HOST (a handful per call).  dev_out_flags [n_nodes] u8: 1 = result node;
+ * *n_result: how many.  Synchronises the stream (one host round trip per BFS level).  The caller orders the result
+ * ((level or 1, node id), environment.py:283) and checks that every input has a belongs_to edge (nx.ancestors raises
+ * otherwise).
+ */
+int ahr_lca_closure(ahr_graph *g, const int32_t *host_ids, int32_t n_ids, uint8_t *dev_out_flags, int64_t *n_result,
+                    void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Device-resident batched gym environment.  Replaces, for n_env environments per launch,
  *   AHRAGGymEnv.reset / .step / .get_action_mask        src/ah_rag/agent/gym_env.py:41-125

@@ -83,6 +83,12 @@ def main() -> None:
         parent_of = lambda n: [v for _, v, d in G.out_edges(n, data=True) if d.get("edge_type") == "belongs_to"]
         cases = [[s_] for s_ in sums[:3]] + [sums[:2], sums[-2:], ents[:1], ents[:2], [ents[0]] + parent_of(ents[0])[:1],
                                              parent_of(ents[1])[:1] + [ents[1]], [], by_type["hyperedge"][:1], ["not-a-node"]]
+        lrng = np.random.default_rng(len(G))
+        hier = [n for n in G if any(d.get("edge_type") == "belongs_to" for _, _, d in G.out_edges(n, data=True)) or
+                any(d.get("edge_type") == "belongs_to" for _, _, d in G.in_edges(n, data=True))]
+        for t in range(24):  # random sets: summaries only (odd t) or any node of the hierarchy
+            pool = sums if (t % 2 and sums) else hier
+            cases.append([pool[int(i)] for i in lrng.integers(len(pool), size=int(lrng.integers(1, 4)))])
         for ids in cases:
             for mr in (5, 1):
                 try:

@@ -226,29 +226,6 @@ def test_device_snapshot_round_trip_and_invalidation(tmp_path):
     _same_arrays(hg4._export_arrays(), csr.csr_from_networkx(hg4.G))
 
 
-@pytest.mark.parametrize("name", gu.fixture_names())
-def test_expand_to_lca_matches_reference_golden(name, tmp_path):
-    """expand_to_lca over the exported CSR against the traces of the unmodified reference
-    (environment.py:243-299), including its quirk (descendant sets) and the error for nodes outside the hierarchy."""
-    from ah_rag_b200.agent.environment import GraphEnvironment
-    fx = gu.load(name)
-    gdir = str(tmp_path / "graph")
-    synth.write_graph_dir(gdir, copy.deepcopy(fx["node_link"]))
-    hg = HierarchicalGraph.load(gdir)
-    env = GraphEnvironment(graph_dir=gdir, logging_enabled=False, hg=hg)
-    assert fx["lca"], "fixture without lca cases"
-    for case in fx["lca"]:
-        if "raises" in case:
-            with pytest.raises(Exception) as ei:
-                env.expand_to_lca(list(case["node_ids"]), max_results=case["max_results"])
-            assert type(ei.value).__name__ == case["raises"], case
-            continue
-        obs, info = env.expand_to_lca(list(case["node_ids"]), max_results=case["max_results"])
-        info = {k: v for k, v in info.items() if k != "time_s"}
-        assert gu.canon(obs) == gu.canon(case["obs"]), case["node_ids"]
-        assert gu.canon(info) == gu.canon(case["info"]), case["node_ids"]
-
-
 def _pairwise_np_dot(mat):
     """fp32 ``np.dot`` per pair, i.e. what the reference evaluates (semantic_aggregator.py:634)."""
     t = mat.shape[0]

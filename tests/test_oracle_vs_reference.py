@@ -47,40 +47,6 @@ def test_random_graphs_search_env_gym(seed):
         assert ia == ib
 
 
-@pytest.mark.parametrize("seed", [31, 32])
-def test_expand_to_lca_against_reference_on_random_graphs(seed, tmp_path):
-    """the CSR-based expand_to_lca of the drop-in environment against the unmodified reference
-    (environment.py:243-299) on random graphs and random input sets, errors included."""
-    from ah_rag_b200.agent.environment import GraphEnvironment
-    from ah_rag_b200.graph.hierarchical_graph import HierarchicalGraph
-    stubs.reset_store()
-    rng = np.random.default_rng(seed)
-    g = synth.make_graph(seed=seed, n_entities=int(rng.integers(20, 120)), n_l1=int(rng.integers(2, 10)),
-                         n_l2=int(rng.integers(0, 4)), n_hyperedges=int(rng.integers(0, 30)),
-                         related_density=float(rng.uniform(0, 0.5)))
-    rs = ref_runner.ReferenceSession(copy.deepcopy(g))
-    renv = rs.make_env()
-    gdir = str(tmp_path / "graph")
-    synth.write_graph_dir(gdir, copy.deepcopy(g))
-    env = GraphEnvironment(graph_dir=gdir, logging_enabled=False, hg=HierarchicalGraph.load(gdir))
-    nodes = list(rs.hg.G.nodes)
-    summaries = [n for n in nodes if rs.hg.G.nodes[n].get("node_type") == "summary"]
-    for t in range(40):
-        pool = summaries if t % 2 else nodes
-        ids = [pool[int(i)] for i in rng.integers(len(pool), size=int(rng.integers(1, 4)))]
-        mr = int(rng.choice([1, 3, 5]))
-        try:
-            want = renv.expand_to_lca(list(ids), max_results=mr)
-        except Exception as e:  # noqa: BLE001 -- nx.ancestors on a node outside the belongs_to subgraph
-            with pytest.raises(type(e)):
-                env.expand_to_lca(list(ids), max_results=mr)
-            continue
-        got = env.expand_to_lca(list(ids), max_results=mr)
-        strip = lambda i: {k: v for k, v in i.items() if k != "time_s"}
-        assert json.dumps(want[0], sort_keys=True) == json.dumps(got[0], sort_keys=True), ids
-        assert strip(want[1]) == strip(got[1]), ids
-
-
 def test_featurizer_and_reward_equal_the_reference_functions():
     """The drop-in featurizer / reward (own structure) against the reference's functions, bit for bit, on the golden
     observations and on random observation dicts (missing keys, None values, observations without "state")."""
