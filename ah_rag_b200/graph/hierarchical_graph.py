@@ -27,6 +27,7 @@ from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
 import networkx as nx
 import numpy as np
 
+ARTIFACT_DIR = "artifacts"
 GRAPH_DIR = "graph"
 
 _DEFAULT_SEARCH_PARAMS = {
@@ -132,8 +133,8 @@ class HierarchicalGraph:
             given = {"title": title, "summary_text": summary_text, "confidence": confidence, "top_words": top_words,
                      "members": members, "judge_scores": judge_scores, "centroid": centroid}
             for key, val in given.items():
-                if val is not None:
-                    d[key] = fields[key] if key in ("top_words", "members", "judge_scores", "centroid") else val
+                if val is not None:  # an update serialises whatever it is given, even an empty list (:145-152)
+                    d[key] = json.dumps(val) if key in ("top_words", "members", "judge_scores", "centroid") else val
         self._touch()
         return nid
 
@@ -152,9 +153,123 @@ class HierarchicalGraph:
                         overlap=overlap, confidence=confidence)
         self._touch()
 
-    def build_from_artifacts(self, *a: Any, **k: Any) -> None:
-        raise NotImplementedError("offline ingest (LLM extraction + BERTopic, hierarchical_graph.py:241-421) is out of "
-                                  "scope of the B200 engine; build the graph with the reference and load() it here")
+    def build_from_artifacts(self, artifacts_dir: str = ARTIFACT_DIR) -> None:
+        """Assemble the graph from the JSON artifacts of the reference's ingest pipeline
+        (hierarchical_graph.py:241-421; the data format in front of the retrieval path):
+
+          topics.json            {"entity_to_parents": {name: [{"topic_id", "prob"}]}, "l1_nodes": [...]}
+          l1_nodes.json          L1 topic records (replaces topics.json's list when present)
+          l1_edges.json          related_summary edges (``aggregate.l1_relations.generate_l1_relations``)
+          extractions.json       hyperedges with their participating entities
+          l2_nodes.json, l1_to_l2.json      second summary level and the L1 -> L2 assignment
+          l1_judge_nodes.json, l1_judge_edges.json   judge scores (per summary node / kept at graph level)
+
+        Insertion order is the reference's (it fixes node and adjacency order, hence the CSR): entities named by
+        ``entity_to_parents``, entities only seen in hyperedges, L1 summaries, belongs_to, related_to, hyperedges with
+        their participation edges, L2 summaries and L1 -> L2 belongs_to, judge scores.  Missing files are skipped."""
+        def read(name: str, default: Any) -> Any:
+            path = os.path.join(artifacts_dir, name)
+            if not os.path.exists(path):
+                return default
+            with open(path, "r", encoding="utf-8") as f:
+                return json.load(f)
+
+        topics = read("topics.json", {})
+        entity_to_parents: Dict[str, List[Dict[str, Any]]] = topics.get("entity_to_parents", {}) if topics else {}
+        l1_nodes = read("l1_nodes.json", None)
+        if l1_nodes is None:
+            l1_nodes = topics.get("l1_nodes", []) if topics else []
+        l1_edges = read("l1_edges.json", [])
+        hyperedges = read("extractions.json", [])
+        l2_nodes = read("l2_nodes.json", [])
+        l1_to_l2 = read("l1_to_l2.json", {})
+        judge_nodes = read("l1_judge_nodes.json", [])
+        judge_edges = read("l1_judge_edges.json", [])
+
+        # what the hyperedges say about each entity: type of its first mention, every distinct non-empty description
+        seen: Dict[str, Dict[str, Any]] = {}
+        for h in hyperedges:
+            for ent in h.get("entities", []):
+                name = ent.get("name")
+                if not name:
+                    continue
+                rec = seen.setdefault(name, {"entity_type": ent.get("type"), "descriptions": []})
+                text = ent.get("description")
+                if text and text not in rec["descriptions"]:
+                    rec["descriptions"].append(text)
+
+        def described(name: str) -> Tuple[Optional[str], Optional[str]]:
+            rec = seen.get(name, {})
+            texts = rec.get("descriptions", [])
+            return ("; ".join(texts) if texts else None), rec.get("entity_type")
+
+        # the reference points every entity at the module-level artifacts directory, whatever directory it was given
+        embedding_ref = (os.path.join(ARTIFACT_DIR, "embeddings.npy"), -1)
+        for name, parents in entity_to_parents.items():
+            text, etype = described(name)
+            self.add_entity(name=name, description=text, entity_type=etype, embedding_ref=embedding_ref,
+                            l1_parents={str(p.get("topic_id")): p.get("prob") for p in parents})
+        for name in seen:
+            if name not in entity_to_parents:
+                text, etype = described(name)
+                self.add_entity(name=name, description=text, entity_type=etype)
+
+        for node in l1_nodes:
+            self.add_summary(topic_id=int(node.get("topic_id")), title=node.get("title"),
+                             summary_text=node.get("summary") or node.get("summary_text"),
+                             confidence=node.get("confidence"), top_words=node.get("top_words") or [],
+                             members=node.get("members") or [], centroid=node.get("centroid"))
+
+        for name, parents in entity_to_parents.items():
+            eid = self.name_to_entity_id.get(name)
+            if not eid:
+                continue
+            for p in parents:
+                sid = self.topic_to_summary_id.get(int(p.get("topic_id")))
+                if sid:
+                    self.add_belongs_to(eid, sid, prob=p.get("prob"))
+
+        for e in l1_edges:
+            a = self.topic_to_summary_id.get(int(e.get("source")))
+            b = self.topic_to_summary_id.get(int(e.get("target")))
+            if a and b:
+                self.add_related(a, b, weight=e.get("weight"), jaccard=e.get("jaccard"), cosine=e.get("cosine"),
+                                 overlap=e.get("overlap"), confidence=e.get("confidence"))
+
+        for pos, h in enumerate(hyperedges):
+            uid = h.get("id")
+            if uid is None:
+                uid = f"hedge_{pos}_{h.get('relation_type', 'unknown')}"
+            hid = self.add_hyperedge(uid=str(uid), description=h.get("hyperedge"), relation_type=h.get("relation_type"),
+                                     confidence_score=h.get("confidence_score"))
+            for ent in h.get("entities", []):
+                eid = self.name_to_entity_id.get(ent.get("name")) if ent.get("name") else None
+                if eid:
+                    self.add_participation(eid, hid, role=ent.get("role") if isinstance(ent, dict) else None)
+
+        if l2_nodes:
+            for n in l2_nodes:
+                sid = self.add_summary(topic_id=int(n.get("topic_id")), title=n.get("title"), summary_text=n.get("summary"),
+                                       confidence=n.get("confidence"), top_words=n.get("top_words"),
+                                       members=n.get("members"), centroid=n.get("centroid"))
+                self.G.nodes[sid]["level"] = 2
+            for l1_key, l2_tid in l1_to_l2.items():
+                try:
+                    l1_tid = int(l1_key)
+                except Exception:
+                    continue
+                lower, upper = self.topic_to_summary_id.get(l1_tid), self.topic_to_summary_id.get(int(l2_tid))
+                if lower and upper:
+                    self.add_belongs_to(lower, upper, prob=1.0)
+
+        by_topic = {int(d.get("topic_id")): n for n, d in self.G.nodes(data=True) if d.get("node_type") == "summary"}
+        for score in judge_nodes:
+            nid = by_topic.get(int(score.get("id")))
+            if nid:
+                self.G.nodes[nid]["judge_scores"] = json.dumps(score)
+        if judge_edges:
+            self.G.graph["judge_edges"] = judge_edges
+        self._touch()
 
     # ------------------------------------------------------------------ persistence (:175-236)
     def save(self, directory: str = GRAPH_DIR, meta: Optional[Dict[str, Any]] = None) -> None:

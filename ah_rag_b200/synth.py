@@ -230,3 +230,60 @@ def make_l1_nodes(seed: int, n_topics: int = 30, dim: int = 16, n_entities: int 
             node.pop("confidence")
         nodes.append(node)
     return nodes
+
+
+def write_artifacts(directory: str, seed: int, variant: int) -> None:
+    """Synthetic JSON artifacts of the reference's ingest pipeline, as ``HierarchicalGraph.build_from_artifacts`` reads
+    them (hierarchical_graph.py:241-421).  ``variant`` 0: topics.json + extractions.json only; 1: + l1_nodes.json and
+    l1_edges.json; 2: + the L2 level and judge files; 3: as 2 without topics.json.  Irregularities on purpose: parents
+    naming a topic that does not exist, entities only seen in hyperedges, entity records without a name, hyperedges
+    without id / relation_type, edges to unknown topics, an L2 topic id that clashes with an L1 one."""
+    rng = np.random.default_rng(seed)
+    names = [f"Entity {i}" for i in range(25)]
+    n_topics = 6
+    e2p: Dict[str, Any] = {}
+    for n in names[:20]:
+        picks = rng.choice(n_topics + 1, size=int(rng.integers(0, 3)), replace=False)
+        e2p[n] = [{"topic_id": int(t), "prob": float(np.round(rng.uniform(0.1, 1), 3))} for t in picks]
+    l1 = [{"topic_id": t, "title": f"T{t}" if t % 2 else None, "summary": f"about {t}" if t % 3 else None,
+           "summary_text": f"alt {t}", "confidence": float(t) + 0.5 if t != 2 else None,
+           "top_words": ["a", "b"] if t % 2 else [], "members": names[t:t + 4] if t else None,
+           "centroid": rng.normal(size=4).tolist() if t != 1 else None} for t in range(n_topics)]
+    edges = [{"source": 0, "target": 1, "weight": 0.5, "jaccard": 0.2, "cosine": 0.8, "overlap": 2, "confidence": 5.0},
+             {"source": 2, "target": 9, "weight": 0.1}, {"source": 3, "target": 4}]
+    hyper = []
+    for i in range(12):
+        ents: List[Dict[str, Any]] = []
+        for _ in range(int(rng.integers(1, 4))):
+            ents.append({"name": str(rng.choice(names)), "type": [None, "PERSON", "ORG"][int(rng.integers(3))],
+                         "description": [None, "", "desc A", "desc B"][int(rng.integers(4))],
+                         "role": [None, "subj", "obj"][int(rng.integers(3))]})
+        if i == 3:
+            ents += [{"name": None}, {"type": "X"}]
+        h = {"hyperedge": f"fact {i}", "relation_type": ["rel", "other"][int(rng.integers(2))],
+             "confidence_score": float(np.round(rng.uniform(1, 10), 1)), "entities": ents}
+        if i % 4 == 0:
+            h["id"] = f"u{i}"
+        if i == 5:
+            h.pop("relation_type")
+        hyper.append(h)
+    os.makedirs(directory, exist_ok=True)
+
+    def dump(name: str, obj: Any) -> None:
+        with open(os.path.join(directory, name), "w", encoding="utf-8") as f:
+            json.dump(obj, f)
+
+    if variant != 3:
+        dump("topics.json", {"entity_to_parents": e2p, "l1_nodes": l1[:3]})
+    if variant >= 1:
+        dump("l1_nodes.json", l1)
+        dump("l1_edges.json", edges)
+    dump("extractions.json", hyper)
+    if variant >= 2:
+        dump("l2_nodes.json", [{"topic_id": 100, "title": "L2a", "summary": "s", "confidence": 7.0, "top_words": ["x"],
+                                "members": ["1", "2"], "centroid": [0.1, 0.2]},
+                               {"topic_id": 3, "title": "clash with L1 3", "members": []}])
+        dump("l1_to_l2.json", {"0": 100, "1": 100, "x": 100, "4": 3, "5": 777})
+        dump("l1_judge_nodes.json", [{"id": 0, "overall": 8.0, "comments": "ok"}, {"id": 100, "overall": 6.5},
+                                     {"id": 55, "overall": 1}])
+        dump("l1_judge_edges.json", [{"source": 0, "target": 1, "overall": 5}])

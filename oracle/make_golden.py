@@ -44,6 +44,7 @@ GYM_ACTION_SEQS = [[1, 0, 2, 2, 3, 4, 5], [0, 0, 0, 0, 0, 0], [2, 1, 3, 3, 1, 2]
 
 def main() -> None:
     assert ref_runner.reference_available(), "needs /root/reference"
+    HG_cls = stubs.import_reference(ref_runner.REF_ROOT)[0]
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     for spec in GRAPHS:
         stubs.reset_store()
@@ -130,6 +131,26 @@ def main() -> None:
     with open(os.path.join(GOLDEN_DIR, "l1_relations.json"), "w", encoding="utf-8") as f:
         json.dump(l1_cases, f)
     print("l1 relation cases", len(l1_cases), "edges", sum(len(c["edges"]) for c in l1_cases))
+
+    # build_from_artifacts (hierarchical_graph.py:241-421): the reference's graph for synthetic artifact sets
+    import contextlib
+    import io
+    import tempfile
+    import networkx as nx
+    art_cases = []
+    for seed, variant in ((0, 0), (1, 1), (2, 2), (3, 3)):
+        d = tempfile.mkdtemp(prefix="ahrag_art_")
+        synth.write_artifacts(d, seed, variant)
+        ref = HG_cls()
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref.build_from_artifacts(d)
+        art_cases.append({"seed": seed, "variant": variant,
+                          "node_link": json.loads(json.dumps(nx.node_link_data(ref.G, edges="links"), default=str)),
+                          "name_to_entity_id": ref.name_to_entity_id,
+                          "topic_to_summary_id": {str(k): v for k, v in ref.topic_to_summary_id.items()}})
+    with open(os.path.join(GOLDEN_DIR, "artifacts_graph.json"), "w", encoding="utf-8") as f:
+        json.dump(art_cases, f)
+    print("artifact graphs", [(len(c["node_link"]["nodes"]), len(c["node_link"]["links"])) for c in art_cases])
 
     # known answers held by the reference's own tests / shipped data
     HG = rs.HG

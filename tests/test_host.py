@@ -254,3 +254,24 @@ def test_l1_relations_host_logic_matches_reference_golden(tmp_path):
         with open(os.path.join(art, "l1_edges.json"), "r", encoding="utf-8") as f:
             assert json.load(f) == c["edges"]
     assert generate_l1_relations([], artifact_dir=None) == []
+
+
+def test_build_from_artifacts_matches_reference_golden(tmp_path):
+    """The data format in front of the path: artifacts/*.json -> graph (hierarchical_graph.py:241-421).  Node order,
+    attributes, link order and the two name maps must equal what the unmodified reference built from the same files."""
+    import networkx as nx
+    with open(os.path.join(gu.GOLDEN_DIR, "artifacts_graph.json"), "r", encoding="utf-8") as f:
+        cases = json.load(f)
+    assert cases
+    for c in cases:
+        d = str(tmp_path / f"art_{c['seed']}_{c['variant']}")
+        synth.write_artifacts(d, c["seed"], c["variant"])
+        hg = HierarchicalGraph()
+        hg.build_from_artifacts(d)
+        got = json.loads(json.dumps(nx.node_link_data(hg.G, edges="links"), default=str))
+        assert gu.canon(got) == gu.canon(c["node_link"]), (c["seed"], c["variant"])
+        assert [n["id"] for n in got["nodes"]] == [n["id"] for n in c["node_link"]["nodes"]]
+        assert [(l["source"], l["target"]) for l in got["links"]] == [(l["source"], l["target"]) for l in c["node_link"]["links"]]
+        assert hg.name_to_entity_id == c["name_to_entity_id"]
+        assert {str(k): v for k, v in hg.topic_to_summary_id.items()} == c["topic_to_summary_id"]
+        assert hg.G.graph["dirty"] is True

@@ -109,3 +109,26 @@ def test_l1_relations_against_reference(seed, tmp_path):
         want = ref_runner.reference_l1_relations(a, **kw)
         got = generate_l1_relations(b, cosine_fn=_pairwise_np_dot, artifact_dir=str(tmp_path / "art"), **kw)
         assert json.dumps(want) == json.dumps(got) and json.dumps(a) == json.dumps(b)
+
+
+def test_build_from_artifacts_against_reference(tmp_path):
+    """build_from_artifacts (own structure) against the unmodified reference on 24 synthetic artifact sets."""
+    import contextlib
+    import io
+    import networkx as nx
+    from ah_rag_b200.graph.hierarchical_graph import HierarchicalGraph as Mine
+    HG = stubs.import_reference(ref_runner.REF_ROOT)[0]
+    for seed in range(6):
+        for variant in range(4):
+            d = str(tmp_path / f"a{seed}_{variant}")
+            synth.write_artifacts(d, seed, variant)
+            ref = HG()
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref.build_from_artifacts(d)
+            mine = Mine()
+            mine.build_from_artifacts(d)
+            a, b = nx.node_link_data(ref.G, edges="links"), nx.node_link_data(mine.G, edges="links")
+            assert json.dumps(a, sort_keys=True, default=str) == json.dumps(b, sort_keys=True, default=str), (seed, variant)
+            assert [x["id"] for x in a["nodes"]] == [x["id"] for x in b["nodes"]]
+            assert [(l["source"], l["target"]) for l in a["links"]] == [(l["source"], l["target"]) for l in b["links"]]
+            assert ref.name_to_entity_id == mine.name_to_entity_id and ref.topic_to_summary_id == mine.topic_to_summary_id
