@@ -356,6 +356,67 @@ class HierarchicalGraph:
     def get_entity_hyperedges(self, entity_id: str) -> List[str]:
         return self._neighbors_by_edge_type(entity_id, "out", "participates_in")
 
+    # ------------------------------------------------------------------ small host utilities (:471-553)
+    def get_siblings(self, node_id: str) -> List[str]:
+        """Other members of the summaries ``node_id`` belongs to (unordered, as the reference's ``list(set)``)."""
+        found = {m for parent in set(self.get_belongs_to(node_id)) for m in self.get_summary_members(parent)}
+        found.discard(node_id)
+        return list(found)
+
+    def search_by_name_or_title(self, q: str, limit: int = 20) -> List[Tuple[str, Dict[str, Any]]]:
+        """Case-insensitive substring match on ``name`` / ``title`` in node order; the cut is checked after every node,
+        so ``limit <= 0`` still returns the first match (reference behaviour)."""
+        needle, hits = q.lower(), []
+        for nid, d in self.G.nodes(data=True):
+            if needle in str(d.get("name") or "").lower() or needle in str(d.get("title") or "").lower():
+                hits.append((nid, d))
+            if len(hits) >= limit:
+                break
+        return hits
+
+    def summaries_with_top_word(self, word: str, limit: int = 50) -> List[str]:
+        needle, hits = word.lower(), []
+        for nid, d in self.G.nodes(data=True):
+            if d.get("node_type") != "summary":
+                continue
+            words = d.get("top_words")
+            if words:
+                if isinstance(words, str):
+                    try:
+                        words = json.loads(words)
+                    except Exception:
+                        words = []
+                if any(needle in str(w).lower() for w in words):
+                    hits.append(nid)
+            if len(hits) >= limit:
+                break
+        return hits
+
+    def validate_belongs_to_dag(self) -> bool:
+        """Is the belongs_to subgraph acyclic?  Kahn's algorithm on the exported CSR (no DiGraph copy)."""
+        from ..agent.environment import GraphEnvironment
+        return GraphEnvironment._belongs_to_is_dag(self._graph_arrays())
+
+    def validate_required_attributes(self) -> Dict[str, List[str]]:
+        required = {"entity": ("name",), "hyperedge": ("description", "relation_type")}
+        problems: Dict[str, List[str]] = {"entity": [], "hyperedge": [], "summary": []}
+        for nid, d in self.G.nodes(data=True):
+            kind = d.get("node_type")
+            if kind in required:
+                if any(not d.get(key) for key in required[kind]):
+                    problems[kind].append(nid)
+            elif kind == "summary" and d.get("topic_id") is None:
+                problems["summary"].append(nid)
+        return problems
+
+    def stats(self) -> Dict[str, Any]:
+        from collections import Counter
+        node_kinds = Counter(d.get("node_type") for _, d in self.G.nodes(data=True))
+        edge_kinds = Counter(d.get("edge_type") for _, _, d in self.G.edges(data=True))
+        return {"nodes": {k: node_kinds.get(k, 0) for k in ("entity", "hyperedge", "summary")},
+                "edges": {k: edge_kinds.get(k, 0) for k in ("participates_in", "belongs_to", "related_to")},
+                "n_nodes": self.G.number_of_nodes(), "n_edges": self.G.number_of_edges()}
+
     # ------------------------------------------------------------------ embeddings (out of scope: pluggable)
     def set_embedder(self, fn: Optional[Embedder]) -> None:
         self.embedder = fn

@@ -132,3 +132,34 @@ def test_build_from_artifacts_against_reference(tmp_path):
             assert [x["id"] for x in a["nodes"]] == [x["id"] for x in b["nodes"]]
             assert [(l["source"], l["target"]) for l in a["links"]] == [(l["source"], l["target"]) for l in b["links"]]
             assert ref.name_to_entity_id == mine.name_to_entity_id and ref.topic_to_summary_id == mine.topic_to_summary_id
+
+
+def test_graph_utility_methods_against_reference(tmp_path):
+    """get_siblings / search_by_name_or_title / summaries_with_top_word / validate_* / stats (hierarchical_graph.py:471-553)."""
+    from ah_rag_b200.graph.hierarchical_graph import HierarchicalGraph as Mine
+    HG = stubs.import_reference(ref_runner.REF_ROOT)[0]
+    for seed, cyc in ((41, False), (42, True)):
+        g = synth.make_graph(seed=seed, n_entities=60, n_l1=7, n_l2=2, n_hyperedges=25, related_density=0.4)
+        if cyc:  # a belongs_to cycle between two summaries, a nameless entity, a hyperedge without description
+            sums = [n["id"] for n in g["nodes"] if n.get("node_type") == "summary"]
+            g["links"] += [{"source": sums[0], "target": sums[1], "edge_type": "belongs_to"},
+                           {"source": sums[1], "target": sums[0], "edge_type": "belongs_to"}]
+            g["nodes"] += [{"id": "ent:anon", "node_type": "entity"}, {"id": "hedge:x", "node_type": "hyperedge", "relation_type": "r"},
+                           {"id": "sum:none", "node_type": "summary", "top_words": "not json"}]
+        d = str(tmp_path / f"g{seed}")
+        synth.write_graph_dir(d, copy.deepcopy(g))
+        ref, mine = HG.load(d), Mine.load(d)
+        assert ref.validate_belongs_to_dag() == mine.validate_belongs_to_dag() == (not cyc)
+        assert ref.validate_required_attributes() == mine.validate_required_attributes()
+        assert ref.stats() == mine.stats()
+        for n in list(ref.G.nodes)[::5]:
+            assert set(ref.get_siblings(n)) == set(mine.get_siblings(n))
+        for q, lim in (("entity", 20), ("E", 3), ("topic", 0), ("zzz", 5), ("", 2)):
+            assert [x[0] for x in ref.search_by_name_or_title(q, lim)] == [x[0] for x in mine.search_by_name_or_title(q, lim)]
+        words = set()
+        for _, dd in ref.G.nodes(data=True):
+            if dd.get("top_words") and isinstance(dd["top_words"], str) and dd["top_words"].startswith("["):
+                words.update(json.loads(dd["top_words"]))
+        for w in sorted(words)[:6] + ["nope"]:
+            for lim in (50, 1):
+                assert ref.summaries_with_top_word(w, lim) == mine.summaries_with_top_word(w, lim)
