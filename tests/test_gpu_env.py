@@ -96,3 +96,36 @@ def test_device_env_capacity_overflow_is_reported(tmp_path):
         env.check_overflow()
     with pytest.raises(ValueError):
         env.step([0, 1])
+
+
+def test_collect_rollouts_matches_sequential_oracle_episodes(tmp_path):
+    """agent.rollout.collect_rollouts (all episodes together, finished ones idling on end_episode) against the oracle gym
+    environment stepped one episode at a time with the same actions, as collect_trajectories.py / ppo_train do."""
+    import torch
+    from ah_rag_b200.agent.gym_env import DeviceVecAHRAGGymEnv
+    from ah_rag_b200.agent.rollout import collect_rollouts, random_policy
+    fx = gu.load("g_dense_s11")
+    hg, _ = _make_hg(fx, tmp_path)
+    B = 48
+    qv = np.stack([fx["query_vecs"][b % len(fx["query_vecs"])] for b in range(B)])
+    venv = DeviceVecAHRAGGymEnv(hg, B, max_steps=6)
+    gen = torch.Generator(device="cuda").manual_seed(123)
+    out = collect_rollouts(venv, qv, policy=random_policy(gen))
+    T = out["actions"].shape[0]
+    assert 1 <= T <= 6 and tuple(out["obs"].shape) == (T, B, 84) and out["rewards"].dtype == torch.float64
+    acts, rew, alive = out["actions"].cpu().numpy(), out["rewards"].cpu().numpy(), out["alive"].cpu().numpy()
+    obs, dones = out["obs"].cpu().numpy(), out["dones"].cpu().numpy()
+    og = ref_search.OracleGraph(copy.deepcopy(fx["node_link"]))
+    for b in range(B):
+        gym = ref_search.OracleGymEnv(ref_search.OracleEnv(og, fx["index_ids"], fx["index_rows"]), max_steps=6)
+        vec, _ = gym.reset(qv[b])
+        total, t, done = 0.0, 0, False
+        while not done:
+            assert alive[t, b] and np.array_equal(obs[t, b].view(np.uint32), vec.view(np.uint32)), (b, t)
+            vec, r, done, _ = gym.step(int(acts[t, b]))
+            assert float(rew[t, b]) == r and bool(dones[t, b]) == done, (b, t)
+            total += r
+            t += 1
+        assert int(out["episode_length"][b]) == t and not alive[t:, b].any() and (acts[t:, b] == 5).all()
+        assert float(out["episode_reward"][b]) == pytest.approx(total, abs=1e-12)
+        assert np.array_equal(out["final_obs"][b].cpu().numpy().view(np.uint32), vec.view(np.uint32))
