@@ -83,6 +83,7 @@ struct ahr_graph {
   int device = 0;
   GraphView view;
   DevBuf ws;
+  DevBuf recs;  // packed node attributes (one 32-byte record per node)
 };
 
 extern "C" {
@@ -543,11 +544,20 @@ int ahr_graph_create(ahr_graph **out, int device, int64_t n_nodes, const int64_t
     g->view.row_ptr[s] = dev_row_ptr[s];
     g->view.col_idx[s] = dev_col_idx[s];
   }
-  g->view.node_type = dev_node_type;
-  g->view.level = dev_level;
-  g->view.judge = dev_judge;
-  g->view.judge_term = dev_judge_term;
-  g->view.conf = dev_conf;
+  g->view.rec = nullptr;
+  if (n_nodes > 0) {
+    // pack the five attribute arrays into one 32-byte record per node (the caller's arrays are not referenced afterwards)
+    int rc = g->recs.reserve((size_t)n_nodes * sizeof(NodeRec));
+    if (rc == AHR_OK)
+      rc = graph_pack_nodes(n_nodes, dev_node_type, dev_level, dev_judge, dev_judge_term, dev_conf,
+                            reinterpret_cast<NodeRec *>(g->recs.ptr), 0);
+    if (rc == AHR_OK && cudaStreamSynchronize(0) != cudaSuccess) {
+      set_error("ahr_graph_create: packing the node attributes failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = AHR_E_CUDA;
+    }
+    if (rc != AHR_OK) { g->recs.release(); delete g; return rc; }
+    g->view.rec = reinterpret_cast<const NodeRec *>(g->recs.ptr);
+  }
   *out = g;
   return AHR_OK;
 }
@@ -556,6 +566,7 @@ int ahr_graph_destroy(ahr_graph *g) {
   if (!g) return AHR_OK;
   DeviceGuard guard(g->device);
   g->ws.release();
+  g->recs.release();
   delete g;
   return AHR_OK;
 }

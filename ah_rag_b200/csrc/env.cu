@@ -59,9 +59,10 @@ __device__ __forceinline__ void env_featurize(const EnvView &e, const GraphView 
     float *o = f + 4 + j * 8;
     if (j < shown) {
       const int32_t v = e.shown_ids[env * ENV_SHOWN + j];
-      const uint8_t t = g.node_type[v];
-      const uint8_t lv = g.level[v];
-      const double judge = g.judge[v], conf = g.conf[v];
+      const NodeRec rec = g.rec[v];  // one sector per shown node
+      const uint8_t t = rec.type;
+      const uint8_t lv = rec.level;
+      const double judge = rec.judge, conf = rec.conf;
       o[0] = t == AHR_NT_ENTITY ? 1.f : 0.f;
       o[1] = t == AHR_NT_SUMMARY ? 1.f : 0.f;
       o[2] = (t != AHR_NT_ENTITY && t != AHR_NT_SUMMARY) ? 1.f : 0.f;

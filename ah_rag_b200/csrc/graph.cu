@@ -36,6 +36,26 @@ __global__ void round4_kernel(const double *__restrict__ x, int64_t n, double *_
   if (i < n) out[i] = round4_py(x[i]);
 }
 
+__global__ void pack_nodes_kernel(int64_t n, const uint8_t *__restrict__ node_type, const uint8_t *__restrict__ level,
+                                  const double *__restrict__ judge, const double *__restrict__ judge_term,
+                                  const double *__restrict__ conf, NodeRec *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  NodeRec r;
+  r.judge = judge[i]; r.judge_term = judge_term[i]; r.conf = conf[i];
+  r.type = node_type[i]; r.level = level[i];
+  for (int j = 0; j < 6; ++j) r.pad[j] = 0;
+  out[i] = r;
+}
+
+int graph_pack_nodes(int64_t n_nodes, const uint8_t *node_type, const uint8_t *level, const double *judge,
+                     const double *judge_term, const double *conf, NodeRec *out, cudaStream_t stream) {
+  if (n_nodes <= 0) return AHR_OK;
+  pack_nodes_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, stream>>>(n_nodes, node_type, level, judge, judge_term, conf, out);
+  AHR_KERNEL_CHECK();
+  return AHR_OK;
+}
+
 int debug_round4(const double *x, int64_t n, double *out, cudaStream_t stream) {
   if (n <= 0) return AHR_OK;
   round4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, n, out);
@@ -115,7 +135,7 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_big_kernel(AnchorArg
         node = v; sem = sem_r; kind = EK_SEED;
         if (a.seed_sem) a.seed_sem[(int64_t)q * a.n_seeds + r] = sem_r;
       } else {
-        const uint8_t t = g.node_type[v];
+        const uint8_t t = g.rec[v].type;
         if (t == AHR_NT_ENTITY && j - 1 < a.prm.parent_cap) {  // first 2 out-belongs_to parents, x0.9 (:733-736)
           const int64_t p0 = g.row_ptr[AHR_CSR_BEL_OUT][v], p1 = g.row_ptr[AHR_CSR_BEL_OUT][v + 1];
           if (p0 + (j - 1) < p1) {
@@ -181,15 +201,16 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_big_kernel(AnchorArg
   for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
     if (!(e_flag[e] & 1)) continue;
     const int32_t node = e_node[e];
-    const uint8_t t = g.node_type[node];
-    const double judge = g.judge[node], conf = g.conf[node];
+    const NodeRec rec = g.rec[node];  // one sector: type, judge, judge_term, conf
+    const uint8_t t = rec.type;
+    const double judge = rec.judge, conf = rec.conf;
     const bool has_j = judge == judge, has_c = conf == conf;  // NaN encodes None
     bool ok = true;
     if (P.type_mask != 0 && !((P.type_mask >> t) & 1)) ok = false;                       // :756-757
     if (P.has_judge_min && (!has_j || judge < P.judge_min)) ok = false;                  // :759-760
     if (P.has_conf_min && (!has_c || conf < P.conf_min)) ok = false;                     // :761-762
     if (!ok) continue;
-    const double jt = has_j ? g.judge_term[node] : 0.0;
+    const double jt = has_j ? rec.judge_term : 0.0;
     const double ct = has_c ? __ddiv_rn(conf, 10.0) : 0.0;
     double score = __dmul_rn(P.alpha, e_sem[e]);
     score = __dadd_rn(score, __dmul_rn(P.beta, jt));
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
         node = v; sem = sem_r; kind = EK_SEED;
         if (a.seed_sem) a.seed_sem[(int64_t)q * a.n_seeds + r] = sem_r;
       } else {
-        const uint8_t t = g.node_type[v];
+        const uint8_t t = g.rec[v].type;
         if (t == AHR_NT_ENTITY && j - 1 < a.prm.parent_cap) {  // first 2 out-belongs_to parents, x0.9 (:733-736)
           const int64_t p0 = g.row_ptr[AHR_CSR_BEL_OUT][v], p1 = g.row_ptr[AHR_CSR_BEL_OUT][v + 1];
           if (p0 + (j - 1) < p1) {
@@ -394,15 +415,16 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
   for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
     if (!(e_flag[e] & 1)) continue;
     const int32_t node = e_node[e];
-    const uint8_t t = g.node_type[node];
-    const double judge = g.judge[node], conf = g.conf[node];
+    const NodeRec rec = g.rec[node];  // one sector: type, judge, judge_term, conf
+    const uint8_t t = rec.type;
+    const double judge = rec.judge, conf = rec.conf;
     const bool has_j = judge == judge, has_c = conf == conf;  // NaN encodes None
     bool ok = true;
     if (P.type_mask != 0 && !((P.type_mask >> t) & 1)) ok = false;                       // :756-757
     if (P.has_judge_min && (!has_j || judge < P.judge_min)) ok = false;                  // :759-760
     if (P.has_conf_min && (!has_c || conf < P.conf_min)) ok = false;                     // :761-762
     if (!ok) continue;
-    const double jt = has_j ? g.judge_term[node] : 0.0;
+    const double jt = has_j ? rec.judge_term : 0.0;
     const double ct = has_c ? __ddiv_rn(conf, 10.0) : 0.0;
     double score = __dmul_rn(P.alpha, e_sem[e]);
     score = __dadd_rn(score, __dmul_rn(P.beta, jt));

@@ -80,7 +80,7 @@ __device__ __forceinline__ void expand_walk(ExpandState &st, const GraphView &g,
     } else {
       full = expand_segment(st, g, AHR_CSR_REL_OUT, v, -1, lane);
       if (!full) full = expand_segment(st, g, AHR_CSR_REL_IN, v, -1, lane);
-      if (!full && g.node_type[v] == AHR_NT_ENTITY) {
+      if (!full && g.rec[v].type == AHR_NT_ENTITY) {
         // second hop: every hyperedge h of v, then the other participants of h  (environment.py:456-467)
         const int64_t h0 = g.row_ptr[AHR_CSR_PART_OUT][v], h1 = g.row_ptr[AHR_CSR_PART_OUT][v + 1];
         for (int64_t hi = h0; hi < h1 && !full; ++hi) {

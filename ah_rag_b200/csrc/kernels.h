@@ -66,15 +66,24 @@ int gather_rows_i64(const float *src_s, const int64_t *src_i, const int32_t *sel
 int gather_query_rows(const void *src, int64_t row_bytes, const int32_t *sel, int32_t n_sel, void *out, cudaStream_t stream);
 
 // ---- graph.cu (K2) ----
+// Node attributes packed into ONE 32-byte record = one DRAM sector per node.  The five separate arrays the caller hands to
+// ahr_graph_create cost five sectors per touched node (hop 1 on c5: 63.5 MB of sector traffic for ~10 MB of useful bytes,
+// profiles/r1_k2_ncu.md); the library packs them once at create time.
+struct alignas(32) NodeRec {
+  double judge;       // NaN = None
+  double judge_term;  // 1 / (1 + exp(-judge / 10)) as evaluated by the host (the reference's own np.exp)
+  double conf;        // NaN = None
+  uint8_t type;       // AHR_NT_*
+  uint8_t level;
+  uint8_t pad[6];
+};
+static_assert(sizeof(NodeRec) == 32, "NodeRec must be one 32-byte sector");
+
 struct GraphView {
   int64_t n_nodes;
   const int64_t *row_ptr[AHR_N_CSR];
   const int32_t *col_idx[AHR_N_CSR];
-  const uint8_t *node_type;
-  const uint8_t *level;
-  const double *judge;
-  const double *judge_term;
-  const double *conf;
+  const NodeRec *rec;  // [n_nodes], library-owned
 };
 int graph_anchor_rerank(const GraphView &g, int32_t nq, int32_t n_seeds, const int32_t *seed_nodes,
                         const float *seed_scores, const ahr_rerank_params &prm, int32_t top_k, int32_t *out_nodes,
@@ -85,6 +94,8 @@ size_t graph_anchor_workspace_bytes(int32_t nq, int32_t n_seeds, const ahr_reran
 int graph_expand(const GraphView &g, int32_t n_env, const int32_t *ops, const int32_t *in_ids,
                  const int32_t *in_offsets, int32_t limit, int32_t *out_ids, int32_t *out_counts, cudaStream_t stream);
 int debug_round4(const double *x, int64_t n, double *out, cudaStream_t stream);
+int graph_pack_nodes(int64_t n_nodes, const uint8_t *node_type, const uint8_t *level, const double *judge,
+                     const double *judge_term, const double *conf, NodeRec *out, cudaStream_t stream);
 
 // ---- lca.cu ----
 size_t graph_lca_workspace_bytes(int64_t n_nodes);

@@ -133,6 +133,8 @@ int ahr_merge_topk_packed(int device, const void *dev_packed, int64_t record_byt
  *   judge       overall judge score, NaN when absent (judge is None)       hierarchical_graph.py:746-752
  *   judge_term  1/(1+exp(-judge/10)) evaluated by the host exactly as :766 does, 0.0 when absent
  *   conf        confidence, NaN when absent                                :753
+ * The CSR arrays are borrowed (they must outlive the handle); the five attribute arrays are copied at create time into
+ * one 32-byte record per node (one DRAM sector per touched node instead of five) and are not referenced afterwards.
  * ---------------------------------------------------------------------------------------------- */
 int ahr_graph_create(ahr_graph **out, int device, int64_t n_nodes, const int64_t *const dev_row_ptr[AHR_N_CSR],
                      const int32_t *const dev_col_idx[AHR_N_CSR], const uint8_t *dev_node_type,
