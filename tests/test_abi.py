@@ -58,3 +58,22 @@ def test_product_never_imports_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     src = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, fn)
+
+
+def test_env_batch_struct_mirrors_header():
+    """ctypes mirror of ``struct ahr_env_batch``: same field names in the same order, 4 int32 + 17 pointers."""
+    import ctypes
+    import re
+    from ah_rag_b200 import _lib
+    with open(os.path.join(ROOT, "include", "ahrag_b200.h"), "r", encoding="utf-8") as f:
+        text = f.read()
+    body = re.search(r"typedef struct ahr_env_batch \{(.*?)\} ahr_env_batch;", text, re.S).group(1)
+    names = []
+    for decl in body.split(";"):
+        decl = re.sub(r"/\*.*?\*/", "", decl, flags=re.S).strip()
+        if not decl:
+            continue
+        _, rest = decl.split(None, 1)
+        names += [n.strip().lstrip("*") for n in rest.split(",")]
+    assert names == [n for n, _ in _lib.EnvBatch._fields_]
+    assert ctypes.sizeof(_lib.EnvBatch) == 4 * 4 + 17 * ctypes.sizeof(ctypes.c_void_p)
