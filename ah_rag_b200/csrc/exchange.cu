@@ -77,10 +77,23 @@ push_kernel(PeerTable peers, int rank, int world, size_t slot_off, size_t rec_by
   if (threadIdx.x == 0) *done_counter = 0;  // ready for the next launch (stream-ordered)
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // Blocks until every peer's record of this epoch has landed (one acquire per peer, by the first `world` threads).
-__global__ void wait_flags_kernel(const uint64_t *flags, int rank, int world, uint64_t epoch) {
-  if ((int)threadIdx.x < world && (int)threadIdx.x != rank)
-    while (ld_acquire_sys_u64(flags + threadIdx.x) < epoch) __nanosleep(64);
+// A peer that never delivers (crashed rank) must not leave this GPU spinning for ever, nor let the merge run on stale
+// data: after `timeout_ns` the kernel traps, which surfaces as a CUDA error on the next call of this process.
+__global__ void wait_flags_kernel(const uint64_t *flags, int rank, int world, uint64_t epoch, unsigned long long timeout_ns) {
+  if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys_u64(flags + threadIdx.x) < epoch) {
+      __nanosleep(64);
+      if (global_timer_ns() - t0 > timeout_ns) __trap();
+    }
+  }
 }
 
 }  // namespace ahr
@@ -96,6 +109,7 @@ struct ahr_comm {
   unsigned int *done_counter = nullptr;
   uint64_t epoch = 0;
   bool connected = false;
+  unsigned long long timeout_ns = 600ull * 1000000000ull;  // AHR_COMM_TIMEOUT_S (default 600 s, like torch's NCCL watchdog)
   size_t slot_offset(int half, int src) const { return flags_bytes + ((size_t)half * world + src) * max_record; }
   size_t flag_offset(int half) const { return (size_t)half * world * sizeof(uint64_t); }
 };
@@ -127,6 +141,8 @@ int ahr_comm_create(ahr_comm **out, int device, int rank, int world, int64_t max
   c->peer.assign(world, nullptr);
   c->opened.assign(world, false);
   c->peer[rank] = c->base;
+  if (const char *e = getenv("AHR_COMM_TIMEOUT_S"))
+    if (atof(e) > 0) c->timeout_ns = (unsigned long long)(atof(e) * 1e9);
   c->connected = world == 1;
   *out = c;
   return AHR_OK;
@@ -210,7 +226,7 @@ int ahr_comm_exchange_merge(ahr_comm *c, int32_t nq, int32_t k, float *dev_out_s
     AHR_KERNEL_CHECK();
     if (stats) AHR_CUDA_CHECK(cudaEventRecord(ev[1], st));
     wait_flags_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const uint64_t *>(c->base + c->flag_offset(half)), c->rank,
-                                        c->world, c->epoch);
+                                        c->world, c->epoch, c->timeout_ns);
     AHR_KERNEL_CHECK();
   } else if (stats) {
     AHR_CUDA_CHECK(cudaEventRecord(ev[1], st));
