@@ -354,13 +354,19 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
   float *fs = reinterpret_cast<float *>(w + o_fs);
   int64_t *fi = reinterpret_cast<int64_t *>(w + o_fi);
   void *qsub = w + o_qsub;
-  // |tensor - canonical| <= eps_rel * ||q|| * ||x||: fp32 accumulation over dim/16 MMA steps plus the in-step
-  // alignment of 16 exact products; 2^-23 per accumulation step with generous headroom
+  // |tensor - canonical| <= eps_rel * ||q|| * ||x||.  Worst-case model of the tcgen05 accumulation (it truncates rather
+  // than rounds, and aligns the 16 exact products of a K = 16 step to the largest exponent before adding them):
+  //   per K-step  <= 2 ulp(acc) for the truncated add + 16 * 2^-24 * max|product| for the alignment
+  //   dim/16 steps, |acc| and sum|products| <= ||q|| ||x||  ->  (dim/16) * 2 * 2^-23 + dim * 2^-24 = (dim/4) * 2^-23
+  // All-positive / strongly correlated rows make the truncation errors add up with the same sign (they cancel on the
+  // zero-mean rows of the synthetic corpora: measured error there is ~ bound/8), so the bound carries a further 2x:
+  // (dim/2 + 64) * 2^-23.  tests/test_gpu_topk.py asserts |tc - canonical| <= eps/4 on all-positive, large-norm and
+  // dim = 1024..4096 inputs.  The only cost of a wide bound is more tier-2 / brute-force fallbacks.
   // fp32 rows go through the hi/lo split: 3x the accumulation steps plus the dropped lo*lo and residual terms
   // (|x - hi - lo| <= 2^-18 |x| per operand -> <= 3 * 2^-18, rounded up to 2^-16)
   const float eps_rel = idx->dtype == AHR_DTYPE_F32
-                            ? (float)((3 * idx->dim / 8 + 32) * std::ldexp(1.0, -23) + std::ldexp(1.0, -16))
-                            : (float)((idx->dim / 8 + 32) * std::ldexp(1.0, -23));
+                            ? (float)((3 * idx->dim / 2 + 64) * std::ldexp(1.0, -23) + std::ldexp(1.0, -16))
+                            : (float)((idx->dim / 2 + 64) * std::ldexp(1.0, -23));
   // one tier over `n` queries at `q`: results into out_* [n, k], uncertified query indices into `fail_list`
   auto tier = [&](const void *q, int32_t n, int32_t kc, float *out_s, int64_t *out_i, int32_t *fail_list, int32_t *n_fail) {
     int r = tc_topk(idx, q, n, kc, cs, ci, nullptr, st);

@@ -17,6 +17,14 @@ all-gather + device k-way merge.
              on its launch stream, against the measured bf16 tensor peak in MEASURED_PEAKS.json.
   cpu_baseline : the oracle's CPU retrieval pass (oracle/cpu_retrieval.py) on a bounded sample, host cores.
 
+  parity_check : after the timed loops, at every N: sampled queries of the timed batch (bf16 mode: recall@k and score
+             tolerance; fp32-exact mode: ids and score bits) against oracle/exact_topk.c scanning ALL corpus rows on
+             the host (every rank scans its own shard, rank 0 merges with the same total order).
+  extra    : driver-timed figures for the other BASELINE configurations -- c4 (100M x 768, 256-query batch: the real
+             sharded configuration at N > 1, the per-GPU shard of the 8-GPU case at N = 1) and c5 (20M-node / 500M-edge
+             graph, 1024 environments: hop 1, hop 2, uncapped-walk bandwidth, gym rollout) with the graph-half CPU
+             baseline.  ``--no-extra`` skips it.
+
 ``--impl reference`` times that CPU pass alone (the reference is pure Python over Chroma/HNSW, which is not
 installable here) and prints the same JSON line with "impl": "reference".
 """
@@ -44,12 +52,22 @@ METRIC = "queries/sec (top-k=50, 10M x 1024 bf16 corpus, 4096-query batch)"
 
 
 def _traffic(world: int):
-    """DRAM bytes per K1 launch from the committed ncu --set full capture (1-GPU c3 workload only)."""
-    path = os.path.join(ROOT, "profiles", "r1_k1_traffic.json")
-    if world == 1 and N_ROWS == 10_000_000 and DIM == 1024 and N_QUERIES == 4096 and os.path.exists(path):
-        with open(path) as f:
-            return json.load(f).get("dram_bytes_per_launch")
-    return None
+    """(DRAM bytes per K1 launch, where the figure comes from).  ncu cannot run inside the timed process, so the figure
+    is the one of the committed ``ncu --set full`` capture of this same command (1-GPU c3 workload only)."""
+    for name in ("r2_k1_traffic.json", "r1_k1_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if world == 1 and N_ROWS == 10_000_000 and DIM == 1024 and N_QUERIES == 4096 and os.path.exists(path):
+            with open(path) as f:
+                d = json.load(f)
+            return d.get("dram_bytes_per_launch"), f"committed ncu capture profiles/{name} ({d.get('commit', 'commit not recorded')})"
+    return None, "no ncu capture for this configuration (ncu runs one GPU, the c3 shape)"
+
+
+def _host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def _peaks():
@@ -153,6 +171,16 @@ def make_queries(torch, device, nq: int, dim: int, seed: int = 5678):
     return q.to(torch.bfloat16).contiguous()
 
 
+def _cpu_sample():
+    """One bounded sample of the CPU retrieval pass: the REAL query batch against a slice of the corpus rows, all host
+    threads (launchers such as torchrun export OMP_NUM_THREADS=1: set the thread count explicitly)."""
+    import torch
+    from oracle import cpu_retrieval
+    torch.set_num_threads(_host_threads())
+    return cpu_retrieval.time_sample(N_ROWS, DIM, TOP_K, int(os.environ.get("AHR_BENCH_CPU_ROWS", 250_000)),
+                                     int(os.environ.get("AHR_BENCH_CPU_QUERIES", N_QUERIES)))
+
+
 def run_reference(args) -> int:
     """CPU arm: the oracle port of the reference's retrieval on the host cores, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -160,30 +188,76 @@ def run_reference(args) -> int:
         return 0
     import torch
     from oracle import cpu_retrieval
-    sample_rows = int(os.environ.get("AHR_BENCH_CPU_ROWS", 500_000))
-    sample_q = int(os.environ.get("AHR_BENCH_CPU_QUERIES", 128))
+    torch.set_num_threads(_host_threads())
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_retrieval.time_sample(N_ROWS, DIM, TOP_K, 65536, 16)
-    vals = []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        vals.append(cpu_retrieval.time_sample(N_ROWS, DIM, TOP_K, sample_rows, sample_q))
-    wall = time.perf_counter() - t0
+        cpu_retrieval.time_sample(N_ROWS, DIM, TOP_K, 65536, 64)
+    vals = [_cpu_sample() for _ in range(args.steps)]
     v = statistics.median([x["value"] for x in vals])
     base = vals[-1]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, args.steps),
+        "steps": args.steps, "warmup": args.warmup,
+        # time one full step (the whole batch against the whole corpus) takes at the measured rate
+        "ms_per_step": 1000.0 * N_QUERIES / v,
+        "sample_seconds_per_step": statistics.median([x["seconds"] for x in vals]),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"c3: synthetic {N_ROWS}x{DIM} corpus, {N_QUERIES}-query batch, top-k={TOP_K}",
                    "note": "reference CPU path = oracle port (torch fp32 GEMM + topk, all host threads); the "
                            "reference's own Chroma/HNSW call is not installable here"},
-        "cpu_baseline": {"value": v, "unit": "queries/s", "cores": base["cores"], "kind": "port", "sample": base["sample"]},
+        "cpu_baseline": {"value": v, "unit": "queries/s", "cores": base["cores"], "host_cpus": base["host_cpus"],
+                         "kind": "port", "sample": base["sample"]},
         "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def parity_check(torch, dist, world, rank, device, rows, lo, q_dev, sharded, k):
+    """Sampled queries of the timed batch against the CPU oracle over ALL corpus rows.  Every rank scans its own shard
+    on its share of the host cores (oracle/exact_topk.c, canonical fp64-ordered scores), rank 0 merges the lists with the
+    same total order (score desc, id asc) and compares: bf16 mode -> recall@k and relative score error; fp32-exact mode
+    -> ids and score bits."""
+    import numpy as np
+    from oracle import exact  # the checker, never the measured path
+    nq = int(q_dev.shape[0])
+    sel = sorted({0, 1, nq // 2, nq - 1})
+    t0 = time.perf_counter()
+    s_b, i_b = sharded.topk(q_dev, k, mode="bf16")
+    s_b, i_b = s_b[sel].cpu().numpy(), i_b[sel].cpu().numpy()
+    s_x, i_x = sharded.topk(q_dev, k, mode="exact")
+    s_x, i_x = s_x[sel].cpu().numpy(), i_x[sel].cpu().numpy()
+    bits = lambda t: t.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+    qs = bits(q_dev[sel])
+    threads = max(1, _host_threads() // world)
+    ps, pi = [], []
+    chunk = 1_000_000
+    for c0 in range(0, int(rows.shape[0]), chunk):  # bounded host memory: 1M rows (2 GB) at a time
+        sc, ids = exact.exact_topk_rowpar(bits(rows[c0:c0 + chunk]), qs, k, id_base=lo + c0, n_threads=threads)
+        ps.append(sc)
+        pi.append(ids)
+    ls, li = exact.merge_topk(ps, pi, k)
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (ls, li))
+        ls, li = exact.merge_topk([p[0] for p in parts], [p[1] for p in parts], k)
+    recall = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(i_b, li)]))
+    # bf16-mode scores against the canonical score of the same row (ids may differ at the k-th boundary)
+    rel = 0.0
+    for r in range(len(sel)):
+        canon = dict(zip(li[r].tolist(), ls[r].tolist()))
+        for idv, sv in zip(i_b[r].tolist(), s_b[r].tolist()):
+            if idv in canon:
+                rel = max(rel, abs(sv - canon[idv]) / max(abs(canon[idv]), 1e-6))
+    ids_equal = bool(np.array_equal(i_x, li))
+    bits_equal = bool(np.array_equal(s_x.view(np.uint32), ls.view(np.uint32)))
+    return {"queries": sel, "rows_scanned": N_ROWS, "n_gpus": world,
+            "exact_ids_equal": ids_equal, "exact_score_bits_equal": bits_equal,
+            "bf16_recall_at_k": recall, "bf16_max_rel_score_err": rel,
+            "pass": bool(ids_equal and bits_equal and recall >= 0.999 and rel <= 1e-2),
+            "oracle": "oracle/exact_topk.c: full scan of every corpus row on the host (canonical fp64-ordered score, "
+                      "ties -> lower id); per-rank shard scans merged with the same total order",
+            "host_threads_per_rank": threads, "seconds": round(time.perf_counter() - t0, 2)}
 
 
 def main() -> int:
@@ -194,6 +268,8 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "exact"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the c4 / c5 block")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled parity check against the CPU oracle")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -297,6 +373,17 @@ def main() -> int:
     sampler.window_end()
     clocks = sampler.stop() if rank == 0 else None
 
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(torch, dist, world, rank, device, rows, lo, q_dev, sharded, TOP_K)
+    extra = None
+    if not args.no_extra and os.environ.get("AHR_BENCH_EXTRA", "1") != "0":
+        # free the c3 shard first: the c4 shard of a 2-GPU run is 76.8 GB
+        del sharded, index, rows
+        torch.cuda.empty_cache()
+        import bench_workloads as bw
+        extra = {"c4": bw.extra_c4(dist, world, rank, device), "c5": bw.extra_c5(dist, world, rank, device)}
+
     ms_step = ms_total / args.steps
     qps = N_QUERIES / (ms_step / 1e3)
     qps_e2e = N_QUERIES / (ms_e2e / args.steps / 1e3)
@@ -320,7 +407,8 @@ def main() -> int:
                     "d2h_bytes_per_step": N_QUERIES * TOP_K * 12},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": _traffic(world),
+                         "frac": achieved / peaks["tflops"], "traffic": _traffic(world)[0],
+                         "traffic_source": _traffic(world)[1],
                          "kernel": "ahr::topk_tc2_kernel (K1, CTA-pair tcgen05 GEMM + top-k epilogue)",
                          "algorithmic_flops_per_launch": flops,
                          "frac_of_burst_peak": (achieved / peaks["tflops_burst"]) if peaks.get("tflops_burst") else None,
@@ -328,12 +416,16 @@ def main() -> int:
                          "peak_source": peaks["source"],
                          "hbm_floor_ms": (hi - lo) * DIM * 2 / (peaks["hbm_gbs"] * 1e9) * 1e3},
             "clocks": clocks,
+            "timing_note": "value and e2e are two separate K-step loops run back to back; under the power cap the SM clock "
+                           "drifts by ~2 % between them, so e2e can read slightly above value",
         }
+        if parity is not None:
+            line["parity_check"] = parity
+        if extra is not None:
+            line["extra"] = extra
         if not args.skip_cpu_baseline and world == 1:
-            from oracle import cpu_retrieval  # checker / reported baseline only, never the measured path
-            line["cpu_baseline"] = {k: v for k, v in cpu_retrieval.time_sample(
-                N_ROWS, DIM, TOP_K, int(os.environ.get("AHR_BENCH_CPU_ROWS", 500_000)),
-                int(os.environ.get("AHR_BENCH_CPU_QUERIES", 128))).items() if k != "seconds"}
+            # checker / reported baseline only, never the measured path
+            line["cpu_baseline"] = {k: v for k, v in _cpu_sample().items() if k != "seconds"}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

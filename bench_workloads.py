@@ -462,6 +462,159 @@ def run_c5dist():
                           "scaling": "environments sharded, graph replicated, no collective"}), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------
+# The "extra" block of bench.py: driver-timed figures for configs[3] (c4) and configs[4] (c5), with the graph-half
+# CPU baseline.  Called by bench.py after its c3 loops, in the same process / process group.
+# ---------------------------------------------------------------------------------------------
+def extra_c4(dist, world, rank, dev, steps=10):
+    """c4 = 100M x 768 bf16, 256-query batch, k = 50 (the HBM / balance-point regime of K1).
+    world > 1: the real configuration -- 100M rows sharded by node range over the ranks, candidate exchange + merge.
+    world = 1: one GPU cannot hold the 153.6 GB, so the per-rank work of the 8-GPU configuration (12.5M rows) is timed,
+    at Q = 256 (CTA pairs) and Q = 64 (one CTA per tile: the pure HBM stream)."""
+    from ah_rag_b200.dist import ShardedIndex, shard_bounds
+    n_total, dim, k = 100_000_000, 768, 50
+    hbm, tf, src = peaks()
+    lo, hi = shard_bounds(n_total, max(world, 8) if world == 1 else world, rank)
+    n = hi - lo
+    X = unit_bf16(n, dim, 1234 + 1000 * rank, dev)
+    Qall = unit_bf16(256, dim, 5678, dev)
+    sh = ShardedIndex.from_rows(X, id_base=lo)
+    peer = sh.enable_peer_exchange(256, k) if world > 1 else False
+    out = {"workload": (f"c4: 100M x 768 bf16 over {world} GPUs (shards of {n} rows), k=50, bf16 mode" if world > 1 else
+                        f"c4 shard: {n} x 768 bf16 = the per-GPU work of c4 on 8 GPUs (one GPU cannot hold 153.6 GB), k=50, bf16 mode"),
+           "n_gpus": world, "exchange": "peer-memory stores" if peer else ("nccl all-gather" if world > 1 else "none"),
+           "hbm_peak_gbs": hbm, "tensor_peak_tflops": tf, "peak_source": src, "batches": []}
+    for nq in (256, 64):
+        Q = Qall[:nq].contiguous()
+        sh.index.set_profiling(True)
+        sh.index.get_profile()
+        ms = _timed_dist(dist, world, dev, lambda: sh.topk(Q, k, mode="bf16"), steps=steps)
+        prof = sh.index.get_profile()
+        sh.index.set_profiling(False)
+        k1 = prof["k1_ms_total"] / max(1, prof["k1_launches"])
+        t_mem = 2.0 * n * dim / (hbm * 1e9) * 1e3
+        t_mma = 2.0 * max(nq, 128) * n * dim / (tf * 1e12) * 1e3  # the tensor core works on whole 128-row query tiles
+        out["batches"].append({"nq": nq, "ms_per_batch": ms, "queries_per_s": nq / ms * 1e3, "k1_ms_rank0": k1,
+                               "hbm_gbs": 2.0 * n * dim / (k1 * 1e-3) / 1e9, "hbm_frac": t_mem / k1,
+                               "t_mem_ms": t_mem, "t_mma_ms": t_mma, "binding": "tensor" if t_mma > t_mem else "hbm",
+                               "frac_of_binding_roofline": max(t_mem, t_mma) / k1, "n_slabs": prof["n_slabs"]})
+    del sh, X
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_c5(dist, world, rank, dev, scale=1.0, cpu_budget_s=6.0):
+    """c5 = synthetic hierarchical graph 20M nodes / 500M edges, 1024 environments x 50 seeds: hop 1 (anchor expansion +
+    rerank), hop 2 (one expand_* per environment), the uncapped-walk bandwidth view, the device gym rollout; graph
+    replicated per GPU, environments sharded over the ranks (no exchange on the hop path).  Rank 0 adds the graph-half CPU
+    baseline (sequential loop, one core): oracle/array_graph.py at this graph's full size, and oracle/ref_search.py over
+    NetworkX on a reduced graph."""
+    hbm, _, src = peaks()
+    a = make_c5_graph(dev, scale)
+    g = DeviceGraph(a, dev)
+    n_env_total, n_seeds, top_k, m, limit = 1024, 50, 50, 5, 10
+    n_env = n_env_total // world
+    seeds, scores, ops = c5_inputs(a, n_env_total, n_seeds, dev)
+    sl = slice(rank * n_env, (rank + 1) * n_env)
+    seeds_l, scores_l, ops_l = seeds[sl].contiguous(), scores[sl].contiguous(), ops[sl].contiguous()
+    prm = engine.SearchParams(member_top_m=m)
+    out1 = g.anchor_rerank(seeds_l, scores_l, prm, top_k)
+    ms_h1 = _timed_dist(dist, world, dev, lambda: g.anchor_rerank(seeds_l, scores_l, prm, top_k, want_cluster=False), steps=20)
+    take = torch.where(ops_l == 2, 1, 2)
+    offs = torch.zeros(n_env + 1, dtype=torch.int32, device=dev)
+    offs[1:] = torch.cumsum(take, 0).to(torch.int32)
+    first2 = out1["nodes"][:, :2]
+    keep = torch.arange(2, device=dev)[None, :] < take[:, None]
+    flat = first2[keep].to(torch.int32).contiguous()
+    oi, oc = g.expand(ops_l, flat, offs, limit)
+    ms_h2 = _timed_dist(dist, world, dev, lambda: g.expand(ops_l, flat, offs, limit), steps=50)
+    # both hops back to back (the per-batch cost of a rollout step that re-anchors)
+    ms_both = _timed_dist(dist, world, dev, lambda: (g.anchor_rerank(seeds_l, scores_l, prm, top_k, want_cluster=False),
+                                                     g.expand(ops_l, flat, offs, limit)), steps=20)
+    # uncapped walk = bandwidth view: 65536 L1 summaries (260 out + ~260 in related_to neighbours each), limit 512
+    l_lo, l_hi = a["ranges"]["l1"]
+    gen = torch.Generator(device=dev).manual_seed(70 + rank)
+    nb = 65536 // world
+    big_in = torch.randint(l_lo, l_hi, (nb,), generator=gen, device=dev).to(torch.int32)
+    big_ops = torch.full((nb,), 2, dtype=torch.int32, device=dev)
+    big_off = torch.arange(nb + 1, dtype=torch.int32, device=dev)
+    g.expand(big_ops, big_in, big_off, 512)
+    ms_bw = _timed_dist(dist, world, dev, lambda: g.expand(big_ops, big_in, big_off, 512), steps=10)
+    rp_o, rp_i = a["row_ptr"][4], a["row_ptr"][5]
+    bi = big_in.long()
+    deg = (rp_o[bi + 1] - rp_o[bi]) + (rp_i[bi + 1] - rp_i[bi])
+    bw_bytes = int(deg.sum().item()) * 4 + nb * (2 * 16 + 4) + nb * 512 * 4  # col_idx + row_ptr pairs + ids in + ids out
+    # device gym rollout: reset from a top-5 anchor + 6 steps
+    envb = engine.EnvBatchState(g, n_env, max_steps=6)
+    rr5 = g.anchor_rerank(seeds_l[:, :5].contiguous(), scores_l[:, :5].contiguous(), prm, 5, want_cluster=False)
+    acts = [torch.randint(0, 5, (n_env,), generator=gen, device=dev).to(torch.int32) for _ in range(6)]
+
+    def rollout():
+        envb.reset(rr5, 5)
+        for t in range(6):
+            envb.step(acts[t])
+
+    ms_roll = _timed_dist(dist, world, dev, rollout, steps=20)
+    envb.check_overflow()
+    out = {"workload": f"c5: synthetic hierarchical graph {a['n_nodes']} nodes / {a['n_edges']} edges, {n_env_total} environments x "
+                       f"{n_seeds} seeds; graph replicated on {world} GPU(s), {n_env} environments per GPU, no collective",
+           "n_gpus": world, "graph_bytes": g.nbytes(),
+           "hop1_anchor_rerank_ms": ms_h1, "hop2_expand_limit10_ms": ms_h2, "two_hops_ms": ms_both,
+           "envs_per_s_two_hops": n_env_total / ms_both * 1e3,
+           "uncapped_walk": {"frontier_nodes_per_gpu": nb, "ms": ms_bw, "algorithmic_bytes_per_gpu": bw_bytes,
+                             "useful_gbs_per_gpu": bw_bytes / (ms_bw * 1e-3) / 1e9,
+                             "frac_of_hbm": bw_bytes / (ms_bw * 1e-3) / 1e9 / hbm},
+           "gym_rollout_reset_plus_6_steps_ms": ms_roll, "gym_env_steps_per_s": n_env_total * 6 / ms_roll * 1e3,
+           "hbm_peak_gbs": hbm, "peak_source": src}
+    if rank == 0:
+        from oracle import array_graph, cpu_graph_baseline  # checker + reported CPU baseline, never the measured path
+        host = {"row_ptr": [t.cpu().numpy() for t in a["row_ptr"]], "col_idx": [t.cpu().numpy() for t in a["col_idx"]],
+                "node_type": a["node_type"].cpu().numpy(), "level": a["level"].cpu().numpy(), "judge": a["judge"].cpu().numpy(),
+                "judge_term": a["judge_term"].cpu().numpy(), "conf": a["conf"].cpu().numpy()}
+        sh, sch, opsh = seeds.cpu().numpy(), scores.cpu().numpy(), ops.cpu().numpy()
+        # parity on a sample of this rank's environments (array oracle over the host copy of the CSR)
+        o1 = {k_: v.cpu().numpy() for k_, v in out1.items()}
+        oih, och, offh, flath = oi.cpu().numpy(), oc.cpu().numpy(), offs.cpu().numpy(), flat.cpu().numpy()
+        sample = list(range(0, n_env, max(1, n_env // 32)))
+        ok1 = all(array_graph.anchor_rerank(host, sh[e], sch[e], top_k, m) ==
+                  [(int(o1["nodes"][e, j]), float(o1["semantic"][e, j]), float(o1["score"][e, j])) for j in range(o1["count"][e])]
+                  for e in sample)
+        ok2 = all(array_graph.expand(host, int(opsh[e]), flath[offh[e]:offh[e + 1]], limit) == list(oih[e, :och[e]]) for e in sample)
+        out["parity_check"] = {"sample_envs": len(sample), "anchor_rerank_bit_exact": bool(ok1), "expand_bit_exact": bool(ok2),
+                               "oracle": "oracle/array_graph.py over the host copy of the CSR"}
+        arr = cpu_graph_baseline.array_loop(host, sh, sch, opsh, top_k, m, limit, cpu_budget_s)
+        out["cpu_baseline"] = {"value": arr["envs_per_s"], "unit": "environments/s (hop 1 + hop 2)", "cores": 1, "kind": "port",
+                               "sample": f"oracle/array_graph.py (numpy CSR restatement) sequential loop over {arr['envs']} of the "
+                                         f"{n_env_total} environments on the full graph, {arr['seconds']:.1f} s"}
+        del host
+        small = make_c5_graph(dev, 0.0025 * scale, seed=43)  # ~50k nodes / ~1.25M edges: what NetworkX builds in seconds
+        hs = {"row_ptr": [t.cpu().numpy() for t in small["row_ptr"]], "col_idx": [t.cpu().numpy() for t in small["col_idx"]],
+              "node_type": small["node_type"].cpu().numpy(), "level": small["level"].cpu().numpy(),
+              "judge": small["judge"].cpu().numpy(), "judge_term": small["judge_term"].cpu().numpy(), "conf": small["conf"].cpu().numpy()}
+        s2, sc2, op2 = c5_inputs(small, 256, n_seeds, dev)
+        nxr = cpu_graph_baseline.networkx_loop(hs, s2.cpu().numpy(), sc2.cpu().numpy(), op2.cpu().numpy(), top_k, m, limit, cpu_budget_s)
+        out["cpu_baseline_networkx"] = {"value": nxr["envs_per_s"], "unit": "environments/s (hop 1 + hop 2)", "cores": 1, "kind": "port",
+                                        "sample": f"oracle/ref_search.py (the reference's algorithm over NetworkX, as the reference holds its "
+                                                  f"graph) sequential loop, {nxr['envs']} environments on a reduced graph of {nxr['nodes']} nodes / "
+                                                  f"{nxr['edges']} edges, {nxr['seconds']:.1f} s (+ {nxr['graph_build_s']:.1f} s to build the DiGraph)"}
+    del g, a
+    torch.cuda.empty_cache()
+    return out
+
+
+def c5_inputs(a, n_env, n_seeds, dev, seed=7):
+    """Seeds (80 % entities, 20 % L1 summaries: the index holds both), descending scores, one hop-2 op per environment."""
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    e_lo, e_hi = a["ranges"]["entity"]
+    l_lo, l_hi = a["ranges"]["l1"]
+    seeds = torch.where(torch.rand((n_env, n_seeds), generator=gen, device=dev) < 0.8,
+                        torch.randint(e_lo, e_hi, (n_env, n_seeds), generator=gen, device=dev),
+                        torch.randint(l_lo, l_hi, (n_env, n_seeds), generator=gen, device=dev)).to(torch.int32)
+    scores = torch.sort(torch.rand((n_env, n_seeds), generator=gen, device=dev) * 0.9 + 0.05, dim=1, descending=True).values
+    ops = torch.randint(0, 3, (n_env,), generator=gen, device=dev).to(torch.int32)
+    return seeds, scores.to(torch.float32).contiguous(), ops
+
+
 def main():
     assert torch.cuda.is_available(), "no CUDA device: the engine has no CPU fallback"
     which = sys.argv[1:] or ["c3x", "c4", "c5", "c2"]

@@ -39,6 +39,7 @@ def _load() -> ctypes.CDLL:
         vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
         lib.ahro_canonical_scores.argtypes = [vp, vp, i64, i32, i32, ctypes.c_int, vp]
         lib.ahro_exact_topk.argtypes = [vp, vp, i64, i32, i32, ctypes.c_int, i32, i64, vp, vp]
+        lib.ahro_exact_topk_rowpar.argtypes = [vp, vp, i64, i32, i32, ctypes.c_int, i32, i64, i32, vp, vp]
         lib.ahro_rescore.argtypes = [vp, vp, i32, i32, ctypes.c_int, i32, vp, vp]
         lib.ahro_round4.argtypes = [ctypes.c_double]
         lib.ahro_round4.restype = ctypes.c_double
@@ -126,6 +127,21 @@ def exact_topk(X: np.ndarray, Q: np.ndarray, k: int, id_base: int = 0):
     ids = np.empty((Q.shape[0], k), dtype=np.int64)
     rc = lib.ahro_exact_topk(X.ctypes.data, Q.ctypes.data, X.shape[0], X.shape[1], Q.shape[0],
                              _dtype_code(X), k, id_base, scores.ctypes.data, ids.ctypes.data)
+    assert rc == 0
+    return scores, ids
+
+
+def exact_topk_rowpar(X: np.ndarray, Q: np.ndarray, k: int, id_base: int = 0, n_threads: int = 0):
+    """``exact_topk`` parallelised over row blocks (few queries over a large corpus); same result bit for bit.
+    ``n_threads`` is explicit because launchers such as torchrun export OMP_NUM_THREADS=1."""
+    lib = _load()
+    X, Q = np.ascontiguousarray(X), np.ascontiguousarray(Q)
+    assert X.dtype == Q.dtype and X.shape[1] == Q.shape[1]
+    scores = np.empty((Q.shape[0], k), dtype=np.float32)
+    ids = np.empty((Q.shape[0], k), dtype=np.int64)
+    nt = int(n_threads) if n_threads > 0 else len(os.sched_getaffinity(0))
+    rc = lib.ahro_exact_topk_rowpar(X.ctypes.data, Q.ctypes.data, X.shape[0], X.shape[1], Q.shape[0],
+                                    _dtype_code(X), k, id_base, nt, scores.ctypes.data, ids.ctypes.data)
     assert rc == 0
     return scores, ids
 

@@ -42,6 +42,31 @@ static inline double canon_dot(const void *q, const void *x, int32_t d, int dtyp
     return acc;
 }
 
+/* canon_dot of four consecutive rows x, x + d, x + 2d, x + 3d at once (same per-pair summation order) */
+static inline void canon_dot4(const void *q, const void *x, int32_t d, int dtype, double acc[4]) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (dtype == 0) {
+        const float *a = (const float *)q, *b = (const float *)x;
+        for (int32_t j = 0; j < d; ++j) {
+            const double qj = (double)a[j];
+            a0 += qj * (double)b[j];
+            a1 += qj * (double)b[(size_t)d + j];
+            a2 += qj * (double)b[2 * (size_t)d + j];
+            a3 += qj * (double)b[3 * (size_t)d + j];
+        }
+    } else {
+        const uint16_t *a = (const uint16_t *)q, *b = (const uint16_t *)x;
+        for (int32_t j = 0; j < d; ++j) {
+            const double qj = (double)bf16_to_f32(a[j]);
+            a0 += qj * (double)bf16_to_f32(b[j]);
+            a1 += qj * (double)bf16_to_f32(b[(size_t)d + j]);
+            a2 += qj * (double)bf16_to_f32(b[2 * (size_t)d + j]);
+            a3 += qj * (double)bf16_to_f32(b[3 * (size_t)d + j]);
+        }
+    }
+    acc[0] = a0; acc[1] = a1; acc[2] = a2; acc[3] = a3;
+}
+
 /* returns 1 when (s1,id1) ranks strictly before (s2,id2) */
 static inline int ranks_before(float s1, int64_t id1, float s2, int64_t id2) {
     return (s1 > s2) || (s1 == s2 && id1 < id2);
@@ -95,6 +120,78 @@ int ahro_exact_topk(const void *X, const void *Q, int64_t n, int32_t d, int32_t 
             bi[p] = -1;
         }
     }
+    return 0;
+}
+
+/*
+ * Same result as ahro_exact_topk, parallel over ROW BLOCKS instead of queries (few queries, many rows: the sampled
+ * parity check of bench.py over the full corpus).  Every block keeps its own list per query with the same comparator;
+ * the lists are merged with it afterwards.  (score desc, id asc) is a total order, so the result does not depend on the
+ * blocking -- tests/test_oracle.py checks it equals ahro_exact_topk bit for bit.
+ */
+static void list_insert(float *bs, int64_t *bi, int32_t *cnt, int32_t k, float s, int64_t id) {
+    if (*cnt == k && !ranks_before(s, id, bs[k - 1], bi[k - 1])) return;
+    int32_t p = *cnt < k ? *cnt : k - 1;
+    while (p > 0 && ranks_before(s, id, bs[p - 1], bi[p - 1])) {
+        bs[p] = bs[p - 1];
+        bi[p] = bi[p - 1];
+        --p;
+    }
+    bs[p] = s;
+    bi[p] = id;
+    if (*cnt < k) ++*cnt;
+}
+
+int ahro_exact_topk_rowpar(const void *X, const void *Q, int64_t n, int32_t d, int32_t nq, int dtype, int32_t k,
+                           int64_t id_base, int32_t n_threads, float *out_scores, int64_t *out_ids) {
+    if (k <= 0 || d <= 0 || nq < 0 || n < 0) return -1;
+    const size_t esz = dtype == 0 ? 4 : 2;
+    const int64_t block = 4096;
+    const int64_t n_blocks = (n + block - 1) / block;
+    int64_t n_lists = n_threads > 0 ? n_threads : 1;
+    if (n_lists > n_blocks) n_lists = n_blocks > 0 ? n_blocks : 1;
+    float *ls = (float *)malloc((size_t)n_lists * nq * k * sizeof(float));
+    int64_t *li = (int64_t *)malloc((size_t)n_lists * nq * k * sizeof(int64_t));
+    int32_t *lc = (int32_t *)calloc((size_t)n_lists * nq, sizeof(int32_t));
+    if (!ls || !li || !lc) { free(ls); free(li); free(lc); return -2; }
+#pragma omp parallel for schedule(static) num_threads((int)n_lists)
+    for (int64_t t = 0; t < n_lists; ++t) {
+        /* list t owns blocks t, t + n_lists, ... */
+        for (int64_t b = t; b < n_blocks; b += n_lists) {
+            const int64_t r0 = b * block, r1 = r0 + block < n ? r0 + block : n;
+            for (int32_t qi = 0; qi < nq; ++qi) {
+                const char *q = (const char *)Q + (size_t)qi * d * esz;
+                float *bs = ls + ((size_t)t * nq + qi) * k;
+                int64_t *bi = li + ((size_t)t * nq + qi) * k;
+                int32_t *cnt = lc + (size_t)t * nq + qi;
+                int64_t r = r0;
+                for (; r + 4 <= r1; r += 4) {
+                    /* four rows side by side: four independent accumulation chains, each still j-ascending */
+                    double acc[4];
+                    canon_dot4(q, (const char *)X + (size_t)r * d * esz, d, dtype, acc);
+                    for (int u = 0; u < 4; ++u) list_insert(bs, bi, cnt, k, (float)acc[u], id_base + r + u);
+                }
+                for (; r < r1; ++r)
+                    list_insert(bs, bi, cnt, k, (float)canon_dot(q, (const char *)X + (size_t)r * d * esz, d, dtype),
+                                id_base + r);
+            }
+        }
+    }
+    for (int32_t qi = 0; qi < nq; ++qi) {
+        float *bs = out_scores + (size_t)qi * k;
+        int64_t *bi = out_ids + (size_t)qi * k;
+        int32_t cnt = 0;
+        for (int64_t t = 0; t < n_lists; ++t) {
+            const int32_t c = lc[(size_t)t * nq + qi];
+            for (int32_t j = 0; j < c; ++j)
+                list_insert(bs, bi, &cnt, k, ls[((size_t)t * nq + qi) * k + j], li[((size_t)t * nq + qi) * k + j]);
+        }
+        for (int32_t p = cnt; p < k; ++p) {
+            bs[p] = -INFINITY;
+            bi[p] = -1;
+        }
+    }
+    free(ls); free(li); free(lc);
     return 0;
 }
 

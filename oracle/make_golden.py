@@ -42,80 +42,87 @@ SEARCH_CASES = [
 GYM_ACTION_SEQS = [[1, 0, 2, 2, 3, 4, 5], [0, 0, 0, 0, 0, 0], [2, 1, 3, 3, 1, 2], [3, 4, 1, 5], [5]]
 
 
+def write_fixture(name, g, queries, search_cases, extra=None, env_queries=(0, 3), env_top_k=5):
+    """Run the UNMODIFIED reference over node-link graph `g` and write tests/golden/<name>.json/.npz: search results,
+    environment / expand_to_lca / gym traces.  Returns the ReferenceSession."""
+    stubs.reset_store()
+    rs = ref_runner.ReferenceSession(g)
+    qvecs = np.stack([stubs.hash_embed(q) for q in queries])
+    fixture = {"name": name, **(extra or {}), "node_link": g,
+               "index_ids": rs.index_ids, "queries": queries, "search": [], "env": [], "gym": [], "lca": []}
+    for qi, q in enumerate(queries):
+        for case in search_cases:
+            out = ref_runner.strip_search(rs.search(q, **case))
+            fixture["search"].append({"query": qi, "kwargs": case, "out": out})
+    # environment traces: reset then every expand op on several id slices, then commit
+    for qi in env_queries:
+        env = rs.make_env()
+        trace = []
+        obs, info = env.reset(seed_query=queries[qi], top_k=env_top_k)
+        info = {k: v for k, v in info.items() if k != "time_s"}
+        trace.append({"call": "reset", "args": {"query": qi, "top_k": env_top_k}, "obs": obs, "info": info})
+        ids = [n["node_id"] for n in obs["selection"]]
+        for op in ("expand_parents", "expand_children", "expand_related"):
+            for sl in (ids[:1], ids[:2], ids[1:4], ids, ["not-a-node"] + ids[:1]):
+                for limit in (10, 3):
+                    o, i = getattr(env, op)(list(sl), limit=limit)
+                    trace.append({"call": op, "args": {"node_ids": list(sl), "limit": limit}, "obs": o, "info": i})
+        o, i = env.commit_selection(ids[:3])
+        trace.append({"call": "commit_selection", "args": {"node_ids": ids[:3]}, "obs": o, "info": i})
+        o, i = env.expand_related(ids[:2])
+        trace.append({"call": "expand_related", "args": {"node_ids": ids[:2], "limit": 10}, "obs": o, "info": i})
+        fixture["env"].append(trace)
+    # expand_to_lca (environment.py:243-299): summaries, entities, mixed sets, a node without belongs_to edges
+    lenv = rs.make_env()
+    G = rs.hg.G
+    by_type = {t: [n for n, d in G.nodes(data=True) if d.get("node_type") == t] for t in ("entity", "summary", "hyperedge")}
+    ents, sums = by_type["entity"], by_type["summary"]
+    parent_of = lambda n: [v for _, v, d in G.out_edges(n, data=True) if d.get("edge_type") == "belongs_to"]
+    cases = [[s_] for s_ in sums[:3]] + [sums[:2], sums[-2:], ents[:1], ents[:2], [ents[0]] + parent_of(ents[0])[:1],
+                                         parent_of(ents[1])[:1] + [ents[1]], [], by_type["hyperedge"][:1], ["not-a-node"]]
+    lrng = np.random.default_rng(len(G))
+    hier = [n for n in G if any(d.get("edge_type") == "belongs_to" for _, _, d in G.out_edges(n, data=True)) or
+            any(d.get("edge_type") == "belongs_to" for _, _, d in G.in_edges(n, data=True))]
+    for t in range(24):  # random sets: summaries only (odd t) or any node of the hierarchy
+        pool = sums if (t % 2 and sums) else hier
+        cases.append([pool[int(i)] for i in lrng.integers(len(pool), size=int(lrng.integers(1, 4)))])
+    for ids in cases:
+        for mr in (5, 1):
+            try:
+                o, i = lenv.expand_to_lca(list(ids), max_results=mr)
+                i = {k: v for k, v in i.items() if k != "time_s"}
+                fixture["lca"].append({"node_ids": list(ids), "max_results": mr, "obs": o, "info": i})
+            except Exception as e:  # nx.ancestors on a node outside the belongs_to subgraph
+                fixture["lca"].append({"node_ids": list(ids), "max_results": mr, "raises": type(e).__name__})
+    for si, seq in enumerate(GYM_ACTION_SEQS):
+        gym = rs.make_gym(max_steps=6)
+        qi = si % len(queries)
+        vec, info = gym.reset(queries[qi])
+        steps = [{"vec": [float(x) for x in vec], "mask": info.get("action_mask")}]
+        for a in seq:
+            v, r, d, inf = gym.step(a)
+            steps.append({"action": a, "vec": [float(x) for x in v], "reward": r, "done": d,
+                          "mask": inf.get("action_mask")})
+            if d:
+                break
+        fixture["gym"].append({"query": qi, "steps": steps})
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    with open(os.path.join(GOLDEN_DIR, name + ".json"), "w", encoding="utf-8") as f:
+        json.dump(fixture, f, ensure_ascii=False)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"),
+                        index_rows=rs.index_rows.astype(np.float32), query_vecs=qvecs.astype(np.float32))
+    print(name, "nodes", rs.hg.G.number_of_nodes(), "edges", rs.hg.G.number_of_edges(),
+          "index", len(rs.index_ids), "search cases", len(fixture["search"]))
+    return rs
+
+
 def main() -> None:
     assert ref_runner.reference_available(), "needs /root/reference"
     HG_cls = stubs.import_reference(ref_runner.REF_ROOT)[0]
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     for spec in GRAPHS:
-        stubs.reset_store()
-        g = synth.make_graph(**spec["kw"])
-        rs = ref_runner.ReferenceSession(g)
-        queries = [f"golden query {i}" for i in range(6)]
-        qvecs = np.stack([stubs.hash_embed(q) for q in queries])
-        fixture = {"name": spec["name"], "make_graph_kwargs": spec["kw"], "node_link": g,
-                   "index_ids": rs.index_ids, "queries": queries, "search": [], "env": [], "gym": [], "lca": []}
-        for qi, q in enumerate(queries):
-            for case in SEARCH_CASES:
-                out = ref_runner.strip_search(rs.search(q, **case))
-                fixture["search"].append({"query": qi, "kwargs": case, "out": out})
-        # environment traces: reset then every expand op on several id slices, then commit
-        for qi in (0, 3):
-            env = rs.make_env()
-            trace = []
-            obs, info = env.reset(seed_query=queries[qi], top_k=5)
-            info = {k: v for k, v in info.items() if k != "time_s"}
-            trace.append({"call": "reset", "args": {"query": qi, "top_k": 5}, "obs": obs, "info": info})
-            ids = [n["node_id"] for n in obs["selection"]]
-            for op in ("expand_parents", "expand_children", "expand_related"):
-                for sl in (ids[:1], ids[:2], ids[1:4], ids, ["not-a-node"] + ids[:1]):
-                    for limit in (10, 3):
-                        o, i = getattr(env, op)(list(sl), limit=limit)
-                        trace.append({"call": op, "args": {"node_ids": list(sl), "limit": limit}, "obs": o, "info": i})
-            o, i = env.commit_selection(ids[:3])
-            trace.append({"call": "commit_selection", "args": {"node_ids": ids[:3]}, "obs": o, "info": i})
-            o, i = env.expand_related(ids[:2])
-            trace.append({"call": "expand_related", "args": {"node_ids": ids[:2], "limit": 10}, "obs": o, "info": i})
-            fixture["env"].append(trace)
-        # expand_to_lca (environment.py:243-299): summaries, entities, mixed sets, a node without belongs_to edges
-        lenv = rs.make_env()
-        G = rs.hg.G
-        by_type = {t: [n for n, d in G.nodes(data=True) if d.get("node_type") == t] for t in ("entity", "summary", "hyperedge")}
-        ents, sums = by_type["entity"], by_type["summary"]
-        parent_of = lambda n: [v for _, v, d in G.out_edges(n, data=True) if d.get("edge_type") == "belongs_to"]
-        cases = [[s_] for s_ in sums[:3]] + [sums[:2], sums[-2:], ents[:1], ents[:2], [ents[0]] + parent_of(ents[0])[:1],
-                                             parent_of(ents[1])[:1] + [ents[1]], [], by_type["hyperedge"][:1], ["not-a-node"]]
-        lrng = np.random.default_rng(len(G))
-        hier = [n for n in G if any(d.get("edge_type") == "belongs_to" for _, _, d in G.out_edges(n, data=True)) or
-                any(d.get("edge_type") == "belongs_to" for _, _, d in G.in_edges(n, data=True))]
-        for t in range(24):  # random sets: summaries only (odd t) or any node of the hierarchy
-            pool = sums if (t % 2 and sums) else hier
-            cases.append([pool[int(i)] for i in lrng.integers(len(pool), size=int(lrng.integers(1, 4)))])
-        for ids in cases:
-            for mr in (5, 1):
-                try:
-                    o, i = lenv.expand_to_lca(list(ids), max_results=mr)
-                    i = {k: v for k, v in i.items() if k != "time_s"}
-                    fixture["lca"].append({"node_ids": list(ids), "max_results": mr, "obs": o, "info": i})
-                except Exception as e:  # nx.ancestors on a node outside the belongs_to subgraph
-                    fixture["lca"].append({"node_ids": list(ids), "max_results": mr, "raises": type(e).__name__})
-        for si, seq in enumerate(GYM_ACTION_SEQS):
-            gym = rs.make_gym(max_steps=6)
-            qi = si % len(queries)
-            vec, info = gym.reset(queries[qi])
-            steps = [{"vec": [float(x) for x in vec], "mask": info.get("action_mask")}]
-            for a in seq:
-                v, r, d, inf = gym.step(a)
-                steps.append({"action": a, "vec": [float(x) for x in v], "reward": r, "done": d,
-                              "mask": inf.get("action_mask")})
-                if d:
-                    break
-            fixture["gym"].append({"query": qi, "steps": steps})
-        with open(os.path.join(GOLDEN_DIR, spec["name"] + ".json"), "w", encoding="utf-8") as f:
-            json.dump(fixture, f, ensure_ascii=False)
-        np.savez_compressed(os.path.join(GOLDEN_DIR, spec["name"] + ".npz"),
-                            index_rows=rs.index_rows.astype(np.float32), query_vecs=qvecs.astype(np.float32))
-        print(spec["name"], "nodes", rs.hg.G.number_of_nodes(), "edges", rs.hg.G.number_of_edges(),
-              "index", len(rs.index_ids), "search cases", len(fixture["search"]))
+        rs = write_fixture(spec["name"], synth.make_graph(**spec["kw"]), [f"golden query {i}" for i in range(6)],
+                           SEARCH_CASES, extra={"make_graph_kwargs": spec["kw"]})
 
     # generate_l1_relations (semantic_aggregator.py:594-680): inputs + the reference's edges and neighbour lists
     import copy

@@ -32,6 +32,17 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["value"] == d["value"] and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the line is self-consistent: ms_per_step is the time of one full 4096-query step at the measured rate
+    assert abs(d["ms_per_step"] * d["value"] / 1000.0 - 4096) < 1e-6 * 4096
+
+
+@pytest.mark.timeout(120)
+def test_reference_arm_uses_all_host_threads_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use every host core it may run on."""
+    p = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"], {"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2"})
+    assert p.returncode == 0, p.stderr[-500:]
+    d = json.loads(p.stdout.strip())
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
 
 
 @pytest.mark.timeout(120)

@@ -95,6 +95,14 @@ def test_c_and_numpy_exact_scorers_agree_bitwise(dtype):
     assert np.array_equal(mi, i2) and np.array_equal(ms.view(np.uint32), s2.view(np.uint32))
     r = exact.rescore(X, Q, i2)
     assert np.array_equal(r.view(np.uint32), s2.view(np.uint32))
+    # row-parallel scan (bench.py's sampled parity check over the full corpus) == the per-query scan
+    big = np.concatenate([X] * 12)  # 9324 rows: several 4096-row blocks, duplicates across blocks -> id tie-breaks
+    for nt in (1, 3, 8):
+        s4, i4 = exact.exact_topk_rowpar(big, Q, 20, id_base=7, n_threads=nt)
+        s5, i5 = exact.exact_topk(big, Q, 20, id_base=7)
+        assert np.array_equal(i4, i5) and np.array_equal(s4.view(np.uint32), s5.view(np.uint32))
+    s6, i6 = exact.exact_topk_rowpar(X[:5], Q, 8, n_threads=4)
+    assert np.array_equal(i6, i3) and np.array_equal(s6.view(np.uint32), s3.view(np.uint32))
 
 
 def test_round4_matches_cpython():
@@ -150,3 +158,36 @@ def test_array_oracle_equals_networkx_oracle(name):
         lim = int(rng.choice([3, 10, 100]))
         want = ref_search.expand(og, ["parents", "children", "related"][t % 3], [nodes[i] for i in ids], lim)
         assert [nodes[i] for i in array_graph.expand(a, t % 3, ids, lim)] == want
+
+
+def test_cpu_graph_baseline_loops_agree():
+    """bench.py's graph-half CPU baseline: the NetworkX form rebuilt from CSR arrays gives the array form's answers
+    (same environments, same hops), so the two baseline numbers time the same work."""
+    from ah_rag_b200 import csr
+    from oracle import array_graph, cpu_graph_baseline
+    fx = gu.load("g_small_s3")
+    og = ref_search.OracleGraph(copy.deepcopy(fx["node_link"]))
+    a = csr.csr_from_networkx(og.G)
+    og2 = cpu_graph_baseline.networkx_graph(a)
+    assert og2.G.number_of_nodes() == og.G.number_of_nodes() and og2.G.number_of_edges() == og.G.number_of_edges()
+    # in-edge order of a DiGraph is global insertion order: re-export so both forms walk the SAME adjacency order (the
+    # bench graphs are generated source-major, where the conversion is order-exact)
+    a = csr.csr_from_networkx(og2.G)
+    assert a["node_ids"] == [str(i) for i in range(len(a["node_ids"]))]
+    rng = np.random.default_rng(9)
+    prm = ref_search.resolve_params(og2, member_top_m=5)
+    n = len(a["node_ids"])
+    for t in range(30):
+        sn = rng.permutation(n)[:8]
+        ss = np.sort(rng.uniform(0.1, 0.9, 8).astype(np.float32))[::-1]
+        want = array_graph.anchor_rerank(a, sn, ss, 8, 5)
+        got = ref_search.anchor_rerank(og2, ref_search.seeds_from_topk([str(int(v)) for v in sn], ss), 8, prm)["reranked"]
+        assert [(int(r["node_id"]), r["semantic"], r["score"]) for r in got] == want
+        ids = [int(i) for i in rng.integers(0, n, size=2)]
+        assert [int(x) for x in ref_search.expand(og2, ["parents", "children", "related"][t % 3], [str(i) for i in ids], 10)] == \
+            array_graph.expand(a, t % 3, ids, 10)
+    seeds = np.stack([rng.permutation(n)[:8] for _ in range(4)])
+    scores = np.sort(rng.uniform(0.1, 0.9, (4, 8)).astype(np.float32), axis=1)[:, ::-1]
+    r1 = cpu_graph_baseline.array_loop(a, seeds, scores, [0, 1, 2, 0], 8, 5, 10, 5.0)
+    r2 = cpu_graph_baseline.networkx_loop(a, seeds, scores, [0, 1, 2, 0], 8, 5, 10, 5.0)
+    assert r1["envs"] == 4 and r2["envs"] == 4 and r1["envs_per_s"] > 0 and r2["envs_per_s"] > 0
