@@ -24,7 +24,7 @@ AHR_IPC_HANDLE_BYTES = 64
 
 EXPORTS = [
     "ahr_last_error", "ahr_version", "ahr_launch_count", "ahr_index_create", "ahr_index_destroy", "ahr_topk",
-    "ahr_topk_host", "ahr_merge_topk", "ahr_merge_topk_packed", "ahr_graph_create", "ahr_graph_destroy", "ahr_anchor_rerank", "ahr_expand",
+    "ahr_topk_host", "ahr_merge_topk", "ahr_merge_topk_packed", "ahr_graph_create", "ahr_graph_destroy", "ahr_anchor_rerank", "ahr_anchor_rerank_rows", "ahr_expand",
     "ahr_debug_tc_scores", "ahr_rescore", "ahr_debug_round4", "ahr_exact_stats", "ahr_set_profiling",
     "ahr_get_profile", "ahr_env_reset", "ahr_env_step", "ahr_comm_create", "ahr_comm_export", "ahr_comm_connect",
     "ahr_comm_destroy", "ahr_comm_begin", "ahr_comm_exchange_merge", "ahr_lca_closure",
@@ -66,6 +66,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.ahr_graph_destroy.argtypes = [vp]
     lib.ahr_anchor_rerank.argtypes = [vp, c_int32, c_int32, vp, vp, POINTER(RerankParams), c_int32,
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ahr_anchor_rerank_rows.argtypes = [vp, c_int32, c_int32, vp, vp, c_int64, vp, POINTER(RerankParams), c_int32,
+                                           vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.ahr_expand.argtypes = [vp, c_int32, vp, vp, vp, c_int32, vp, vp, vp]
     lib.ahr_debug_tc_scores.argtypes = [vp, vp, c_int32, vp, vp]
     lib.ahr_rescore.argtypes = [vp, vp, c_int32, c_int32, vp, vp, vp]

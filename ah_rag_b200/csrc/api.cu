@@ -64,6 +64,7 @@ struct ahr_index {
   int seed_stride = 0;   // AHR_TC_SEED_STRIDE: sample pass over every n-th corpus tile seeds the thresholds.  Off by
                          // default: exact and tested, but since the v5 epilogue it buys nothing measurable (history file)
   int force_slabs = 0;     // AHR_TC_SLABS: override the slab heuristic (experiments)
+  bool shared_bound = true;  // AHR_TC_SHARED_BOUND=0 switches the cross-slab admission bound off (A/B runs)
   DevBuf x_hi, x_lo;   // fp32 index: bf16 hi/lo halves of the rows (library-owned), maps below point at them
   CUtensorMap map_x2_lo;
   DevBuf q_split;      // fp32 queries split per call
@@ -83,7 +84,7 @@ struct ahr_graph {
   int device = 0;
   GraphView view;
   DevBuf ws;
-  DevBuf recs;  // packed node attributes (one 32-byte record per node)
+  DevBuf recs;  // packed node lines (one 64-byte NodeLine per node)
 };
 
 extern "C" {
@@ -140,6 +141,7 @@ int ahr_index_create(ahr_index **out, int device, int64_t n_rows, int32_t dim, i
   if (const char *e = getenv("AHR_TC_SEED_STRIDE")) idx->seed_stride = std::max(0, atoi(e));
   if (const char *e = getenv("AHR_TC_SLABS")) idx->force_slabs = std::max(0, atoi(e));
   if (const char *e = getenv("AHR_TC_STATS")) idx->tc_stats = atoi(e) != 0;
+  if (const char *e = getenv("AHR_TC_SHARED_BOUND")) idx->shared_bound = atoi(e) != 0;
   cudaError_t e = cudaMalloc(&idx->d_max_norm, sizeof(float));
   if (e != cudaSuccess) { delete idx; set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return AHR_E_NOMEM; }
   int rc = row_norms_max(dev_rows, dtype, n_rows, dim, idx->d_max_norm, 0);
@@ -231,7 +233,7 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
   const size_t o_ps = carve(n_part * 4), o_pi = carve(n_part * 4), o_ss = carve(n_spart * 4), o_si = carve(n_spart * 4),
-               o_ts = carve((size_t)nq * k * 4), o_ti = carve((size_t)nq * k * 8);
+               o_ts = carve((size_t)nq * k * 4), o_ti = carve((size_t)nq * k * 8), o_tb = carve((size_t)nq_pad * 4 * std::max(S, Ss));
   int rc = idx->ws.reserve(off);
   if (rc != AHR_OK) return rc;
   uint8_t *w = reinterpret_cast<uint8_t *>(idx->ws.ptr);
@@ -260,12 +262,18 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
   };
   TcExtra ex;
   ex.q_rows = nq_pad;
+  if (idx->shared_bound && !dbg_scores) {
+    // what every slab publishes for every query (tc_shared.cuh, "shared bound"): 0 = nothing published yet
+    ex.thr_shared = reinterpret_cast<uint32_t *>(w + o_tb);
+    AHR_CUDA_CHECK(cudaMemsetAsync(ex.thr_shared, 0, (size_t)nq_pad * 4 * S, st));
+  }
   if (stride > 1) {
     float *ss = reinterpret_cast<float *>(w + o_ss), *ts = reinterpret_cast<float *>(w + o_ts);
     int32_t *si = reinterpret_cast<int32_t *>(w + o_si);
     int64_t *ti = reinterpret_cast<int64_t *>(w + o_ti);
     TcExtra exs = ex;
     exs.tile_stride = stride;
+    exs.thr_shared = nullptr;  // the sample pass is short and keeps plain lists
     rc = launch(Ss, ss, si, exs, nullptr);
     if (rc != AHR_OK) return rc;
     rc = select_topk(ss, si, nullptr, (int64_t)Ss * k, (int64_t)Ss * k, nq, k, 0, false, ts, ti, st);
@@ -550,19 +558,20 @@ int ahr_graph_create(ahr_graph **out, int device, int64_t n_nodes, const int64_t
     g->view.row_ptr[s] = dev_row_ptr[s];
     g->view.col_idx[s] = dev_col_idx[s];
   }
-  g->view.rec = nullptr;
+  g->view.line = nullptr;
   if (n_nodes > 0) {
-    // pack the five attribute arrays into one 32-byte record per node (the caller's arrays are not referenced afterwards)
-    int rc = g->recs.reserve((size_t)n_nodes * sizeof(NodeRec));
+    // pack the five attribute arrays + the head of each node's anchor list into one 64-byte line per node (the caller's
+    // attribute arrays are not referenced afterwards)
+    int rc = g->recs.reserve((size_t)n_nodes * sizeof(NodeLine));
     if (rc == AHR_OK)
-      rc = graph_pack_nodes(n_nodes, dev_node_type, dev_level, dev_judge, dev_judge_term, dev_conf,
-                            reinterpret_cast<NodeRec *>(g->recs.ptr), 0);
+      rc = graph_pack_nodes(n_nodes, dev_node_type, dev_level, dev_judge, dev_judge_term, dev_conf, dev_row_ptr, dev_col_idx,
+                            reinterpret_cast<NodeLine *>(g->recs.ptr), 0);
     if (rc == AHR_OK && cudaStreamSynchronize(0) != cudaSuccess) {
       set_error("ahr_graph_create: packing the node attributes failed: %s", cudaGetErrorString(cudaGetLastError()));
       rc = AHR_E_CUDA;
     }
     if (rc != AHR_OK) { g->recs.release(); delete g; return rc; }
-    g->view.rec = reinterpret_cast<const NodeRec *>(g->recs.ptr);
+    g->view.line = reinterpret_cast<const NodeLine *>(g->recs.ptr);
   }
   *out = g;
   return AHR_OK;
@@ -577,14 +586,15 @@ int ahr_graph_destroy(ahr_graph *g) {
   return AHR_OK;
 }
 
-int ahr_anchor_rerank(ahr_graph *g, int32_t nq, int32_t n_seeds, const int32_t *dev_seed_nodes,
-                      const float *dev_seed_scores, const ahr_rerank_params *params, int32_t top_k,
-                      int32_t *dev_out_nodes, double *dev_out_semantic, double *dev_out_score, int32_t *dev_out_count,
-                      int32_t *dev_exp_nodes, double *dev_exp_semantic, uint8_t *dev_exp_kind, int32_t *dev_exp_count,
-                      double *dev_seed_semantic, void *stream) {
+static int anchor_rerank_common(ahr_graph *g, int32_t nq, int32_t n_seeds, const int32_t *dev_seed_nodes,
+                                const int64_t *dev_seed_rows, const int32_t *dev_row_to_node, int64_t n_rows,
+                                const float *dev_seed_scores, const ahr_rerank_params *params, int32_t top_k,
+                                int32_t *dev_out_nodes, double *dev_out_semantic, double *dev_out_score,
+                                int32_t *dev_out_count, int32_t *dev_exp_nodes, double *dev_exp_semantic,
+                                uint8_t *dev_exp_kind, int32_t *dev_exp_count, double *dev_seed_semantic, void *stream) {
   AHR_REQUIRE(g && params, "ahr_anchor_rerank: NULL handle or params");
   if (nq == 0) return AHR_OK;
-  AHR_REQUIRE(dev_seed_nodes && dev_seed_scores && dev_out_nodes && dev_out_semantic && dev_out_score && dev_out_count,
+  AHR_REQUIRE(dev_seed_scores && dev_out_nodes && dev_out_semantic && dev_out_score && dev_out_count,
               "ahr_anchor_rerank: NULL buffer");
   AHR_REQUIRE(!dev_exp_nodes || dev_exp_semantic, "ahr_anchor_rerank: exp_nodes needs exp_semantic");
   DeviceGuard guard(g->device);
@@ -593,10 +603,33 @@ int ahr_anchor_rerank(ahr_graph *g, int32_t nq, int32_t n_seeds, const int32_t *
     int rc = g->ws.reserve(need);
     if (rc != AHR_OK) return rc;
   }
-  return graph_anchor_rerank(g->view, nq, n_seeds, dev_seed_nodes, dev_seed_scores, *params, top_k, dev_out_nodes,
-                             dev_out_semantic, dev_out_score, dev_out_count, dev_exp_nodes, dev_exp_semantic,
-                             dev_exp_kind, dev_exp_count, dev_seed_semantic, g->ws.ptr, g->ws.bytes,
+  return graph_anchor_rerank(g->view, nq, n_seeds, dev_seed_nodes, dev_seed_rows, dev_row_to_node, n_rows, dev_seed_scores,
+                             *params, top_k, dev_out_nodes, dev_out_semantic, dev_out_score, dev_out_count, dev_exp_nodes,
+                             dev_exp_semantic, dev_exp_kind, dev_exp_count, dev_seed_semantic, g->ws.ptr, g->ws.bytes,
                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ahr_anchor_rerank(ahr_graph *g, int32_t nq, int32_t n_seeds, const int32_t *dev_seed_nodes,
+                      const float *dev_seed_scores, const ahr_rerank_params *params, int32_t top_k,
+                      int32_t *dev_out_nodes, double *dev_out_semantic, double *dev_out_score, int32_t *dev_out_count,
+                      int32_t *dev_exp_nodes, double *dev_exp_semantic, uint8_t *dev_exp_kind, int32_t *dev_exp_count,
+                      double *dev_seed_semantic, void *stream) {
+  AHR_REQUIRE(nq == 0 || dev_seed_nodes, "ahr_anchor_rerank: NULL seed list");
+  return anchor_rerank_common(g, nq, n_seeds, dev_seed_nodes, nullptr, nullptr, 0, dev_seed_scores, params, top_k,
+                              dev_out_nodes, dev_out_semantic, dev_out_score, dev_out_count, dev_exp_nodes, dev_exp_semantic,
+                              dev_exp_kind, dev_exp_count, dev_seed_semantic, stream);
+}
+
+int ahr_anchor_rerank_rows(ahr_graph *g, int32_t nq, int32_t n_seeds, const int64_t *dev_seed_rows,
+                           const int32_t *dev_row_to_node, int64_t n_rows, const float *dev_seed_scores,
+                           const ahr_rerank_params *params, int32_t top_k, int32_t *dev_out_nodes,
+                           double *dev_out_semantic, double *dev_out_score, int32_t *dev_out_count, int32_t *dev_exp_nodes,
+                           double *dev_exp_semantic, uint8_t *dev_exp_kind, int32_t *dev_exp_count,
+                           double *dev_seed_semantic, void *stream) {
+  AHR_REQUIRE(nq == 0 || (dev_seed_rows && dev_row_to_node && n_rows >= 0), "ahr_anchor_rerank_rows: NULL seed rows / table");
+  return anchor_rerank_common(g, nq, n_seeds, nullptr, dev_seed_rows, dev_row_to_node, n_rows, dev_seed_scores, params, top_k,
+                              dev_out_nodes, dev_out_semantic, dev_out_score, dev_out_count, dev_exp_nodes, dev_exp_semantic,
+                              dev_exp_kind, dev_exp_count, dev_seed_semantic, stream);
 }
 
 int ahr_expand(ahr_graph *g, int32_t n_env, const int32_t *dev_ops, const int32_t *dev_in_ids,

@@ -59,7 +59,7 @@ __device__ __forceinline__ void env_featurize(const EnvView &e, const GraphView 
     float *o = f + 4 + j * 8;
     if (j < shown) {
       const int32_t v = e.shown_ids[env * ENV_SHOWN + j];
-      const NodeRec rec = g.rec[v];  // one sector per shown node
+      const NodeHead rec = g.line[v].head;  // one sector per shown node
       const uint8_t t = rec.type;
       const uint8_t lv = rec.level;
       const double judge = rec.judge, conf = rec.conf;

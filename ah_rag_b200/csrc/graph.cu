@@ -38,20 +38,32 @@ __global__ void round4_kernel(const double *__restrict__ x, int64_t n, double *_
 
 __global__ void pack_nodes_kernel(int64_t n, const uint8_t *__restrict__ node_type, const uint8_t *__restrict__ level,
                                   const double *__restrict__ judge, const double *__restrict__ judge_term,
-                                  const double *__restrict__ conf, NodeRec *__restrict__ out) {
+                                  const double *__restrict__ conf, const int64_t *__restrict__ rp_bel_out,
+                                  const int32_t *__restrict__ ci_bel_out, const int64_t *__restrict__ rp_bel_in,
+                                  const int32_t *__restrict__ ci_bel_in, NodeLine *__restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  NodeRec r;
-  r.judge = judge[i]; r.judge_term = judge_term[i]; r.conf = conf[i];
-  r.type = node_type[i]; r.level = level[i];
-  for (int j = 0; j < 6; ++j) r.pad[j] = 0;
+  NodeLine r;
+  r.head.judge = judge[i]; r.head.judge_term = judge_term[i]; r.head.conf = conf[i];
+  r.head.type = node_type[i]; r.head.level = level[i];
+  r.head.pad[0] = r.head.pad[1] = 0;
+  // anchor list: what a seed of this type expands into (hierarchical_graph.py:733-740)
+  const int64_t *rp = r.head.type == AHR_NT_ENTITY ? rp_bel_out : (r.head.type == AHR_NT_SUMMARY ? rp_bel_in : nullptr);
+  const int32_t *ci = r.head.type == AHR_NT_ENTITY ? ci_bel_out : ci_bel_in;
+  int64_t p0 = 0, deg = 0;
+  if (rp != nullptr) { p0 = rp[i]; deg = rp[i + 1] - p0; }
+  r.head.anchor_deg = (int32_t)(deg > INT32_MAX ? INT32_MAX : deg);
+  for (int j = 0; j < NODE_ANCHOR_INLINE; ++j) r.anchor[j] = j < deg ? ci[p0 + j] : -1;
   out[i] = r;
 }
 
 int graph_pack_nodes(int64_t n_nodes, const uint8_t *node_type, const uint8_t *level, const double *judge,
-                     const double *judge_term, const double *conf, NodeRec *out, cudaStream_t stream) {
+                     const double *judge_term, const double *conf, const int64_t *const row_ptr[AHR_N_CSR],
+                     const int32_t *const col_idx[AHR_N_CSR], NodeLine *out, cudaStream_t stream) {
   if (n_nodes <= 0) return AHR_OK;
-  pack_nodes_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, stream>>>(n_nodes, node_type, level, judge, judge_term, conf, out);
+  pack_nodes_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, stream>>>(
+      n_nodes, node_type, level, judge, judge_term, conf, row_ptr[AHR_CSR_BEL_OUT], col_idx[AHR_CSR_BEL_OUT],
+      row_ptr[AHR_CSR_BEL_IN], col_idx[AHR_CSR_BEL_IN], out);
   AHR_KERNEL_CHECK();
   return AHR_OK;
 }
@@ -74,8 +86,12 @@ enum : uint8_t { EK_ABSENT = 0, EK_SEED = AHR_EK_SEED, EK_PARENT = AHR_EK_PARENT
 struct AnchorArgs {
   GraphView g;
   int32_t nq, n_seeds, top_k, fan, cap;  // fan = max(parent_cap, member_top_m); cap = n_seeds * (1 + fan)
+  int32_t hsize;                         // hash slots of the large-map variant (power of two >= 2 * cap)
   ahr_rerank_params prm;
-  const int32_t *seed_nodes;
+  const int32_t *seed_nodes;             // dense node ids, or
+  const int64_t *seed_rows;              // index rows as ahr_topk returns them (id_base = 0) + the row -> node table
+  const int32_t *row_to_node;
+  int64_t n_rows;
   const float *seed_scores;
   int32_t *out_nodes;
   double *out_sem;
@@ -86,170 +102,13 @@ struct AnchorArgs {
   uint8_t *exp_kind;
   int32_t *exp_count;
   double *seed_sem;
-  uint8_t *workspace;  // per query: cap * (4 + 8 + 8 + 1 + 1) bytes when cap > AR_SMEM_CAP
+  uint8_t *workspace;  // per query anchor_ws_per_query(cap, hsize) bytes when cap > AR_SMEM_CAP
 };
 
-__host__ __device__ inline size_t anchor_ws_per_query(int cap) { return ((size_t)cap * 22 + 15) & ~(size_t)15; }
-
-// General version: any capacity (the expanded map lives in the global workspace when it outgrows shared memory).
-__global__ void __launch_bounds__(AR_THREADS) anchor_rerank_big_kernel(AnchorArgs a) {
-  __shared__ double sm_sem[AR_SMEM_CAP];
-  __shared__ double sm_rs[AR_SMEM_CAP];
-  __shared__ int32_t sm_node[AR_SMEM_CAP];
-  __shared__ uint8_t sm_kind[AR_SMEM_CAP];
-  __shared__ uint8_t sm_flag[AR_SMEM_CAP];
-  __shared__ int sm_counts[2];
-
-  const int q = blockIdx.x;
-  const int cap = a.cap, fan = a.fan, per = 1 + fan;
-  double *e_sem, *e_rs;
-  int32_t *e_node;
-  uint8_t *e_kind, *e_flag;  // flag: bit0 = first occurrence, bit1 = passes filters
-  if (cap <= AR_SMEM_CAP) {
-    e_sem = sm_sem; e_rs = sm_rs; e_node = sm_node; e_kind = sm_kind; e_flag = sm_flag;
-  } else {
-    uint8_t *w = a.workspace + (size_t)q * anchor_ws_per_query(cap);
-    e_sem = reinterpret_cast<double *>(w);
-    e_rs = e_sem + cap;
-    e_node = reinterpret_cast<int32_t *>(e_rs + cap);
-    e_kind = reinterpret_cast<uint8_t *>(e_node + cap);
-    e_flag = e_kind + cap;
-  }
-  const GraphView &g = a.g;
-  const int32_t *seeds = a.seed_nodes + (int64_t)q * a.n_seeds;
-  const float *sscore = a.seed_scores + (int64_t)q * a.n_seeds;
-
-  // ---- A. generate the candidate list in reference order: seed r, then its expansions ----
-  for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
-    const int r = e / per, j = e % per;
-    int32_t v = seeds[r];
-    if (v >= g.n_nodes) v = -1;
-    int32_t node = -1;
-    double sem = 0.0;
-    uint8_t kind = EK_ABSENT;
-    if (v >= 0) {
-      // hnswlib's cosine space reports dist = 1.0f - <q,x> (fp32); the reference then takes
-      // semantic = 1.0 - float(dist) in fp64 (hierarchical_graph.py:723)
-      const double sem_r = 1.0 - (double)__fsub_rn(1.0f, sscore[r]);
-      if (j == 0) {
-        node = v; sem = sem_r; kind = EK_SEED;
-        if (a.seed_sem) a.seed_sem[(int64_t)q * a.n_seeds + r] = sem_r;
-      } else {
-        const uint8_t t = g.rec[v].type;
-        if (t == AHR_NT_ENTITY && j - 1 < a.prm.parent_cap) {  // first 2 out-belongs_to parents, x0.9 (:733-736)
-          const int64_t p0 = g.row_ptr[AHR_CSR_BEL_OUT][v], p1 = g.row_ptr[AHR_CSR_BEL_OUT][v + 1];
-          if (p0 + (j - 1) < p1) {
-            node = g.col_idx[AHR_CSR_BEL_OUT][p0 + (j - 1)];
-            sem = __dmul_rn(sem_r, 0.9);
-            kind = EK_PARENT;
-          }
-        } else if (t == AHR_NT_SUMMARY && j - 1 < a.prm.member_top_m) {  // first m in-belongs_to members, x0.85 (:737-740)
-          const int64_t p0 = g.row_ptr[AHR_CSR_BEL_IN][v], p1 = g.row_ptr[AHR_CSR_BEL_IN][v + 1];
-          if (p0 + (j - 1) < p1) {
-            node = g.col_idx[AHR_CSR_BEL_IN][p0 + (j - 1)];
-            sem = __dmul_rn(sem_r, 0.85);
-            kind = EK_MEMBER;
-          }
-        }
-      }
-    } else if (j == 0 && a.seed_sem) {
-      a.seed_sem[(int64_t)q * a.n_seeds + r] = 0.0;
-    }
-    e_node[e] = node; e_sem[e] = sem; e_kind[e] = kind; e_flag[e] = 0;
-  }
-  if (threadIdx.x < 2) sm_counts[threadIdx.x] = 0;
-  __syncthreads();
-
-  // ---- B. first-writer-wins dedup; a seed always owns the value of its node (:732) ----
-  for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
-    const int32_t node = e_node[e];
-    if (node < 0) continue;
-    bool first = true;
-    for (int t = 0; t < e; ++t)
-      if (e_node[t] == node) { first = false; break; }
-    if (!first) continue;
-    // the LAST seed entry carrying this node overwrites the value (dict assignment), position stays
-    int seed_e = -1;
-    for (int t = 0; t < cap; t += per)
-      if (e_node[t] == node) seed_e = t;
-    e_flag[e] = 1 | (seed_e >= 0 ? 4 : 0);
-    if (seed_e >= 0) e_rs[e] = e_sem[seed_e]; else e_rs[e] = e_sem[e];
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < cap; e += AR_THREADS)
-    if (e_flag[e] & 1) {
-      e_sem[e] = e_rs[e];
-      if (e_flag[e] & 4) e_kind[e] = EK_SEED;
-    }
-  __syncthreads();
-
-  // ---- expanded map in insertion order (return_cluster=True) ----
-  if (a.exp_nodes) {
-    for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
-      if (!(e_flag[e] & 1)) continue;
-      int pos = 0;
-      for (int t = 0; t < e; ++t) pos += e_flag[t] & 1;
-      a.exp_nodes[(int64_t)q * cap + pos] = e_node[e];
-      a.exp_sem[(int64_t)q * cap + pos] = e_sem[e];
-      if (a.exp_kind) a.exp_kind[(int64_t)q * cap + pos] = e_kind[e];
-      atomicAdd(&sm_counts[0], 1);
-    }
-  }
-
-  // ---- C. filters + linear rerank in fp64, same operation order as :764-768, no FMA contraction ----
-  const ahr_rerank_params &P = a.prm;
-  for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
-    if (!(e_flag[e] & 1)) continue;
-    const int32_t node = e_node[e];
-    const NodeRec rec = g.rec[node];  // one sector: type, judge, judge_term, conf
-    const uint8_t t = rec.type;
-    const double judge = rec.judge, conf = rec.conf;
-    const bool has_j = judge == judge, has_c = conf == conf;  // NaN encodes None
-    bool ok = true;
-    if (P.type_mask != 0 && !((P.type_mask >> t) & 1)) ok = false;                       // :756-757
-    if (P.has_judge_min && (!has_j || judge < P.judge_min)) ok = false;                  // :759-760
-    if (P.has_conf_min && (!has_c || conf < P.conf_min)) ok = false;                     // :761-762
-    if (!ok) continue;
-    const double jt = has_j ? rec.judge_term : 0.0;
-    const double ct = has_c ? __ddiv_rn(conf, 10.0) : 0.0;
-    double score = __dmul_rn(P.alpha, e_sem[e]);
-    score = __dadd_rn(score, __dmul_rn(P.beta, jt));
-    score = __dadd_rn(score, __dmul_rn(P.gamma, ct));
-    score = __dadd_rn(score, __dmul_rn(P.delta, P.boost[t & 3]));
-    e_rs[e] = round4_py(score);
-    e_flag[e] |= 2;
-  }
-  __syncthreads();
-
-  // ---- D. stable descending sort on the ROUNDED score (:781), keep top_k ----
-  for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
-    if (!(e_flag[e] & 2)) continue;
-    const double rs = e_rs[e];
-    int rank = 0;
-    for (int t = 0; t < cap; ++t) {
-      if (!(e_flag[t] & 2) || t == e) continue;
-      const double o = e_rs[t];
-      if (o > rs || (o == rs && t < e)) ++rank;
-    }
-    atomicAdd(&sm_counts[1], 1);
-    if (rank < a.top_k) {
-      const int64_t o = (int64_t)q * a.top_k + rank;
-      a.out_nodes[o] = e_node[e];
-      a.out_sem[o] = round4_py(e_sem[e]);
-      a.out_score[o] = rs;
-    }
-  }
-  __syncthreads();
-  const int n_valid = sm_counts[1];
-  const int n_out = n_valid < a.top_k ? n_valid : a.top_k;
-  for (int j = n_out + threadIdx.x; j < a.top_k; j += AR_THREADS) {
-    const int64_t o = (int64_t)q * a.top_k + j;
-    a.out_nodes[o] = -1; a.out_sem[o] = 0.0; a.out_score[o] = 0.0;
-  }
-  if (threadIdx.x == 0) {
-    a.out_count[q] = n_out;
-    if (a.exp_count) a.exp_count[q] = sm_counts[0];
-  }
+// large maps: sem[cap] rs[cap] c_rs[cap] (fp64) | node[cap] c_e[cap] h_key[hsize] h_first[hsize] h_seed[hsize] (int32) |
+// kind[cap] flag[cap] (u8)
+__host__ __device__ inline size_t anchor_ws_per_query(int cap, int hsize) {
+  return (((size_t)cap * (3 * 8 + 2 * 4 + 2) + (size_t)hsize * 12) + 15) & ~(size_t)15;
 }
 
 // Block-wide exclusive prefix sum of one int per thread (AR_THREADS = 4 warps); returns the block total in `total`.
@@ -275,39 +134,62 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *sm_warp /*[4]*/,
   return base + x - v;
 }
 
-// Fast path (expanded map fits shared memory: cap <= AR_SMEM_CAP, i.e. every configuration the reference's callers
-// use).  Same results as anchor_rerank_big_kernel, O(cap) work for the map instead of O(cap^2):
-//   dedup        open-addressing hash table in shared memory: first occurrence = atomicMin of the entry index,
-//                "a seed owns its node's value" = atomicMax over the seed entries carrying the node
+// One kernel for every map size.  BIG = false: the expanded map (cap <= AR_SMEM_CAP entries, i.e. every configuration the
+// reference's callers use) and its hash table live in shared memory; BIG = true: same code over the global workspace.
+//   generation   entry (r, j): seed r (j = 0) or its j-th expansion.  ONE 64-byte line per seed (NodeLine: attributes + the
+//                first 8 entries of the list a seed of that type expands into) replaces the chain
+//                seed -> attributes -> row_ptr -> col_idx (r1: 63.5 MB of DRAM sectors for ~10 MB of useful bytes,
+//                profiles/r1_k2_ncu.md); the CSR is only touched for expansions beyond the 8 inline entries.
+//   dedup        open-addressing hash table: first occurrence = atomicMin of the entry index, "a seed owns its node's
+//                value" (:732) = atomicMax over the seed entries carrying the node
 //   positions    block prefix sums (insertion order of the expanded map, order of the filtered list)
-//   stable sort  rank counting over the COMPACTED filtered list (the only O(n^2) step left, n <= cap)
-// The O(cap^2) dedup/position loops of the first version made the kernel instruction-bound: 117 k warp instructions per
-// query at 50 seeds (profiles/r1_k2_c5_ncu.md).
+//   rerank       fp64, the reference's operation order, one 32-byte sector (NodeHead) per emitted node
+//   stable sort  rank counting over the COMPACTED filtered list (the only O(n^2) step, n <= cap)
+// shared-memory footprint of the small-map variant: sem[cap] rs[cap] (fp64) | hval[2 * hsize] node[cap] hkey[hsize] (int32)
+// | kind[cap] flag[cap] (u8).  Sized by the ACTUAL capacity: 50 seeds x 6 = 300 entries need 19 KB, not the 47 KB of a
+// 1024-entry map, so 11 CTAs share an SM instead of 4 (the kernel is latency-bound on its dependent line loads).
+__host__ __device__ inline size_t anchor_smem_bytes(int cap, int hsize) {
+  return (size_t)cap * (8 + 8 + 4 + 1 + 1) + (size_t)hsize * 12 + 16;
+}
+
+template <bool BIG>
 __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a) {
-  constexpr int HASH_MAX = 2 * AR_SMEM_CAP;
-  __shared__ double sm_sem[AR_SMEM_CAP];
-  __shared__ double sm_rs[AR_SMEM_CAP];
-  __shared__ int32_t sm_node[AR_SMEM_CAP];
-  __shared__ uint8_t sm_kind[AR_SMEM_CAP];
-  __shared__ uint8_t sm_flag[AR_SMEM_CAP];
-  __shared__ int32_t h_key[HASH_MAX];                       // node id, -1 = free
-  __shared__ __align__(8) int32_t h_val[2 * HASH_MAX];      // [0, HASH_MAX): first entry, [HASH_MAX, ..): last seed entry
+  extern __shared__ __align__(16) uint8_t ar_smem[];
   __shared__ int sm_warp[AR_THREADS / 32];
-  // after the dedup the hash values are dead: the compacted filtered list lives there
-  double *c_rs = reinterpret_cast<double *>(h_val);         // [AR_SMEM_CAP] rounded scores, 8 KB
-  int32_t *c_e = h_val + 2 * AR_SMEM_CAP;                   // [AR_SMEM_CAP] entry index, 4 KB
-  int32_t *h_first = h_val, *h_seed = h_val + HASH_MAX;
 
   const int q = blockIdx.x;
   const int cap = a.cap, fan = a.fan, per = 1 + fan;
-  double *e_sem = sm_sem, *e_rs = sm_rs;
-  int32_t *e_node = sm_node;
-  uint8_t *e_kind = sm_kind, *e_flag = sm_flag;
+  const int hsize = a.hsize;
+  double *e_sem, *e_rs, *c_rs;
+  int32_t *e_node, *c_e, *h_key, *h_first, *h_seed;
+  uint8_t *e_kind, *e_flag;  // flag: bit0 = first occurrence, bit1 = passes filters, bit2 = owned by a seed
+  if (BIG) {
+    uint8_t *w = a.workspace + (size_t)q * anchor_ws_per_query(cap, hsize);
+    e_sem = reinterpret_cast<double *>(w);
+    e_rs = e_sem + cap;
+    c_rs = e_rs + cap;
+    e_node = reinterpret_cast<int32_t *>(c_rs + cap);
+    c_e = e_node + cap;
+    h_key = c_e + cap;
+    h_first = h_key + hsize;
+    h_seed = h_first + hsize;
+    e_kind = reinterpret_cast<uint8_t *>(h_seed + hsize);
+    e_flag = e_kind + cap;
+  } else {
+    e_sem = reinterpret_cast<double *>(ar_smem);
+    e_rs = e_sem + cap;
+    h_first = reinterpret_cast<int32_t *>(e_rs + cap);  // [hsize] first entry carrying the node
+    h_seed = h_first + hsize;                           // [hsize] last seed entry carrying the node
+    e_node = h_seed + hsize;
+    h_key = e_node + cap;                               // [hsize] node id, -1 = free
+    e_kind = reinterpret_cast<uint8_t *>(h_key + hsize);
+    e_flag = e_kind + cap;
+    // after the dedup the hash values are dead: the compacted filtered list lives there (12 * cap <= 8 * hsize bytes)
+    c_rs = reinterpret_cast<double *>(h_first);
+    c_e = h_first + 2 * cap;
+  }
   const GraphView &g = a.g;
-  const int32_t *seeds = a.seed_nodes + (int64_t)q * a.n_seeds;
   const float *sscore = a.seed_scores + (int64_t)q * a.n_seeds;
-  int hsize = 64;
-  while (hsize < 2 * cap) hsize <<= 1;  // <= HASH_MAX because cap <= AR_SMEM_CAP
   const int hmask = hsize - 1;
   for (int i = threadIdx.x; i < hsize; i += AR_THREADS) {
     h_key[i] = -1;
@@ -318,7 +200,13 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
   // ---- A. generate the candidate list in reference order: seed r, then its expansions ----
   for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
     const int r = e / per, j = e % per;
-    int32_t v = seeds[r];
+    int32_t v;
+    if (a.seed_rows != nullptr) {  // index row -> dense node id (the Chroma id -> G.nodes lookup of :731)
+      const int64_t row = a.seed_rows[(int64_t)q * a.n_seeds + r];
+      v = (row >= 0 && row < a.n_rows) ? a.row_to_node[row] : -1;
+    } else {
+      v = a.seed_nodes[(int64_t)q * a.n_seeds + r];
+    }
     if (v >= g.n_nodes) v = -1;
     int32_t node = -1;
     double sem = 0.0;
@@ -331,21 +219,20 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
         node = v; sem = sem_r; kind = EK_SEED;
         if (a.seed_sem) a.seed_sem[(int64_t)q * a.n_seeds + r] = sem_r;
       } else {
-        const uint8_t t = g.rec[v].type;
-        if (t == AHR_NT_ENTITY && j - 1 < a.prm.parent_cap) {  // first 2 out-belongs_to parents, x0.9 (:733-736)
-          const int64_t p0 = g.row_ptr[AHR_CSR_BEL_OUT][v], p1 = g.row_ptr[AHR_CSR_BEL_OUT][v + 1];
-          if (p0 + (j - 1) < p1) {
-            node = g.col_idx[AHR_CSR_BEL_OUT][p0 + (j - 1)];
-            sem = __dmul_rn(sem_r, 0.9);
-            kind = EK_PARENT;
+        const NodeLine *L = g.line + v;
+        const uint8_t t = L->head.type;
+        // entity: first parent_cap out-belongs_to parents, x0.9 (:733-736); summary: first m members, x0.85 (:737-740)
+        const int want = t == AHR_NT_ENTITY ? a.prm.parent_cap : (t == AHR_NT_SUMMARY ? a.prm.member_top_m : 0);
+        const int i = j - 1;
+        if (i < want && i < L->head.anchor_deg) {
+          if (i < NODE_ANCHOR_INLINE) {
+            node = L->anchor[i];
+          } else {
+            const int slot = t == AHR_NT_ENTITY ? AHR_CSR_BEL_OUT : AHR_CSR_BEL_IN;
+            node = g.col_idx[slot][g.row_ptr[slot][v] + i];
           }
-        } else if (t == AHR_NT_SUMMARY && j - 1 < a.prm.member_top_m) {  // first m in-belongs_to members, x0.85 (:737-740)
-          const int64_t p0 = g.row_ptr[AHR_CSR_BEL_IN][v], p1 = g.row_ptr[AHR_CSR_BEL_IN][v + 1];
-          if (p0 + (j - 1) < p1) {
-            node = g.col_idx[AHR_CSR_BEL_IN][p0 + (j - 1)];
-            sem = __dmul_rn(sem_r, 0.85);
-            kind = EK_MEMBER;
-          }
+          sem = __dmul_rn(sem_r, t == AHR_NT_ENTITY ? 0.9 : 0.85);
+          kind = t == AHR_NT_ENTITY ? EK_PARENT : EK_MEMBER;
         }
       }
     } else if (j == 0 && a.seed_sem) {
@@ -415,7 +302,7 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
   for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
     if (!(e_flag[e] & 1)) continue;
     const int32_t node = e_node[e];
-    const NodeRec rec = g.rec[node];  // one sector: type, judge, judge_term, conf
+    const NodeHead rec = g.line[node].head;  // one sector: type, judge, judge_term, conf
     const uint8_t t = rec.type;
     const double judge = rec.judge, conf = rec.conf;
     const bool has_j = judge == judge, has_c = conf == conf;  // NaN encodes None
@@ -470,14 +357,21 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
   if (threadIdx.x == 0) a.out_count[q] = n_out;
 }
 
+static int anchor_hash_slots(int64_t cap) {
+  int h = 64;
+  while (h < 2 * cap) h <<= 1;
+  return h;
+}
+
 size_t graph_anchor_workspace_bytes(int32_t nq, int32_t n_seeds, const ahr_rerank_params &prm) {
   const int fan = std::max(prm.parent_cap, prm.member_top_m);
   const int64_t cap = (int64_t)n_seeds * (1 + std::max(fan, 0));
   if (cap <= AR_SMEM_CAP) return 0;
-  return (size_t)nq * anchor_ws_per_query((int)cap);
+  return (size_t)nq * anchor_ws_per_query((int)cap, anchor_hash_slots(cap));
 }
 
 int graph_anchor_rerank(const GraphView &g, int32_t nq, int32_t n_seeds, const int32_t *seed_nodes,
+                        const int64_t *seed_rows, const int32_t *row_to_node, int64_t n_rows,
                         const float *seed_scores, const ahr_rerank_params &prm, int32_t top_k, int32_t *out_nodes,
                         double *out_sem, double *out_score, int32_t *out_count, int32_t *exp_nodes, double *exp_sem,
                         uint8_t *exp_kind, int32_t *exp_count, double *seed_sem, void *workspace,
@@ -492,26 +386,30 @@ int graph_anchor_rerank(const GraphView &g, int32_t nq, int32_t n_seeds, const i
   const int64_t cap = (int64_t)n_seeds * (1 + a.fan);
   AHR_REQUIRE(cap <= (1 << 20), "anchor_rerank: expanded map capacity %lld too large", (long long)cap);
   a.cap = (int)cap;
+  a.hsize = anchor_hash_slots(cap);
   a.prm = prm;
-  a.seed_nodes = seed_nodes; a.seed_scores = seed_scores;
+  a.seed_nodes = seed_nodes; a.seed_rows = seed_rows; a.row_to_node = row_to_node; a.n_rows = n_rows;
+  a.seed_scores = seed_scores;
   a.out_nodes = out_nodes; a.out_sem = out_sem; a.out_score = out_score; a.out_count = out_count;
   a.exp_nodes = exp_nodes; a.exp_sem = exp_sem; a.exp_count = exp_count; a.seed_sem = seed_sem;
   a.exp_kind = exp_kind;
   a.workspace = reinterpret_cast<uint8_t *>(workspace);
-  if (cap > AR_SMEM_CAP)
-    AHR_REQUIRE(workspace && workspace_bytes >= (size_t)nq * anchor_ws_per_query((int)cap), "anchor_rerank: workspace too small");
-  if (cap <= AR_SMEM_CAP) anchor_rerank_kernel<<<nq, AR_THREADS, 0, stream>>>(a);
-  else anchor_rerank_big_kernel<<<nq, AR_THREADS, 0, stream>>>(a);
+  if (cap > AR_SMEM_CAP) {
+    AHR_REQUIRE(workspace && workspace_bytes >= (size_t)nq * anchor_ws_per_query((int)cap, a.hsize), "anchor_rerank: workspace too small");
+    anchor_rerank_kernel<true><<<nq, AR_THREADS, 0, stream>>>(a);
+  } else {
+    anchor_rerank_kernel<false><<<nq, AR_THREADS, anchor_smem_bytes(a.cap, a.hsize), stream>>>(a);  // <= 46 KB
+  }
   AHR_KERNEL_CHECK();
   return AHR_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// frontier expansion: one warp per environment
+// frontier expansion, reference-sized limits (<= 64): one warp per environment
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EXP_WARPS * 32)
 expand_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const int32_t *__restrict__ in_ids,
-              const int32_t *__restrict__ in_offsets, int32_t limit, int hash_slots, int32_t *__restrict__ out_ids,
+              const int32_t *__restrict__ in_offsets, int32_t limit, int32_t *__restrict__ out_ids,
               int32_t *__restrict__ out_counts) {
   extern __shared__ int32_t sm_out[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -520,39 +418,245 @@ expand_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const
   ExpandState st;
   st.out = sm_out + (size_t)w * limit;
   st.count = 0; st.raw = 0; st.limit = limit;
-  if (hash_slots > 0) {  // large limits: a hash set instead of scanning the list for every candidate
-    st.hash = sm_out + (size_t)EXP_WARPS * limit + (size_t)w * hash_slots;
-    st.hmask = hash_slots - 1;
-    for (int j = lane; j < hash_slots; j += 32) st.hash[j] = -1;
-    __syncwarp();
-  }
   expand_walk(st, g, ops[env], in_ids + in_offsets[env], in_offsets[env + 1] - in_offsets[env], lane);
   for (int j = lane; j < limit; j += 32) out_ids[(int64_t)env * limit + j] = j < st.count ? st.out[j] : -1;
   if (lane == 0) out_counts[env] = st.count;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frontier expansion, large limits: one CTA per environment, EDGE-parallel.
+//
+// The warp walker above inserts neighbours in order, 32 at a time, with two votes, a match and a scan of the list (or a
+// hash probe) per batch: ~200 warp instructions per 32 neighbours, 0.52 ms for the 273 MB bandwidth view on c5 = 0.08 of
+// HBM (profiles/r1_c5_v7.json).  Order only matters for WHICH occurrence of a value survives and WHERE it lands, and both
+// follow from positions, so the insertion itself needs no order:
+//   every neighbour gets its position p in the reference's concatenation (segment base + offset; excluded elements leave
+//   holes, which is harmless -- positions only have to be monotone);
+//   insert    all threads at once: claim the value's slot of a shared-memory hash table (atomicCAS) and atomicMin p into it;
+//   resolve   element p is the first occurrence of its value iff the table holds p: set bit p of a bitmap;
+//   compact   output index = number of set bits below p (prefix popcount) + what earlier rounds emitted.
+// Long inputs are processed in rounds of `W` positions against the same table (values emitted by earlier rounds stay in
+// it, marked -1); a round that brings the output to `limit` ends the call, so the table never holds more than
+// (limit - 1) + W values.  The stop rule of the reference ("un-deduplicated length >= limit after finishing an input
+// node", environment.py:404-406) is evaluated per input node on the exact count of non-excluded neighbours.
+// ---------------------------------------------------------------------------------------------
+constexpr int EW_THREADS = 64;  // small CTAs: the walk is a chain of dependent loads, what counts is environments in flight per SM
+
+struct EwLayout {
+  int W;      // positions per round (multiple of 32)
+  int T_max;  // hash slots (power of two)
+  __host__ __device__ size_t bytes() const { return (size_t)T_max * 8 + (size_t)W * 4 + (size_t)W * 2 + (size_t)(W / 32) * 8; }
+};
+__host__ __device__ inline int ew_table_slots(int values) {  // open addressing at a load factor <= 0.75
+  int t = 64;
+  while (3 * t < 4 * values) t <<= 1;
+  return t;
+}
+__host__ __device__ inline EwLayout ew_layout(int limit) {
+  EwLayout l;
+  l.W = 256;  // a round about half as long as the limit: 9.8 KB per CTA at limit 512 -> 23 CTAs (environments) per SM
+  while (2 * l.W < limit) l.W <<= 1;
+  l.T_max = ew_table_slots(limit + l.W);
+  return l;
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+expand_wide_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const int32_t *__restrict__ in_ids,
+                   const int32_t *__restrict__ in_offsets, int32_t limit, int32_t *__restrict__ out_ids,
+                   int32_t *__restrict__ out_counts) {
+  extern __shared__ __align__(16) uint8_t ew_smem[];
+  __shared__ unsigned long long s_est;
+  __shared__ int s_raw, s_total;
+  const EwLayout lay = ew_layout(limit);
+  int32_t *tkey = reinterpret_cast<int32_t *>(ew_smem);                 // [T] value, -1 = free
+  int32_t *tpos = tkey + lay.T_max;                                     // [T] lowest position this round; -1 = emitted earlier
+  int32_t *rval = tpos + lay.T_max;                                     // [W] value at round position p, -1 = hole
+  uint16_t *rslot = reinterpret_cast<uint16_t *>(rval + lay.W);         // [W] its table slot
+  uint32_t *bits = reinterpret_cast<uint32_t *>(rslot + lay.W);         // [W / 32] first-occurrence flags
+  uint32_t *pref = bits + lay.W / 32;                                   // [W / 32] exclusive prefix popcounts
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int env = blockIdx.x;
+  const int op = ops[env];
+  const int32_t *ids = in_ids + in_offsets[env];
+  const int n_ids = in_offsets[env + 1] - in_offsets[env];
+  int32_t *out = out_ids + (int64_t)env * limit;
+  auto deg = [&](int slot, int32_t v) { return g.row_ptr[slot][v + 1] - g.row_ptr[slot][v]; };
+
+  // ---- size the table for THIS environment: an upper bound of the positions it can produce ----
+  if (tid == 0) { s_est = 0; s_raw = 0; }
+  __syncthreads();
+  for (int i = tid; i < n_ids; i += EW_THREADS) {
+    const int32_t v = ids[i];
+    if (v < 0 || v >= g.n_nodes) continue;
+    int64_t d;
+    if (op == AHR_OP_PARENTS) d = deg(AHR_CSR_BEL_OUT, v);
+    else if (op == AHR_OP_CHILDREN) d = deg(AHR_CSR_BEL_IN, v);
+    else {
+      d = deg(AHR_CSR_REL_OUT, v) + deg(AHR_CSR_REL_IN, v);
+      if (g.line[v].head.type == AHR_NT_ENTITY) {
+        const int64_t h0 = g.row_ptr[AHR_CSR_PART_OUT][v], h1 = g.row_ptr[AHR_CSR_PART_OUT][v + 1];
+        for (int64_t hi = h0; hi < h1 && d < (1 << 24); ++hi) d += 1 + deg(AHR_CSR_PART_IN, g.col_idx[AHR_CSR_PART_OUT][hi]);
+      }
+    }
+    atomicAdd(&s_est, (unsigned long long)min(d, (int64_t)(1 << 24)));
+  }
+  __syncthreads();
+  const int est = (int)min(max(s_est, 1ull), (unsigned long long)(1 << 24));
+  const int W = min(lay.W, (est + 31) & ~31);
+  const int T = ew_table_slots(min(min(limit, est) + W, est));  // <= lay.T_max
+  const int tshift = 32 - (31 - __clz(T));        // hash = top log2(T) bits of the product
+  for (int i = tid; i < T; i += EW_THREADS) { tkey[i] = -1; tpos[i] = 0x7fffffff; }
+  for (int i = tid; i < W / 32; i += EW_THREADS) bits[i] = 0;
+  __syncthreads();
+
+  int fill = 0, out_count = 0;  // uniform across the block
+  int my_valid = 0;             // this thread's non-excluded neighbours of the current input node
+  bool done = false;
+
+  auto insert = [&](int32_t val, bool valid, int p) {
+    int slot = 0;
+    if (valid) {
+      slot = (int)(((uint32_t)val * 2654435761u) >> tshift);
+      for (;;) {
+        const int32_t k = atomicCAS(&tkey[slot], -1, val);
+        if (k == -1 || k == val) break;
+        slot = (slot + 1) & (T - 1);
+      }
+      atomicMin(&tpos[slot], p);
+    }
+    rval[p] = valid ? val : -1;
+    rslot[p] = (uint16_t)slot;
+  };
+  // resolve + compact the positions [0, fill) of this round
+  auto flush = [&]() {
+    __syncthreads();
+    for (int p = tid; p < fill; p += EW_THREADS)
+      if (rval[p] >= 0 && tpos[rslot[p]] == p) atomicOr(&bits[p >> 5], 1u << (p & 31));
+    __syncthreads();
+    if (tid < 32) {  // exclusive prefix popcount over the W / 32 (<= 64) words
+      const int nw = W / 32;
+      const int c0 = lane < nw ? __popc(bits[lane]) : 0, c1 = 32 + lane < nw ? __popc(bits[32 + lane]) : 0;
+      int x0 = c0, x1 = c1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int y0 = __shfl_up_sync(0xffffffffu, x0, d), y1 = __shfl_up_sync(0xffffffffu, x1, d);
+        if (lane >= d) { x0 += y0; x1 += y1; }
+      }
+      const int tot0 = __shfl_sync(0xffffffffu, x0, 31);
+      if (lane < nw) pref[lane] = x0 - c0;
+      if (32 + lane < nw) pref[32 + lane] = tot0 + x1 - c1;
+      if (lane == 31) s_total = tot0 + x1;
+    }
+    __syncthreads();
+    for (int p = tid; p < fill; p += EW_THREADS) {
+      const uint32_t wbits = bits[p >> 5];
+      if (!((wbits >> (p & 31)) & 1u)) continue;
+      const int rank = out_count + pref[p >> 5] + __popc(wbits & ((1u << (p & 31)) - 1u));
+      if (rank < limit) out[rank] = rval[p];
+      tpos[rslot[p]] = -1;  // emitted (or beyond the limit, in which case the call ends here)
+    }
+    out_count = min(limit, out_count + s_total);
+    __syncthreads();  // the next round overwrites rval / rslot / s_total
+    for (int i = tid; i < W / 32; i += EW_THREADS) bits[i] = 0;  // next read: after the barrier that opens the next flush
+    fill = 0;
+    if (out_count >= limit) done = true;
+  };
+  // one CSR segment (or, with literal >= 0, the single value `literal`) appended to the concatenation
+  auto segment = [&](int slot, int32_t v, int32_t exclude, int32_t literal) {
+    const int64_t p0 = literal >= 0 ? 0 : g.row_ptr[slot][v];
+    const int64_t len = literal >= 0 ? 1 : g.row_ptr[slot][v + 1] - p0;
+    int64_t off = 0;
+    while (off < len && !done) {
+      const int n = (int)min(len - off, (int64_t)(W - fill));
+      const int32_t *src = literal >= 0 ? nullptr : g.col_idx[slot] + p0 + off;
+      for (int i0 = 0; i0 < n; i0 += 4 * EW_THREADS) {  // four coalesced loads in flight per thread, then the inserts
+        int32_t val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * EW_THREADS + tid;
+          val[u] = i < n ? (literal >= 0 ? literal : src[i]) : exclude;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * EW_THREADS + tid;
+          if (i < n) {
+            const bool valid = val[u] != exclude;
+            my_valid += valid ? 1 : 0;
+            insert(val[u], valid, fill + i);
+          }
+        }
+      }
+      fill += n;
+      off += n;
+      if (fill == W) flush();
+    }
+  };
+  // pull a neighbour list into L2 while the lists before it are being inserted (one line per thread and step)
+  auto prefetch = [&](int slot, int32_t v) {
+    const int64_t p0 = g.row_ptr[slot][v], p1 = g.row_ptr[slot][v + 1];
+    const char *b = reinterpret_cast<const char *>(g.col_idx[slot] + p0);
+    const int64_t bytes = min((p1 - p0) * 4, (int64_t)(lay.W + limit) * 4);
+    for (int64_t o = (int64_t)tid * 128; o < bytes; o += (int64_t)EW_THREADS * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+  };
+
+  for (int idx = 0; idx < n_ids && !done; ++idx) {
+    const int32_t v = ids[idx];
+    if (v < 0 || v >= g.n_nodes) continue;  // `if nid not in G: continue`
+    my_valid = 0;
+    if (op == AHR_OP_PARENTS) {
+      segment(AHR_CSR_BEL_OUT, v, -1, -1);
+    } else if (op == AHR_OP_CHILDREN) {
+      segment(AHR_CSR_BEL_IN, v, -1, -1);
+    } else {
+      prefetch(AHR_CSR_REL_IN, v);
+      segment(AHR_CSR_REL_OUT, v, -1, -1);
+      segment(AHR_CSR_REL_IN, v, -1, -1);
+      if (g.line[v].head.type == AHR_NT_ENTITY) {
+        // second hop: every hyperedge h of v, then the other participants of h  (environment.py:456-467)
+        const int64_t h0 = g.row_ptr[AHR_CSR_PART_OUT][v], h1 = g.row_ptr[AHR_CSR_PART_OUT][v + 1];
+        for (int64_t hi = h0; hi < h1 && !done; ++hi) {
+          const int32_t h = g.col_idx[AHR_CSR_PART_OUT][hi];
+          segment(0, 0, -1, h);
+          segment(AHR_CSR_PART_IN, h, v, -1);
+        }
+      }
+    }
+    if (done) break;
+    // stop rule on the UN-deduplicated length, checked after finishing v
+    if (my_valid) atomicAdd(&s_raw, my_valid);
+    __syncthreads();
+    const int raw = s_raw;
+    __syncthreads();
+    if (raw >= limit) break;
+  }
+  if (!done && fill > 0) flush();
+  for (int j = out_count + tid; j < limit; j += EW_THREADS) out[j] = -1;
+  if (tid == 0) out_counts[env] = out_count;
 }
 
 int graph_expand(const GraphView &g, int32_t n_env, const int32_t *ops, const int32_t *in_ids,
                  const int32_t *in_offsets, int32_t limit, int32_t *out_ids, int32_t *out_counts, cudaStream_t stream) {
   AHR_REQUIRE(limit >= 1 && limit <= 2048, "expand: limit must be in [1, 2048] (got %d)", limit);
   if (n_env <= 0) return AHR_OK;
-  // the list can hold `limit` values but a batch of up to 32 is inserted before the cut: 2 * (limit + 32) slots, power of 2
-  int hash_slots = 0;
-  if (limit > 64) {
-    hash_slots = 128;
-    while (hash_slots < 2 * (limit + 32)) hash_slots <<= 1;
+  if (limit <= 64) {
+    const size_t smem = (size_t)EXP_WARPS * limit * sizeof(int32_t);
+    expand_kernel<<<(n_env + EXP_WARPS - 1) / EXP_WARPS, EXP_WARPS * 32, smem, stream>>>(g, n_env, ops, in_ids, in_offsets,
+                                                                                        limit, out_ids, out_counts);
+    AHR_KERNEL_CHECK();
+    return AHR_OK;
   }
-  const size_t smem = (size_t)EXP_WARPS * (limit + hash_slots) * sizeof(int32_t);
+  const size_t smem = ew_layout(limit).bytes();
   if (smem > 48 * 1024) {
     static std::atomic<uint64_t> configured{0};
     int dev = 0;
     AHR_CUDA_CHECK(cudaGetDevice(&dev));
     if (!((configured.load(std::memory_order_relaxed) >> (dev & 63)) & 1)) {
-      AHR_CUDA_CHECK(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024));
+      AHR_CUDA_CHECK(cudaFuncSetAttribute(expand_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       configured.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
     }
   }
-  expand_kernel<<<(n_env + EXP_WARPS - 1) / EXP_WARPS, EXP_WARPS * 32, smem, stream>>>(g, n_env, ops, in_ids, in_offsets,
-                                                                                      limit, hash_slots, out_ids, out_counts);
+  expand_wide_kernel<<<n_env, EW_THREADS, smem, stream>>>(g, n_env, ops, in_ids, in_offsets, limit, out_ids, out_counts);
   AHR_KERNEL_CHECK();
   return AHR_OK;
 }

@@ -13,11 +13,10 @@ struct ExpandState {
   int count;
   int raw;
   int limit;
-  int32_t *hash = nullptr;  // optional open-addressing set of the values in `out` (-1 = free), hmask + 1 slots
-  int hmask = 0;            // used for large limits, where scanning `out` per candidate would be O(limit)
 };
 
 // append values to the order-preserving unique list; returns true once the list is full
+// (limits up to 64: the list is scanned per candidate; larger limits take the edge-parallel kernel of graph.cu)
 __device__ __forceinline__ bool expand_push(ExpandState &st, int32_t val, bool valid, int lane) {
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   st.raw += __popc(vmask);
@@ -25,20 +24,8 @@ __device__ __forceinline__ bool expand_push(ExpandState &st, int32_t val, bool v
   const unsigned peers = __match_any_sync(0xffffffffu, valid ? val : (int32_t)(-2 - lane));
   const bool first_in_batch = (__ffs(peers & vmask) - 1) == lane;
   bool dup = false;
-  if (st.hash != nullptr) {
-    // only the batch's representative of a value probes / inserts, so lane order still decides the list order
-    if (valid && first_in_batch) {
-      int slot = (int)(((uint32_t)val * 2654435761u) >> 8) & st.hmask;
-      for (;;) {
-        const int32_t k = atomicCAS(&st.hash[slot], -1, val);
-        if (k == -1) break;
-        if (k == val) { dup = true; break; }
-        slot = (slot + 1) & st.hmask;
-      }
-    }
-  } else if (valid) {
+  if (valid)
     for (int t = 0; t < st.count; ++t) dup |= (st.out[t] == val);
-  }
   const bool fresh = valid && !dup && first_in_batch;
   const unsigned nmask = __ballot_sync(0xffffffffu, fresh);
   const int pos = st.count + __popc(nmask & ((1u << lane) - 1u));
@@ -80,7 +67,7 @@ __device__ __forceinline__ void expand_walk(ExpandState &st, const GraphView &g,
     } else {
       full = expand_segment(st, g, AHR_CSR_REL_OUT, v, -1, lane);
       if (!full) full = expand_segment(st, g, AHR_CSR_REL_IN, v, -1, lane);
-      if (!full && g.rec[v].type == AHR_NT_ENTITY) {
+      if (!full && g.line[v].head.type == AHR_NT_ENTITY) {
         // second hop: every hyperedge h of v, then the other participants of h  (environment.py:456-467)
         const int64_t h0 = g.row_ptr[AHR_CSR_PART_OUT][v], h1 = g.row_ptr[AHR_CSR_PART_OUT][v + 1];
         for (int64_t hi = h0; hi < h1 && !full; ++hi) {

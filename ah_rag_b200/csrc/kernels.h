@@ -66,27 +66,39 @@ int gather_rows_i64(const float *src_s, const int64_t *src_i, const int32_t *sel
 int gather_query_rows(const void *src, int64_t row_bytes, const int32_t *sel, int32_t n_sel, void *out, cudaStream_t stream);
 
 // ---- graph.cu (K2) ----
-// Node attributes packed into ONE 32-byte record = one DRAM sector per node.  The five separate arrays the caller hands to
-// ahr_graph_create cost five sectors per touched node (hop 1 on c5: 63.5 MB of sector traffic for ~10 MB of useful bytes,
-// profiles/r1_k2_ncu.md); the library packs them once at create time.
-struct alignas(32) NodeRec {
-  double judge;       // NaN = None
-  double judge_term;  // 1 / (1 + exp(-judge / 10)) as evaluated by the host (the reference's own np.exp)
-  double conf;        // NaN = None
-  uint8_t type;       // AHR_NT_*
+// Node attributes + the head of the node's anchor list packed into ONE 64-byte line per node (library-owned, built by
+// ahr_graph_create).  The five separate attribute arrays cost five DRAM sectors per touched node, and a seed's expansion
+// walked seed -> attributes -> row_ptr -> col_idx -> attributes: four dependent random sectors (hop 1 on c5: 63.5 MB of
+// sector traffic for ~10 MB of useful bytes, profiles/r1_k2_ncu.md).
+//   sector 0 (NodeHead)  what the rerank / featurizer read for every emitted node
+//   sector 1             the first 8 entries of the list a seed of this type expands into: entity -> belongs_to parents
+//                        (G.out_edges order), summary -> members (G.in_edges order); -1 padded.  The reference's caps
+//                        (2 parents, member_top_m = 5) never leave the line.
+constexpr int NODE_ANCHOR_INLINE = 8;
+struct alignas(32) NodeHead {
+  double judge;        // NaN = None
+  double judge_term;   // 1 / (1 + exp(-judge / 10)) as evaluated by the host (the reference's own np.exp)
+  double conf;         // NaN = None
+  int32_t anchor_deg;  // full length of the anchor list (0 for hyperedges / unknown types)
+  uint8_t type;        // AHR_NT_*
   uint8_t level;
-  uint8_t pad[6];
+  uint8_t pad[2];
 };
-static_assert(sizeof(NodeRec) == 32, "NodeRec must be one 32-byte sector");
+struct alignas(64) NodeLine {
+  NodeHead head;
+  int32_t anchor[NODE_ANCHOR_INLINE];
+};
+static_assert(sizeof(NodeHead) == 32 && sizeof(NodeLine) == 64, "NodeLine must be two 32-byte sectors");
 
 struct GraphView {
   int64_t n_nodes;
   const int64_t *row_ptr[AHR_N_CSR];
   const int32_t *col_idx[AHR_N_CSR];
-  const NodeRec *rec;  // [n_nodes], library-owned
+  const NodeLine *line;  // [n_nodes], library-owned
 };
+// seeds: dense node ids (seed_nodes), or index rows + the row -> node table (seed_rows / row_to_node / n_rows)
 int graph_anchor_rerank(const GraphView &g, int32_t nq, int32_t n_seeds, const int32_t *seed_nodes,
-                        const float *seed_scores, const ahr_rerank_params &prm, int32_t top_k, int32_t *out_nodes,
+                        const int64_t *seed_rows, const int32_t *row_to_node, int64_t n_rows, const float *seed_scores, const ahr_rerank_params &prm, int32_t top_k, int32_t *out_nodes,
                         double *out_sem, double *out_score, int32_t *out_count, int32_t *exp_nodes, double *exp_sem,
                         uint8_t *exp_kind, int32_t *exp_count, double *seed_sem, void *workspace, size_t workspace_bytes,
                         cudaStream_t stream);
@@ -95,7 +107,8 @@ int graph_expand(const GraphView &g, int32_t n_env, const int32_t *ops, const in
                  const int32_t *in_offsets, int32_t limit, int32_t *out_ids, int32_t *out_counts, cudaStream_t stream);
 int debug_round4(const double *x, int64_t n, double *out, cudaStream_t stream);
 int graph_pack_nodes(int64_t n_nodes, const uint8_t *node_type, const uint8_t *level, const double *judge,
-                     const double *judge_term, const double *conf, NodeRec *out, cudaStream_t stream);
+                     const double *judge_term, const double *conf, const int64_t *const row_ptr[AHR_N_CSR],
+                     const int32_t *const col_idx[AHR_N_CSR], NodeLine *out, cudaStream_t stream);
 
 // ---- lca.cu ----
 size_t graph_lca_workspace_bytes(int64_t n_nodes);

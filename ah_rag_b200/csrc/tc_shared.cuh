@@ -29,6 +29,9 @@ struct TcParams {
   int32_t tile_stride;   // corpus tile i of this launch is tile i * tile_stride of the index (sample pass: > 1)
   int32_t thr_stride;    // thr_src[q * thr_stride] = k-th best score of query q over a SAMPLE of the corpus rows
   const float *thr_src;  // optional: seeds every list's admission threshold (see seed_threshold)
+  uint32_t *thr_shared;  // optional [n_slabs][q_rows]: what every slab has published for every query (see "shared bound")
+  int32_t q_rows;        // row pitch of thr_shared (queries padded to whole tiles)
+  int32_t bound_m;       // each slab publishes the bound_m-th best score of its list: n_slabs * bound_m >= k
 };
 
 // Optional knobs of a K1 launch (host side).
@@ -37,6 +40,7 @@ struct TcExtra {
   int32_t tile_stride = 1;
   const float *thr_src = nullptr;
   int32_t thr_stride = 0;
+  uint32_t *thr_shared = nullptr;  // zero-initialised by the caller before the launch
 };
 
 // mbarrier wait that optionally accounts the cycles spent waiting
@@ -110,6 +114,50 @@ __device__ __forceinline__ float seed_threshold(const TcParams &p, int64_t q, bo
   return orderable_float(float_orderable(s) - 1u);
 }
 
+// Shared admission bound.  Every (slab, query) list learns its own threshold from scratch: ~k ln(rows per slab / k) appends
+// per row, front-loaded, and a chunk is "slow" as soon as ONE of the warp's 32 rows has a candidate.  With many short slabs
+// (a 256-query batch over a 12.5M-row shard runs 74 slabs of 169k rows) 57 % of all chunks were slow and the MMA issuer
+// spent >= 24 % of the kernel waiting for the epilogue to hand TMEM back (profiles/r2_k1_q256_wait_counters_before.txt).
+//
+// Slabs are disjoint row ranges.  If every slab s holds at least m rows scoring >= b_s for a query, the corpus holds at
+// least S * m >= k rows scoring >= B = min_s b_s, so the query's global k-th best is >= B and a row scoring strictly below
+// B can be dropped by EVERY slab.  Each list publishes its m-th best score, m = ceil(k / S), whenever it is compacted
+// (thr_shared[slab][q], orderable uint image of the float, 0 = nothing yet, single writer, monotone); the epilogue threads
+// re-read the S values of their query every few tiles and raise their threshold to just below the minimum -- rows scoring
+// EXACTLY B are kept (they may win the id tie-break), hence float_below().  Until all S slabs have published the minimum
+// is 0 = no bound.  Relaxed accesses: a stale value is a valid, merely weaker, bound, so the result -- the global top-k
+// under the total order -- does not depend on timing.  With S = 74, k = 50 this is the minimum of the slabs' running
+// maxima, about the 74th best score seen so far over the WHOLE corpus, against the 50th best of one slab before.
+__device__ __forceinline__ float float_below(float s) {
+  if (s == 0.0f) return -1.401298464e-45f;  // +-0 compare equal: step below both
+  return orderable_float(float_orderable(s) - 1u);
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// minimum over the slabs of what they published for query q (0 as soon as one slab has not published)
+__device__ __forceinline__ uint32_t shared_bound_peek(const TcParams &p, int64_t q, bool active) {
+  if (!active) return 0;
+  uint32_t b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu;
+  const uint32_t *src = p.thr_shared + q;
+  int s = 0;
+  for (; s + 1 < p.n_slabs; s += 2) {  // two independent chains; the loads pipeline in L2
+    b0 = min(b0, ld_relaxed_u32(src + (int64_t)s * p.q_rows));
+    b1 = min(b1, ld_relaxed_u32(src + (int64_t)(s + 1) * p.q_rows));
+  }
+  if (s < p.n_slabs) b0 = min(b0, ld_relaxed_u32(src + (int64_t)s * p.q_rows));
+  return min(b0, b1);
+}
+__device__ __forceinline__ float shared_bound_apply(uint32_t bits, float thr) {
+  // 0x007FFFFF is the image of -inf: anything at or below it carries no information
+  return bits > 0x00800000u ? fmaxf(thr, float_below(orderable_float(bits))) : thr;
+}
+
 // All 32 lanes call.  Sorts the first `cnt` entries of the list at shared address `list_addr` (best first), pads the
 // rest with the empty key, writes all KLIST slots back.  Returns the score of the k-th entry (-inf if cnt < k).
 template <int KLIST>
@@ -178,7 +226,8 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
 // scratch_lane: shared address of this lane's column of the warp's chunk scratch (score of column j at + j*128).
 template <int KLIST>
 static __device__ __noinline__ void epilogue_overflow(uint32_t scratch_lane, unsigned pending, int k, int32_t id0,
-                                                      uint32_t lists_warp, float &thr_ref, int &cnt_ref) {
+                                                      uint32_t lists_warp, float &thr_ref, int &cnt_ref,
+                                                      uint32_t *bound_slot, int bound_m) {
   const int lane = threadIdx.x & 31;
   const uint32_t my_list = lists_warp + (uint32_t)lane * (KLIST * 8);
   float thr = thr_ref;
@@ -201,7 +250,9 @@ static __device__ __noinline__ void epilogue_overflow(uint32_t scratch_lane, uns
       const float kth = warp_list_compact<KLIST>(lists_warp + (uint32_t)owner * (KLIST * 8), KLIST, k);
       if (lane == owner) {
         cnt = k;
-        thr = kth;
+        thr = fmaxf(thr, kth);  // never below a bound taken from thr_shared
+        // the list is sorted now: its bound_m-th best score goes to the other slabs (single writer, only ever grows)
+        if (bound_slot != nullptr) st_relaxed_u32(bound_slot, (uint32_t)(lds_u64(my_list + (bound_m - 1) * 8) >> 32));
       }
     }
   }
@@ -223,7 +274,8 @@ template <int KLIST, int BN, bool DBG, typename Release>
 __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bool row_valid, int k, int64_t col0,
                                                    int64_t q_global, const TcParams &p, uint32_t lists_warp,
                                                    uint32_t scratch_warp, float &thr, int &cnt,
-                                                   unsigned long long *n_slow, Release release) {
+                                                   unsigned long long *n_slow, uint32_t *bound_slot, int bound_m,
+                                                   float &best, Release release) {
   const int lane = threadIdx.x & 31;
   const uint32_t my_list = lists_warp + (uint32_t)lane * (KLIST * 8);
   const uint32_t scratch_lane = scratch_warp + (uint32_t)lane * 4;
@@ -257,17 +309,26 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bo
         for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
         if (n_valid < 32) bits &= (1u << n_valid) - 1u;
         const int32_t id0 = (int32_t)(col0 + c);
+        float cmax = -INFINITY;
         while (bits != 0 && cnt < KLIST) {  // ascending column order: equal scores keep the lower row id
           const int j = __ffs(bits) - 1;
           bits &= bits - 1;
-          sts_u64(my_list + cnt * 8, make_key(lds_f32(scratch_lane + j * 128), id0 + j));
+          const float sc = lds_f32(scratch_lane + j * 128);
+          sts_u64(my_list + cnt * 8, make_key(sc, id0 + j));
+          cmax = fmaxf(cmax, sc);
           ++cnt;
         }
         pending = bits;
+        // bound_m == 1: the list's best score IS what this slab publishes -- no need to wait for the next compaction
+        // (lists that rarely fill up would otherwise sit on a stale value)
+        if (bound_m == 1 && bound_slot != nullptr && cmax > best) {
+          best = cmax;
+          st_relaxed_u32(bound_slot, float_orderable(cmax));
+        }
       }
       // a full list is compacted right away, even with nothing pending: its threshold is stale
       if (__any_sync(0xffffffffu, cnt == KLIST))
-        epilogue_overflow<KLIST>(scratch_lane, pending, k, (int32_t)(col0 + c), lists_warp, thr, cnt);
+        epilogue_overflow<KLIST>(scratch_lane, pending, k, (int32_t)(col0 + c), lists_warp, thr, cnt, bound_slot, bound_m);
     }
   };
 #pragma unroll 1

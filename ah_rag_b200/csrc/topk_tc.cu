@@ -149,14 +149,21 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const bool row_valid = q_global < p.nq;
       float thr = seed_threshold(p, q_global, row_valid);  // admission threshold of this thread's row
       int cnt = 0;            // entries in this thread's list
+      float best = -INFINITY;  // best score appended so far (published when each slab publishes its top-1)
+      const bool bound_on = p.thr_shared != nullptr && row_valid;
+      uint32_t *bound_slot = bound_on ? p.thr_shared + (int64_t)slab * p.q_rows + q_global : nullptr;
       for (int64_t ct = t0; ct < t1; ++ct) {
+        // every tile while the lists are young, every 8th afterwards; issued before the wait: the L2 latency hides behind it
+        const int64_t age = ct - t0;
+        const uint32_t bound_bits = shared_bound_peek(p, q_global, bound_on && (age < 8 || (age & 7) == 0));
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
+        thr = shared_bound_apply(bound_bits, thr);
         const int64_t col0 = ct * p.tile_stride * TC_BN;
         const int ncols = (int)min((int64_t)TC_BN, p.n_rows - col0);
         uint64_t *release_bar = &tempty[acc];
         epilogue_scan_tile<KLIST, TC_BN, DBG>(t_lane + (uint32_t)(acc * TC_BN), ncols, row_valid, k, col0, q_global, p,
-                                              lists_warp, scratch_warp, thr, cnt, nullptr, [&]() {
+                                              lists_warp, scratch_warp, thr, cnt, nullptr, bound_slot, p.bound_m, best, [&]() {
                                                 tc_fence_before();
                                                 __syncwarp();
                                                 if (lane == 0) mbar_arrive(release_bar);
@@ -276,6 +283,9 @@ int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows
   p.n_ctiles = ((n_rows + TC_BN - 1) / TC_BN + p.tile_stride - 1) / p.tile_stride;
   p.thr_src = ex.thr_src;
   p.thr_stride = ex.thr_stride;
+  p.thr_shared = n_slabs > 1 ? ex.thr_shared : nullptr;  // one slab: its own threshold is the bound
+  p.q_rows = std::max(ex.q_rows, nq);
+  p.bound_m = (k + n_slabs - 1) / n_slabs;
   p.nq = nq;
   p.dim = dim;
   p.n_qtiles = (nq + TC_BM - 1) / TC_BM;

@@ -234,14 +234,21 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const bool row_valid = q_global < p.nq;
       float thr = seed_threshold(p, q_global, row_valid);  // admission threshold of this thread's row
       int cnt = 0;            // entries in this thread's list
+      float best = -INFINITY;  // best score appended so far (published when each slab publishes its top-1)
+      const bool bound_on = p.thr_shared != nullptr && row_valid;
+      uint32_t *bound_slot = bound_on ? p.thr_shared + (int64_t)slab * p.q_rows + q_global : nullptr;
       for (int64_t ct = t0; ct < t1; ++ct) {
+        // every tile while the lists are young, every 8th afterwards; issued before the wait: the L2 latency hides behind it
+        const int64_t age = ct - t0;
+        const uint32_t bound_bits = shared_bound_peek(p, q_global, bound_on && (age < 8 || (age & 7) == 0));
         mbar_wait_acct(&tfull[acc], acc_phase, acct);
         tc_fence_after();
+        thr = shared_bound_apply(bound_bits, thr);
         const int64_t col0 = ct * p.tile_stride * T2_BN;
         const int ncols = (int)min((int64_t)T2_BN, p.n_rows - col0);
         const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[acc]), 0);
         epilogue_scan_tile<KLIST, T2_BN, DBG>(t_lane + (uint32_t)(acc * T2_BN), ncols, row_valid, k, col0, q_global, p,
-                                              lists_warp, scratch_warp, thr, cnt, p.stats ? n_slow : nullptr, [&]() {  // uniform: every lane counts
+                                              lists_warp, scratch_warp, thr, cnt, p.stats ? n_slow : nullptr, bound_slot, p.bound_m, best, [&]() {  // uniform: every lane counts
                                                 tc_fence_before();
                                                 __syncwarp();
                                                 if (lane == 0) mbar_arrive_cluster(tempty_leader);  // leader's barrier
@@ -326,6 +333,9 @@ int tc2_topk_partials(const CUtensorMap &map_x, const CUtensorMap *map_x_lo, con
   p.n_ctiles = ((n_rows + T2_BN - 1) / T2_BN + p.tile_stride - 1) / p.tile_stride;
   p.thr_src = ex.thr_src;
   p.thr_stride = ex.thr_stride;
+  p.thr_shared = n_slabs > 1 ? ex.thr_shared : nullptr;  // one slab: its own threshold is the bound
+  p.q_rows = std::max(ex.q_rows, nq);
+  p.bound_m = (k + n_slabs - 1) / n_slabs;
   p.nq = nq;
   p.dim = dim;
   p.n_qtiles = (nq + 2 * T2_BM - 1) / (2 * T2_BM);
@@ -347,8 +357,14 @@ int tc2_topk_partials(const CUtensorMap &map_x, const CUtensorMap *map_x_lo, con
     // the rest of the SM's 228 KB stays L1.  Measured alternatives (profiles/r1_k1_epilogue_history.md, "rings"):
     // 3+5 / 3+6 starve the tensor-bound workload (-18 %), 4+5 and 5+4 change nothing on either regime.
     // AHR_TC_RING=45 keeps the 4+5 build for experiments.
-    static const int ring = getenv("AHR_TC_RING") ? atoi(getenv("AHR_TC_RING")) : 44;
+    // AHR_TC_RING = 44 | 45 | 36 forces one build.  Default: a single query tile (<= 256 queries) streams the corpus from
+    // HBM while the same 12-16 query k-blocks come out of L2 again and again -- one more corpus slot takes the MMA issuer's
+    // wait for data from 1.76M to 1.02M of 5.3M cycles (profiles/r2_k1_q256_wait_counters.md); with several query tiles the
+    // corpus is mostly L2 traffic too and the extra 16 KB of shared memory only costs L1 (c3: 63 -> 69 ms).
+    static const int ring_env = getenv("AHR_TC_RING") ? atoi(getenv("AHR_TC_RING")) : 0;
+    const int ring = ring_env ? ring_env : (p.n_qtiles == 1 ? 45 : 44);
     if (ring == 45) return tc2_launch_t<64, 4, 5, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
+    if (ring == 36) return tc2_launch_t<64, 3, 6, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
     return tc2_launch_t<64, 4, 4, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
   }
   return tc2_launch_t<128, 2, 2, false>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);

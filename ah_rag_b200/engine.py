@@ -275,12 +275,19 @@ class GraphCSR:
         return sum(t.numel() * t.element_size() for t in ts)
 
     def anchor_rerank(self, seed_nodes: torch.Tensor, seed_scores: torch.Tensor, params: SearchParams, top_k: int,
-                      want_cluster: bool = True) -> Dict[str, torch.Tensor]:
-        """Batched hierarchical_graph.py:719-789.  seed_nodes int32 [nq, n_seeds] (-1 = none), seed_scores fp32."""
+                      want_cluster: bool = True, row_to_node: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Batched hierarchical_graph.py:719-789.  seed_scores fp32 [nq, n_seeds]; seed_nodes either int32 dense node ids
+        (-1 = none) or, with ``row_to_node`` (int32 [n_rows]), the int64 index rows exactly as ``VectorIndex.topk`` returns
+        them -- the row -> node lookup then happens inside the kernel (``ahr_anchor_rerank_rows``)."""
         _require_cuda(seed_nodes, "seed_nodes")
         _require_cuda(seed_scores, "seed_scores")
-        if seed_nodes.dtype != torch.int32 or seed_scores.dtype != torch.float32 or seed_nodes.shape != seed_scores.shape:
-            raise ValueError("seed_nodes must be int32 and seed_scores float32 of the same [nq, n_seeds] shape")
+        want = torch.int64 if row_to_node is not None else torch.int32
+        if seed_nodes.dtype != want or seed_scores.dtype != torch.float32 or seed_nodes.shape != seed_scores.shape:
+            raise ValueError(f"seed_nodes must be {want} and seed_scores float32 of the same [nq, n_seeds] shape")
+        if row_to_node is not None:
+            _require_cuda(row_to_node, "row_to_node")
+            if row_to_node.dtype != torch.int32:
+                raise ValueError("row_to_node must be int32")
         nq, ns = int(seed_nodes.shape[0]), int(seed_nodes.shape[1])
         dev = self.device
         cp = params.to_c()
@@ -300,16 +307,22 @@ class GraphCSR:
             out["seed_semantic"] = torch.empty((nq, ns), dtype=torch.float64, device=dev)
         if nq == 0:
             return out
-        with torch.cuda.device(dev):
-            check(self.lib.ahr_anchor_rerank(
-                self._h, nq, ns, seed_nodes.data_ptr(), seed_scores.data_ptr(), ctypes.byref(cp), int(top_k),
+        tail = (ctypes.byref(cp), int(top_k),
                 out["nodes"].data_ptr(), out["semantic"].data_ptr(), out["score"].data_ptr(), out["count"].data_ptr(),
                 out["exp_nodes"].data_ptr() if want_cluster else null,
                 out["exp_semantic"].data_ptr() if want_cluster else null,
                 out["exp_kind"].data_ptr() if want_cluster else null,
                 out["exp_count"].data_ptr() if want_cluster else null,
                 out["seed_semantic"].data_ptr() if want_cluster else null,
-                _stream_ptr(dev)), "ahr_anchor_rerank")
+                _stream_ptr(dev))
+        with torch.cuda.device(dev):
+            if row_to_node is not None:
+                check(self.lib.ahr_anchor_rerank_rows(self._h, nq, ns, seed_nodes.data_ptr(), row_to_node.data_ptr(),
+                                                      int(row_to_node.numel()), seed_scores.data_ptr(), *tail),
+                      "ahr_anchor_rerank_rows")
+            else:
+                check(self.lib.ahr_anchor_rerank(self._h, nq, ns, seed_nodes.data_ptr(), seed_scores.data_ptr(), *tail),
+                      "ahr_anchor_rerank")
         return out
 
     def lca_closure(self, node_ids: Sequence[int]) -> torch.Tensor:

@@ -621,9 +621,8 @@ class HierarchicalGraph:
         else:
             qd = q.to(dev).to(torch.float32).contiguous()
             scores, rows = di["index"].topk(qd, k_eff, mode="exact")
-        seed_nodes = torch.where(rows >= 0, di["row_to_node"][rows.clamp(min=0)], torch.full_like(rows, -1, dtype=torch.int32))
-        out = csr.anchor_rerank(seed_nodes.to(torch.int32).contiguous(), scores, params, int(top_k),
-                                want_cluster=want_cluster)
+        # the index rows go straight into the expansion kernel: the row -> node lookup happens there
+        out = csr.anchor_rerank(rows, scores, params, int(top_k), want_cluster=want_cluster, row_to_node=di["row_to_node"])
         return out, rows
 
     def search_batch(self, query_embeddings, top_k: int = 5, member_top_m: int = 5,

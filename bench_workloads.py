@@ -61,6 +61,33 @@ def timed(fn, steps=5, warmup=3):
     return e0.elapsed_time(e1) / steps
 
 
+def timed_graph(fn, steps=20, warmup=3, inner=8):
+    """Device time of one call of ``fn``: ``inner`` calls captured into a CUDA graph (the library only enqueues on the
+    caller's stream), the graph replayed ``steps`` times between two events.  Takes the Python / ctypes launch cost
+    (~30 us per call here, more than the 20-30 us kernels being measured) out of the figure."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        fn()
+        st.synchronize()
+        with torch.cuda.graph(graph, stream=st):
+            for _ in range(inner):
+                fn()
+    torch.cuda.synchronize()
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (steps * inner)
+
+
 def run_c3x(dev):
     n, dim, nq, k = 10_000_000, 1024, 4096, 50
     X, Q = unit_bf16(n, dim, 1234, dev), unit_bf16(nq, dim, 5678, dev)
@@ -267,6 +294,7 @@ def run_c5(dev, scale=1.0):
     prm = engine.SearchParams(member_top_m=m)
     out = g.anchor_rerank(seeds, scores, prm, top_k)
     ms_anchor = timed(lambda: g.anchor_rerank(seeds, scores, prm, top_k, want_cluster=False), steps=20)
+    ms_anchor_dev = timed_graph(lambda: g.anchor_rerank(seeds, scores, prm, top_k, want_cluster=False))
     # hop 2: one expand per env on the first ids of the reranked list, ops uniform over {parents, children, related}
     ops = torch.randint(0, 3, (n_env,), generator=gen, device=dev).to(torch.int32)
     take = torch.where(ops == 2, 1, 2)
@@ -276,6 +304,7 @@ def run_c5(dev, scale=1.0):
     flat = torch.cat([sel[e, :int(t)] for e, t in enumerate(take.tolist())]).to(torch.int32).contiguous()
     oi, oc = g.expand(ops, flat, offs, limit)
     ms_expand = timed(lambda: g.expand(ops, flat, offs, limit), steps=50)
+    ms_expand_dev = timed_graph(lambda: g.expand(ops, flat, offs, limit))
     # uncapped-ish variant: limit 2048 lets the walk read whole neighbour lists (bandwidth view)
     oi2, oc2 = g.expand(ops, flat, offs, 2048)
     ms_expand_big = timed(lambda: g.expand(ops, flat, offs, 2048), steps=20)
@@ -322,6 +351,7 @@ def run_c5(dev, scale=1.0):
     print(json.dumps({"workload": f"c5: synthetic hierarchical graph {n} nodes / {a['n_edges']} edges (scale {scale}), 1024 envs x 50 seeds",
                       "graph_bytes": g.nbytes(), "build_s": round(time.time() - t0, 1),
                       "hop1_anchor_rerank_ms": ms_anchor, "hop1_envs_per_s": n_env / ms_anchor * 1e3,
+                      "hop1_device_ms_cuda_graph": ms_anchor_dev, "hop2_device_ms_cuda_graph": ms_expand_dev,
                       "hop2_expand_limit10_ms": ms_expand, "hop2_envs_per_s": n_env / ms_expand * 1e3,
                       "hop2_expand_limit2048_ms": ms_expand_big, "hop2_nodes_emitted": emitted,
                       "hop_bw_65536_nodes_ms": ms_bw, "hop_bw_algorithmic_bytes": bw_bytes,
@@ -520,6 +550,7 @@ def extra_c5(dist, world, rank, dev, scale=1.0, cpu_budget_s=6.0):
     prm = engine.SearchParams(member_top_m=m)
     out1 = g.anchor_rerank(seeds_l, scores_l, prm, top_k)
     ms_h1 = _timed_dist(dist, world, dev, lambda: g.anchor_rerank(seeds_l, scores_l, prm, top_k, want_cluster=False), steps=20)
+    ms_h1_dev = timed_graph(lambda: g.anchor_rerank(seeds_l, scores_l, prm, top_k, want_cluster=False))
     take = torch.where(ops_l == 2, 1, 2)
     offs = torch.zeros(n_env + 1, dtype=torch.int32, device=dev)
     offs[1:] = torch.cumsum(take, 0).to(torch.int32)
@@ -528,6 +559,7 @@ def extra_c5(dist, world, rank, dev, scale=1.0, cpu_budget_s=6.0):
     flat = first2[keep].to(torch.int32).contiguous()
     oi, oc = g.expand(ops_l, flat, offs, limit)
     ms_h2 = _timed_dist(dist, world, dev, lambda: g.expand(ops_l, flat, offs, limit), steps=50)
+    ms_h2_dev = timed_graph(lambda: g.expand(ops_l, flat, offs, limit))
     # both hops back to back (the per-batch cost of a rollout step that re-anchors)
     ms_both = _timed_dist(dist, world, dev, lambda: (g.anchor_rerank(seeds_l, scores_l, prm, top_k, want_cluster=False),
                                                      g.expand(ops_l, flat, offs, limit)), steps=20)
@@ -560,6 +592,9 @@ def extra_c5(dist, world, rank, dev, scale=1.0, cpu_budget_s=6.0):
                        f"{n_seeds} seeds; graph replicated on {world} GPU(s), {n_env} environments per GPU, no collective",
            "n_gpus": world, "graph_bytes": g.nbytes(),
            "hop1_anchor_rerank_ms": ms_h1, "hop2_expand_limit10_ms": ms_h2, "two_hops_ms": ms_both,
+           "hop1_device_ms_cuda_graph": ms_h1_dev, "hop2_device_ms_cuda_graph": ms_h2_dev,
+           "timing_note": "the *_ms figures are per call through Python/ctypes (launch-bound at ~30 us per call); "
+                          "*_device_ms_cuda_graph replay the same calls from a CUDA graph = device time",
            "envs_per_s_two_hops": n_env_total / ms_both * 1e3,
            "uncapped_walk": {"frontier_nodes_per_gpu": nb, "ms": ms_bw, "algorithmic_bytes_per_gpu": bw_bytes,
                              "useful_gbs_per_gpu": bw_bytes / (ms_bw * 1e-3) / 1e9,

@@ -134,7 +134,9 @@ int ahr_merge_topk_packed(int device, const void *dev_packed, int64_t record_byt
  *   judge_term  1/(1+exp(-judge/10)) evaluated by the host exactly as :766 does, 0.0 when absent
  *   conf        confidence, NaN when absent                                :753
  * The CSR arrays are borrowed (they must outlive the handle); the five attribute arrays are copied at create time into
- * one 32-byte record per node (one DRAM sector per touched node instead of five) and are not referenced afterwards.
+ * one 64-byte line per node together with the first 8 entries of the list a seed of that type expands into (belongs_to
+ * parents of an entity / members of a summary), so a seed costs one line instead of a chain of four dependent sectors;
+ * the attribute arrays are not referenced afterwards.
  * ---------------------------------------------------------------------------------------------- */
 int ahr_graph_create(ahr_graph **out, int device, int64_t n_nodes, const int64_t *const dev_row_ptr[AHR_N_CSR],
                      const int32_t *const dev_col_idx[AHR_N_CSR], const uint8_t *dev_node_type,
@@ -173,6 +175,19 @@ int ahr_anchor_rerank(ahr_graph *g, int32_t nq, int32_t n_seeds, const int32_t *
                       int32_t *dev_out_nodes, double *dev_out_semantic, double *dev_out_score,
                       int32_t *dev_out_count, int32_t *dev_exp_nodes, double *dev_exp_semantic,
                       uint8_t *dev_exp_kind, int32_t *dev_exp_count, double *dev_seed_semantic, void *stream);
+
+/*
+ * Same call fed straight from ahr_topk: dev_seed_rows [nq, n_seeds] are the int64 ids of an index created with
+ * id_base = 0 (index rows, -1 = empty slot), dev_row_to_node [n_rows] maps an index row to its dense node id (-1 = the
+ * indexed id is not a node of the graph) -- the lookup hierarchical_graph.py:731 does with G.nodes.get(nid).  Saves the
+ * gather / cast launches between the two kernels of a search.
+ */
+int ahr_anchor_rerank_rows(ahr_graph *g, int32_t nq, int32_t n_seeds, const int64_t *dev_seed_rows,
+                           const int32_t *dev_row_to_node, int64_t n_rows, const float *dev_seed_scores,
+                           const ahr_rerank_params *params, int32_t top_k, int32_t *dev_out_nodes,
+                           double *dev_out_semantic, double *dev_out_score, int32_t *dev_out_count, int32_t *dev_exp_nodes,
+                           double *dev_exp_semantic, uint8_t *dev_exp_kind, int32_t *dev_exp_count,
+                           double *dev_seed_semantic, void *stream);
 
 /*
  * Batched frontier expansion.  Replaces, for n_env environments at once,

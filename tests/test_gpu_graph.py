@@ -134,3 +134,76 @@ def test_batched_random_graph_vs_oracle(engine, seed):
         for e in range(n_env):
             want = ref_search.expand(og, names[ops[e]], [nodes[i] for i in ids[offs[e]:offs[e + 1]]], limit)
             assert [nodes[i] for i in out_ids[e, :out_cnt[e]]] == want
+
+
+def _random_csr(rng, n_ent, n_sum, n_hyp, hub_deg):
+    """CSR arrays built directly (dense ids: entities | summaries | hyperedges), with hub nodes whose lists are longer
+    than one round of the edge-parallel kernel (1024 / 2048 positions) and plenty of duplicates across segments."""
+    n = n_ent + n_sum + n_hyp
+    s0, h0 = n_ent, n_ent + n_sum
+
+    def csr(lists):
+        rp = np.zeros(n + 1, dtype=np.int64)
+        rp[1:] = np.cumsum([len(l) for l in lists])
+        return rp, (np.concatenate([np.asarray(l, dtype=np.int32) for l in lists]) if rp[-1] else np.zeros(0, np.int32))
+
+    def transpose(lists):
+        inv = [[] for _ in range(n)]
+        for u, l in enumerate(lists):
+            for v in l:
+                inv[int(v)].append(u)
+        return inv
+
+    bel = [[] for _ in range(n)]
+    for e in range(n_ent):
+        bel[e] = list(s0 + rng.choice(n_sum, size=int(rng.integers(1, 4)), replace=False))
+    for e in rng.choice(n_ent, size=min(n_ent, hub_deg), replace=False):  # summary s0 becomes a hub: hub_deg members
+        if s0 not in bel[e]:
+            bel[e].append(s0)
+    part = [[] for _ in range(n)]
+    for h in range(n_hyp):
+        for e in rng.choice(n_ent, size=int(rng.integers(2, 9)), replace=False):
+            part[int(e)].append(h0 + h)
+    rel = [[] for _ in range(n)]
+    for s_ in range(n_sum):
+        rel[s0 + s_] = list(s0 + rng.choice(n_sum, size=int(rng.integers(0, min(n_sum, 40))), replace=False))
+    rel[s0 + 1] = list(s0 + rng.permutation(n_sum))  # related hub
+    slots = [part, transpose(part), bel, transpose(bel), rel, transpose(rel)]
+    arrs = [csr(l) for l in slots]
+    nt = np.zeros(n, np.uint8)
+    nt[s0:h0] = 1
+    nt[h0:] = 2
+    return {"n_nodes": n, "row_ptr": [a[0] for a in arrs], "col_idx": [a[1] for a in arrs], "node_type": nt,
+            "level": np.zeros(n, np.uint8), "judge": np.full(n, np.nan), "judge_term": np.zeros(n), "conf": np.full(n, np.nan)}
+
+
+@pytest.mark.parametrize("limit", [65, 100, 512, 1024, 2048])
+def test_expand_large_limits_edge_parallel_kernel(limit):
+    """Limits above 64 take the edge-parallel kernel (one CTA per environment, rounds of 1024 / 2048 positions): hub nodes
+    with lists longer than a round, several input ids, duplicates across segments and rounds, the 2-hop related walk with
+    the excluded input node, ids outside the graph, empty inputs -- against the array oracle (environment.py:393-480)."""
+    from ah_rag_b200 import engine
+    from oracle import array_graph
+    rng = np.random.default_rng(limit)
+    a = _random_csr(rng, n_ent=6000, n_sum=1500, n_hyp=800, hub_deg=4500)
+    g = engine.GraphCSR(a)
+    n, s0 = a["n_nodes"], 6000
+    ops, ids, offs = [], [], [0]
+    for e in range(300):
+        op = e % 3
+        k = int(rng.integers(0, 5))
+        pick = [int(x) for x in rng.integers(0, n, size=k)]
+        if e % 7 == 0:
+            pick = [s0, s0 + 1] + pick            # the hubs first
+        if e % 11 == 0:
+            pick = pick + [s0, -1, n + 5, s0]     # repeated hub, ids outside the graph
+        ops.append(op)
+        ids += pick
+        offs.append(len(ids))
+    oi, oc = g.expand(torch.tensor(ops, dtype=torch.int32).cuda(), torch.tensor(ids, dtype=torch.int32).cuda(),
+                      torch.tensor(offs, dtype=torch.int32).cuda(), limit)
+    oi, oc = oi.cpu().numpy(), oc.cpu().numpy()
+    for e in range(300):
+        want = array_graph.expand(a, ops[e], ids[offs[e]:offs[e + 1]], limit)
+        assert list(oi[e, :oc[e]]) == want, (limit, e, ops[e])
+        assert (oi[e, oc[e]:] == -1).all()
