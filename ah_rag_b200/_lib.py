@@ -27,7 +27,7 @@ EXPORTS = [
     "ahr_topk_host", "ahr_merge_topk", "ahr_merge_topk_packed", "ahr_graph_create", "ahr_graph_destroy", "ahr_anchor_rerank", "ahr_anchor_rerank_rows", "ahr_expand",
     "ahr_debug_tc_scores", "ahr_rescore", "ahr_debug_round4", "ahr_exact_stats", "ahr_set_profiling",
     "ahr_get_profile", "ahr_env_reset", "ahr_env_step", "ahr_comm_create", "ahr_comm_export", "ahr_comm_connect",
-    "ahr_comm_destroy", "ahr_comm_begin", "ahr_comm_exchange_merge", "ahr_lca_closure",
+    "ahr_comm_destroy", "ahr_comm_begin", "ahr_comm_exchange_merge", "ahr_topk_sharded", "ahr_lca_closure",
 ]
 
 
@@ -82,6 +82,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.ahr_comm_destroy.argtypes = [vp]
     lib.ahr_comm_begin.argtypes = [vp, c_int32, c_int32, POINTER(vp), POINTER(vp)]
     lib.ahr_comm_exchange_merge.argtypes = [vp, c_int32, c_int32, vp, vp, vp]
+    lib.ahr_topk_sharded.argtypes = [vp, vp, vp, c_int32, c_int32, c_int, vp, vp, vp]
     lib.ahr_lca_closure.argtypes = [vp, POINTER(c_int32), c_int32, vp, POINTER(c_int64), vp]
     lib.ahr_env_step.argtypes = [vp, POINTER(EnvBatch), vp, c_int32, c_double, vp, vp, vp, vp, vp]
     for name in EXPORTS:

@@ -20,26 +20,40 @@ void set_error(const char *fmt, ...) {
   g_error = buf;
 }
 
-// grow-only device buffer
+// Grow-only device buffer.  Growing must not synchronise the device (cudaFree does): the superseded allocation is RETIRED
+// -- kept until the handle is destroyed -- and the new one is at least 1.5x the old, so the retired blocks of a handle add
+// up to less than twice its final workspace.  Kernels already enqueued on the old block keep a valid pointer.
 struct DevBuf {
   void *ptr = nullptr;
   size_t bytes = 0;
+  std::vector<void *> retired;
   int reserve(size_t need) {
     if (need <= bytes) return AHR_OK;
-    if (ptr) AHR_CUDA_CHECK(cudaFree(ptr));
-    ptr = nullptr;
-    bytes = 0;
+    need = std::max(need, bytes + bytes / 2);
     need = (need + 255) & ~(size_t)255;
-    cudaError_t e = cudaMalloc(&ptr, need);
+    void *fresh = nullptr;
+    cudaError_t e = cudaMalloc(&fresh, need);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      // out of memory: give the retired blocks back (this does synchronise) and try once more
+      for (void *r : retired) cudaFree(r);
+      retired.clear();
+      e = cudaMalloc(&fresh, need);
+    }
     if (e != cudaSuccess) {
       set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+      cudaGetLastError();
       return AHR_E_NOMEM;
     }
+    if (ptr) retired.push_back(ptr);
+    ptr = fresh;
     bytes = need;
     return AHR_OK;
   }
   void release() {
     if (ptr) cudaFree(ptr);
+    for (void *r : retired) cudaFree(r);
+    retired.clear();
     ptr = nullptr;
     bytes = 0;
   }
@@ -191,7 +205,7 @@ static int exact_bruteforce(ahr_index *idx, const void *dev_q, const int32_t *q_
 // Optional sample pass (AHR_TC_SEED_STRIDE=n): a 1/n sample of the corpus tiles is scored first and its k-th best score
 // per query seeds every list's admission threshold in the main pass (tc_shared.cuh: seed_threshold).
 static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, float *out_scores, int64_t *out_ids,
-                   float *dbg_scores, cudaStream_t st) {
+                   float *dbg_scores, cudaStream_t st, const PeerPush *push = nullptr) {
   AHR_REQUIRE(idx->has_map, "index is not TMA-addressable (dim %% 8 != 0 or rows not 16-byte aligned)");
   AHR_REQUIRE((reinterpret_cast<uintptr_t>(dev_q) & 15) == 0, "queries must be 16-byte aligned");
   const bool split = idx->dtype == AHR_DTYPE_F32;  // fp32 operands: hi + lo bf16 halves, 3 operand segments
@@ -303,8 +317,33 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
               total / n_lead, sum[1] / n_lead, sum[2] / n_lead, sum[0] / idx->sm_count, sum[4] / idx->sm_count,
               sum[5] / idx->sm_count, sum[6] / idx->sm_count, sum[7] / idx->sm_count);
   }
-  return select_topk(ps, pi, nullptr, (int64_t)S * k, (int64_t)S * k, nq, k, idx->id_base, false, out_scores, out_ids, st);
+  // per-query reduction of the S slab lists (each sorted, empties last): rank-counting merge for a few lists, bitonic
+  // selection otherwise; with `push` the result also goes to the peers of the sharded index from the same launch
+  if (merge_sorted_applicable(S, k, k))
+    return merge_sorted_lists(ps, pi, nullptr, (int64_t)S * k, S, k, k, k, nq, k, idx->id_base, out_scores, out_ids, push, st);
+  rc = select_topk(ps, pi, nullptr, (int64_t)S * k, (int64_t)S * k, nq, k, idx->id_base, false, out_scores, out_ids, st);
+  if (rc == AHR_OK && push != nullptr && push->world > 1) rc = peer_push_record(*push, (size_t)nq * k * 12, st);
+  return rc;
 }
+
+}  // extern "C"
+
+namespace ahr {
+int index_topk_bf16(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, float *dev_scores, int64_t *dev_ids,
+                    const PeerPush *push, cudaStream_t stream) {
+  AHR_REQUIRE(idx != nullptr && dev_q && dev_scores && dev_ids, "ahr_topk: NULL argument");
+  AHR_REQUIRE(nq >= 1 && k >= 1 && k <= 120, "AHR_MODE_BF16 supports 1 <= k <= 120 (got %d)", k);
+  DeviceGuard guard(idx->device);
+  if (idx->n_rows == 0) {
+    int rc = select_topk(dev_scores, nullptr, nullptr, 0, 0, nq, k, 0, false, dev_scores, dev_ids, stream);
+    if (rc == AHR_OK && push != nullptr && push->world > 1) rc = peer_push_record(*push, (size_t)nq * k * 12, stream);
+    return rc;
+  }
+  return tc_topk(idx, dev_q, nq, k, dev_scores, dev_ids, nullptr, stream, push);
+}
+}  // namespace ahr
+
+extern "C" {
 
 int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode, float *dev_scores, int64_t *dev_ids,
              void *stream) {
@@ -453,7 +492,11 @@ int ahr_merge_topk(int device, const float *dev_scores, const int64_t *dev_ids, 
   if (nq == 0) return AHR_OK;
   AHR_REQUIRE(dev_scores && dev_ids && dev_out_scores && dev_out_ids, "ahr_merge_topk: NULL buffer");
   DeviceGuard guard(device);
-  // [parts, nq, k]: candidate i = (part, j) of query q at q * k + part * (nq * k) + j
+  // [parts, nq, k]: candidate i = (part, j) of query q at q * k + part * (nq * k) + j.  The lists are the sorted outputs
+  // of ahr_topk (documented contract), so a few of them merge by rank counting.
+  if (merge_sorted_applicable(parts, k, k))
+    return merge_sorted_lists(dev_scores, nullptr, dev_ids, k, parts, k, (int64_t)nq * k, (int64_t)nq * k, nq, k, 0,
+                              dev_out_scores, dev_out_ids, nullptr, reinterpret_cast<cudaStream_t>(stream));
   return select_topk_strided(dev_scores, nullptr, dev_ids, k, (int64_t)parts * k, k, (int64_t)nq * k, nq, k, 0, false,
                              dev_out_scores, dev_out_ids, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -471,6 +514,9 @@ int ahr_merge_topk_packed(int device, const void *dev_packed, int64_t record_byt
   const float *scores = reinterpret_cast<const float *>(dev_packed);
   const int64_t *ids = reinterpret_cast<const int64_t *>(reinterpret_cast<const uint8_t *>(dev_packed) + sb);
   // part p: scores at + p * record_bytes / 4 floats, ids at + p * record_bytes / 8 int64
+  if (merge_sorted_applicable(parts, k, k))
+    return merge_sorted_lists(scores, nullptr, ids, k, parts, k, record_bytes / 4, record_bytes / 8, nq, k, 0, dev_out_scores,
+                              dev_out_ids, nullptr, reinterpret_cast<cudaStream_t>(stream));
   return select_topk_strided2(scores, nullptr, ids, k, (int64_t)parts * k, k, record_bytes / 4, record_bytes / 8, nq, k, 0,
                               false, dev_out_scores, dev_out_ids, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -645,19 +691,19 @@ int ahr_expand(ahr_graph *g, int32_t n_env, const int32_t *dev_ops, const int32_
 
 int ahr_lca_closure(ahr_graph *g, const int32_t *host_ids, int32_t n_ids, uint8_t *dev_out_flags, int64_t *n_result,
                     void *stream) {
-  AHR_REQUIRE(g && dev_out_flags && n_result, "ahr_lca_closure: NULL argument");
+  AHR_REQUIRE(g && dev_out_flags, "ahr_lca_closure: NULL argument");
   AHR_REQUIRE(n_ids >= 0 && (n_ids == 0 || host_ids != nullptr), "ahr_lca_closure: bad input list");
   for (int32_t i = 0; i < n_ids; ++i)
     AHR_REQUIRE(host_ids[i] >= 0 && host_ids[i] < g->view.n_nodes, "ahr_lca_closure: node id %d out of range", host_ids[i]);
   DeviceGuard guard(g->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  *n_result = 0;
+  if (n_result) *n_result = 0;
   if (g->view.n_nodes == 0) return AHR_OK;
   if (n_ids == 0) {  // set.intersection() of nothing: the reference returns no node (environment.py:276)
     AHR_CUDA_CHECK(cudaMemsetAsync(dev_out_flags, 0, (size_t)g->view.n_nodes, st));
     return AHR_OK;
   }
-  int rc = g->ws.reserve(graph_lca_workspace_bytes(g->view.n_nodes));
+  int rc = g->ws.reserve(graph_lca_workspace_bytes(g->view.n_nodes, n_ids));
   if (rc != AHR_OK) return rc;
   return graph_lca_closure(g->view, host_ids, n_ids, dev_out_flags, n_result, g->ws.ptr, st);
 }

@@ -30,10 +30,6 @@ constexpr int PUSH_THREADS = 256;
 constexpr int PUSH_BLOCKS_PER_PEER = 20;  // 140 blocks at 8 GPUs: about one per SM
 constexpr int MAX_WORLD = 16;
 
-struct PeerTable {
-  uint8_t *base[MAX_WORLD];  // peer allocations (base[rank] = own)
-};
-
 __device__ __forceinline__ void st_release_sys_u64(uint64_t *p, uint64_t v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -44,9 +40,9 @@ __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t *p) {
 }
 
 __global__ void __launch_bounds__(PUSH_THREADS)
-push_kernel(PeerTable peers, int rank, int world, size_t slot_off, size_t rec_bytes, size_t flag_off, uint64_t epoch,
-            unsigned int *done_counter) {
-  const uint8_t *src = peers.base[rank] + slot_off;
+push_kernel(PeerPush peers, size_t rec_bytes) {
+  const int rank = peers.rank, world = peers.world;
+  const uint8_t *src = peers.base[rank] + peers.slot_off;
   const size_t n16 = rec_bytes / 16;
   // every peer gets its own group of blocks, so all the peers are written concurrently (a loop over the peers left the
   // transfer latency-bound on one destination at a time: 25 us per peer, 175 us at 8 GPUs)
@@ -56,7 +52,7 @@ push_kernel(PeerTable peers, int rank, int world, size_t slot_off, size_t rec_by
   const int pi = blockIdx.x / per_peer, sub = blockIdx.x - pi * per_peer;
   if (pi < n_peers) {
     const int peer = pi < rank ? pi : pi + 1;
-    uint4 *dst4 = reinterpret_cast<uint4 *>(peers.base[peer] + slot_off);  // the peer's slot `rank`, over NVLink
+    uint4 *dst4 = reinterpret_cast<uint4 *>(peers.base[peer] + peers.slot_off);  // the peer's slot `rank`, over NVLink
     const size_t stride = (size_t)per_peer * PUSH_THREADS;
     size_t i = (size_t)sub * PUSH_THREADS + threadIdx.x;
     for (; i + 3 * stride < n16; i += 4 * stride) {  // four independent loads in flight per thread
@@ -68,13 +64,20 @@ push_kernel(PeerTable peers, int rank, int world, size_t slot_off, size_t rec_by
   __threadfence_system();
   __syncthreads();
   __shared__ bool last;
-  if (threadIdx.x == 0) last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) last = atomicAdd(peers.done_counter, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!last) return;
   __threadfence_system();
   if (threadIdx.x < world && (int)threadIdx.x != rank)
-    st_release_sys_u64(reinterpret_cast<uint64_t *>(peers.base[threadIdx.x] + flag_off) + rank, epoch);
-  if (threadIdx.x == 0) *done_counter = 0;  // ready for the next launch (stream-ordered)
+    st_release_sys_u64(reinterpret_cast<uint64_t *>(peers.base[threadIdx.x] + peers.flag_off) + rank, peers.epoch);
+  if (threadIdx.x == 0) *peers.done_counter = 0;  // ready for the next launch (stream-ordered)
+}
+
+// a rank that failed after it entered an exchange tells its peers so: they stop at once instead of waiting out the timeout
+constexpr uint64_t EPOCH_POISON = ~0ull;
+__global__ void poison_kernel(PeerPush peers) {
+  if ((int)threadIdx.x < peers.world && (int)threadIdx.x != peers.rank)
+    st_release_sys_u64(reinterpret_cast<uint64_t *>(peers.base[threadIdx.x] + peers.flag_off) + peers.rank, EPOCH_POISON);
 }
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -89,10 +92,12 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __global__ void wait_flags_kernel(const uint64_t *flags, int rank, int world, uint64_t epoch, unsigned long long timeout_ns) {
   if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
     const unsigned long long t0 = global_timer_ns();
-    while (ld_acquire_sys_u64(flags + threadIdx.x) < epoch) {
+    uint64_t seen;
+    while ((seen = ld_acquire_sys_u64(flags + threadIdx.x)) < epoch) {
       __nanosleep(64);
       if (global_timer_ns() - t0 > timeout_ns) __trap();
     }
+    if (seen == EPOCH_POISON) __trap();  // the peer failed inside this exchange: fail now, never merge stale data
   }
 }
 
@@ -191,64 +196,119 @@ int ahr_comm_destroy(ahr_comm *c) {
   return AHR_OK;
 }
 
+static PeerPush make_push(const ahr_comm *c, uint64_t epoch, size_t scores_bytes) {
+  PeerPush p;
+  for (int r = 0; r < c->world && r < 16; ++r) p.base[r] = c->peer[r];
+  p.rank = c->rank;
+  p.world = c->world;
+  const int half = (int)(epoch & 1);
+  p.slot_off = c->slot_offset(half, c->rank);
+  p.flag_off = c->flag_offset(half);
+  p.scores_bytes = scores_bytes;
+  p.epoch = epoch;
+  p.done_counter = c->done_counter;
+  return p;
+}
+
+}  // extern "C"
+
+namespace ahr {
+int peer_push_record(const PeerPush &push, size_t rec_bytes, cudaStream_t stream) {
+  if (push.world <= 1) return AHR_OK;
+  push_kernel<<<PUSH_BLOCKS_PER_PEER * (push.world - 1), PUSH_THREADS, 0, stream>>>(push, rec_bytes);
+  AHR_KERNEL_CHECK();
+  return AHR_OK;
+}
+}  // namespace ahr
+
+extern "C" {
+
+// wait for every peer's record of `epoch`, then merge the world slots of that half into out
+static int wait_and_merge(ahr_comm *c, uint64_t epoch, int32_t nq, int32_t k, float *dev_out_scores, int64_t *dev_out_ids,
+                          cudaStream_t st) {
+  const size_t sb = (size_t)nq * k * 4;
+  const int half = (int)(epoch & 1);
+  if (c->world > 1) {
+    wait_flags_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const uint64_t *>(c->base + c->flag_offset(half)), c->rank,
+                                        c->world, epoch, c->timeout_ns);
+    AHR_KERNEL_CHECK();
+  }
+  // k-way merge over the world slots of this half: part p at + p * max_record.  The slots are sorted lists.
+  const float *scores = reinterpret_cast<const float *>(c->base + c->slot_offset(half, 0));
+  const int64_t *ids = reinterpret_cast<const int64_t *>(c->base + c->slot_offset(half, 0) + sb);
+  if (merge_sorted_applicable(c->world, k, k))
+    return merge_sorted_lists(scores, nullptr, ids, k, c->world, k, (int64_t)(c->max_record / 4), (int64_t)(c->max_record / 8),
+                              nq, k, 0, dev_out_scores, dev_out_ids, nullptr, st);
+  return select_topk_strided2(scores, nullptr, ids, k, (int64_t)c->world * k, k, (int64_t)(c->max_record / 4),
+                              (int64_t)(c->max_record / 8), nq, k, 0, false, dev_out_scores, dev_out_ids, st);
+}
+
+static int check_exchange_shape(const ahr_comm *c, int32_t nq, int32_t k, const char *who) {
+  AHR_REQUIRE(c->connected, "%s: peers are not connected (ahr_comm_connect)", who);
+  AHR_REQUIRE(nq >= 1 && k >= 1, "%s: bad sizes nq=%d k=%d", who, nq, k);
+  const size_t sb = (size_t)nq * k * 4;
+  AHR_REQUIRE(sb % 16 == 0, "%s: nq * k must be a multiple of 4 (16-byte peer stores)", who);
+  AHR_REQUIRE(sb * 3 <= c->max_record, "%s: record of %zu bytes exceeds the buffer's %zu", who, sb * 3, c->max_record);
+  return AHR_OK;
+}
+
 int ahr_comm_begin(ahr_comm *c, int32_t nq, int32_t k, float **dev_slot_scores, int64_t **dev_slot_ids) {
   AHR_REQUIRE(c && dev_slot_scores && dev_slot_ids, "ahr_comm_begin: NULL argument");
-  AHR_REQUIRE(c->connected, "ahr_comm_begin: peers are not connected (ahr_comm_connect)");
-  AHR_REQUIRE(nq >= 1 && k >= 1, "ahr_comm_begin: bad sizes nq=%d k=%d", nq, k);
-  const size_t sb = (size_t)nq * k * 4, rec = sb * 3;
-  AHR_REQUIRE(sb % 16 == 0, "ahr_comm_begin: nq * k must be a multiple of 4 (16-byte peer stores)");
-  AHR_REQUIRE(rec <= c->max_record, "ahr_comm_begin: record of %zu bytes exceeds the buffer's %zu", rec, c->max_record);
-  c->epoch += 1;
-  const int half = (int)(c->epoch & 1);
+  int rc = check_exchange_shape(c, nq, k, "ahr_comm_begin");
+  if (rc != AHR_OK) return rc;
+  // the slot of the NEXT exchange; the epoch itself only advances in ahr_comm_exchange_merge, so a caller that fails
+  // between the two calls has not desynchronised the ranks
+  const int half = (int)((c->epoch + 1) & 1);
   uint8_t *slot = c->base + c->slot_offset(half, c->rank);
   *dev_slot_scores = reinterpret_cast<float *>(slot);
-  *dev_slot_ids = reinterpret_cast<int64_t *>(slot + sb);
+  *dev_slot_ids = reinterpret_cast<int64_t *>(slot + (size_t)nq * k * 4);
   return AHR_OK;
 }
 
 int ahr_comm_exchange_merge(ahr_comm *c, int32_t nq, int32_t k, float *dev_out_scores, int64_t *dev_out_ids, void *stream) {
   AHR_REQUIRE(c && dev_out_scores && dev_out_ids, "ahr_comm_exchange_merge: NULL argument");
-  AHR_REQUIRE(c->connected && c->epoch > 0, "ahr_comm_exchange_merge: call ahr_comm_begin first");
+  int rc = check_exchange_shape(c, nq, k, "ahr_comm_exchange_merge");
+  if (rc != AHR_OK) return rc;
   DeviceGuard guard(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t sb = (size_t)nq * k * 4, rec = sb * 3;
-  const int half = (int)(c->epoch & 1);
-  static const bool stats = getenv("AHR_COMM_STATS") != nullptr;  // debug: per-phase device times on stderr (synchronises)
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  if (stats)
-    for (auto &e : ev) AHR_CUDA_CHECK(cudaEventCreate(&e));
-  if (stats) AHR_CUDA_CHECK(cudaEventRecord(ev[0], st));
-  if (c->world > 1) {
-    PeerTable t;
-    for (int p = 0; p < MAX_WORLD; ++p) t.base[p] = p < c->world ? c->peer[p] : nullptr;
-    push_kernel<<<PUSH_BLOCKS_PER_PEER * (c->world - 1), PUSH_THREADS, 0, st>>>(t, c->rank, c->world, c->slot_offset(half, c->rank), rec,
-                                                      c->flag_offset(half), c->epoch, c->done_counter);
-    AHR_KERNEL_CHECK();
-    if (stats) AHR_CUDA_CHECK(cudaEventRecord(ev[1], st));
-    wait_flags_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const uint64_t *>(c->base + c->flag_offset(half)), c->rank,
-                                        c->world, c->epoch, c->timeout_ns);
-    AHR_KERNEL_CHECK();
-  } else if (stats) {
-    AHR_CUDA_CHECK(cudaEventRecord(ev[1], st));
-  }
-  if (stats) AHR_CUDA_CHECK(cudaEventRecord(ev[2], st));
-  // k-way merge over the world slots of this half: part p at + p * max_record
-  const float *scores = reinterpret_cast<const float *>(c->base + c->slot_offset(half, 0));
-  const int64_t *ids = reinterpret_cast<const int64_t *>(c->base + c->slot_offset(half, 0) + sb);
-  int rc = select_topk_strided2(scores, nullptr, ids, k, (int64_t)c->world * k, k, (int64_t)(c->max_record / 4),
-                                (int64_t)(c->max_record / 8), nq, k, 0, false, dev_out_scores, dev_out_ids, st);
-  if (stats && rc == AHR_OK) {
-    AHR_CUDA_CHECK(cudaEventRecord(ev[3], st));
-    AHR_CUDA_CHECK(cudaEventSynchronize(ev[3]));
-    float t_push = 0, t_wait = 0, t_merge = 0;
-    cudaEventElapsedTime(&t_push, ev[0], ev[1]);
-    cudaEventElapsedTime(&t_wait, ev[1], ev[2]);
-    cudaEventElapsedTime(&t_merge, ev[2], ev[3]);
-    fprintf(stderr, "[ahr comm stats] rank %d epoch %llu: push %.1f us (%.1f MB to %d peers), wait %.1f us, merge %.1f us\n",
-            c->rank, (unsigned long long)c->epoch, t_push * 1e3, rec / 1e6, c->world - 1, t_wait * 1e3, t_merge * 1e3);
-    for (auto &e : ev) cudaEventDestroy(e);
-  }
+  c->epoch += 1;
+  const PeerPush push = make_push(c, c->epoch, (size_t)nq * k * 4);
+  rc = peer_push_record(push, (size_t)nq * k * 12, st);
+  if (rc == AHR_OK) rc = wait_and_merge(c, c->epoch, nq, k, dev_out_scores, dev_out_ids, st);
   return rc;
+}
+
+int ahr_topk_sharded(ahr_index *idx, ahr_comm *c, const void *dev_q, int32_t nq, int32_t k, int mode, float *dev_out_scores,
+                     int64_t *dev_out_ids, void *stream) {
+  AHR_REQUIRE(idx && c && dev_q && dev_out_scores && dev_out_ids, "ahr_topk_sharded: NULL argument");
+  AHR_REQUIRE(mode == AHR_MODE_BF16 || mode == AHR_MODE_EXACT, "ahr_topk_sharded: unknown mode %d", mode);
+  int rc = check_exchange_shape(c, nq, k, "ahr_topk_sharded");  // everything that can be refused is refused BEFORE the epoch moves
+  if (rc != AHR_OK) return rc;
+  AHR_REQUIRE(mode != AHR_MODE_BF16 || k <= 120, "AHR_MODE_BF16 supports k <= 120 (got %d); use AHR_MODE_EXACT", k);
+  DeviceGuard guard(c->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  c->epoch += 1;
+  const uint64_t epoch = c->epoch;
+  const size_t sb = (size_t)nq * k * 4;
+  const PeerPush push = make_push(c, epoch, sb);
+  uint8_t *slot = c->base + push.slot_off;
+  float *slot_s = reinterpret_cast<float *>(slot);
+  int64_t *slot_i = reinterpret_cast<int64_t *>(slot + sb);
+  if (mode == AHR_MODE_BF16) {
+    // the reduction of the slab lists writes this rank's slot AND the peers' copies of it, and publishes the flags
+    rc = index_topk_bf16(idx, dev_q, nq, k, slot_s, slot_i, &push, st);
+  } else {
+    rc = ahr_topk(idx, dev_q, nq, k, mode, slot_s, slot_i, stream);
+    if (rc == AHR_OK) rc = peer_push_record(push, sb * 3, st);
+  }
+  if (rc != AHR_OK) {
+    // this rank cannot deliver: tell the peers (they trap at once instead of waiting out AHR_COMM_TIMEOUT_S)
+    const std::string why = ahr_last_error();
+    if (c->world > 1) poison_kernel<<<1, 32, 0, st>>>(push);
+    set_error("%s", why.c_str());
+    return rc;
+  }
+  return wait_and_merge(c, epoch, nq, k, dev_out_scores, dev_out_ids, st);
 }
 
 }  // extern "C"

@@ -45,6 +45,28 @@ int select_topk_strided2(const float *cand_scores, const int32_t *cand_ids32, co
                          int32_t k, int64_t id_offset, bool carry_in, float *out_scores, int64_t *out_ids,
                          cudaStream_t stream);
 constexpr int SELECT_MAX_K = 1024;
+// Peer destinations of a fused "reduce + push" launch (exchange.cu fills it from an ahr_comm): slot `rank` of every peer's
+// exchange buffer receives this rank's [nq, k] result, the last block publishes `epoch` into the peers' flags.
+struct PeerPush {
+  uint8_t *base[16] = {};   // mapped peer allocations (base[rank] = own)
+  int rank = 0, world = 1;
+  size_t slot_off = 0;      // byte offset of slot `rank` of the current half inside every allocation
+  size_t flag_off = 0;      // byte offset of the current half's flag array
+  size_t scores_bytes = 0;  // nq * k * 4: the ids of a record start there
+  uint64_t epoch = 0;
+  unsigned int *done_counter = nullptr;
+};
+// Merge of n_lists SORTED lists per query (valid entries first, (score desc, id asc)): list g, slot j of query q at
+// q * stride + g * stride_list + j (ids: stride_list_ids).  Optionally pushes the result to the peers (PeerPush).
+bool merge_sorted_applicable(int32_t n_lists, int32_t k_in, int32_t k);
+int merge_sorted_lists(const float *cand_scores, const int32_t *cand_ids32, const int64_t *cand_ids64, int64_t stride,
+                       int32_t n_lists, int32_t k_in, int64_t stride_list, int64_t stride_list_ids, int32_t nq, int32_t k,
+                       int64_t id_offset, float *out_scores, int64_t *out_ids, const PeerPush *push, cudaStream_t stream);
+// exchange.cu: the stand-alone push of a finished record (shapes the fused reduction does not take, fp32-exact mode)
+int peer_push_record(const PeerPush &push, size_t rec_bytes, cudaStream_t stream);
+// the bf16-mode top-k of an index with the final reduction pushing to the peers (api.cu; used by ahr_topk_sharded)
+int index_topk_bf16(struct ::ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, float *dev_scores, int64_t *dev_ids,
+                    const PeerPush *push, cudaStream_t stream);
 
 // ---- topk_exact.cu (K1x) ----
 // canonical scores of rows [row0, row0 + n_chunk) for the queries listed in q_sel (or all nq when q_sel == nullptr):
@@ -111,7 +133,7 @@ int graph_pack_nodes(int64_t n_nodes, const uint8_t *node_type, const uint8_t *l
                      const int32_t *const col_idx[AHR_N_CSR], NodeLine *out, cudaStream_t stream);
 
 // ---- lca.cu ----
-size_t graph_lca_workspace_bytes(int64_t n_nodes);
+size_t graph_lca_workspace_bytes(int64_t n_nodes, int32_t n_ids);
 int graph_lca_closure(const GraphView &g, const int32_t *host_ids, int32_t n_ids, uint8_t *out_flags, int64_t *n_result,
                       void *workspace, cudaStream_t stream);
 

@@ -11,6 +11,7 @@ the ``Collection.query`` seam (hierarchical_graph.py:714).
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -98,7 +99,9 @@ class ShardedIndex:
         nq = int(q.shape[0])
         peer = getattr(self, "peer", None)
         if peer is not None and (nq * k) % 4 == 0 and nq * k * 12 <= peer.max_record_bytes:
-            # the local top-k writes straight into this rank's slot; the slot is stored into every peer's buffer
+            # one library call: local top-k, its slab reduction storing into every peer's buffer, wait, merge
+            if os.environ.get("AHR_EXCHANGE_FUSED", "1") != "0":
+                return peer.topk_sharded(self.index, q, k, mode)
             ps, pi = peer.begin(nq, k)
             self.index.topk_raw(q, k, mode, ps, pi)
             return peer.exchange_merge(nq, k)

@@ -330,12 +330,10 @@ class GraphCSR:
         over belongs_to and have no belongs_to parent with the same property (``ahr_lca_closure``)."""
         ids = (ctypes.c_int32 * max(1, len(node_ids)))(*[int(v) for v in node_ids])
         flags = torch.empty((self.n_nodes,), dtype=torch.uint8, device=self.device)
-        n = ctypes.c_int64()
         with torch.cuda.device(self.device):
-            check(self.lib.ahr_lca_closure(self._h, ids, len(node_ids), flags.data_ptr(), ctypes.byref(n),
-                                           _stream_ptr(self.device)), "ahr_lca_closure")
-        if n.value == 0:
-            return torch.empty((0,), dtype=torch.int64, device=self.device)
+            # no count requested: the library call is asynchronous, torch.nonzero below is the one synchronisation
+            check(self.lib.ahr_lca_closure(self._h, ids, len(node_ids), flags.data_ptr(), None, _stream_ptr(self.device)),
+                  "ahr_lca_closure")
         return torch.nonzero(flags, as_tuple=False).view(-1)
 
     def expand(self, ops: torch.Tensor, in_ids: torch.Tensor, in_offsets: torch.Tensor, limit: int = 10
@@ -418,6 +416,44 @@ class EnvBatchState:
         self._ready = True
         return self.features, self.mask
 
+    def capture_rollout(self, rerank: Dict[str, torch.Tensor], n_seeds: int, actions: torch.Tensor):
+        """Reset + ``T`` steps as ONE CUDA graph (``actions``: int32 [T, B] on the device, read at replay time, so a policy
+        can overwrite it between replays).  The seven launches of a 6-step episode are 8-15 us of device time each but
+        ~90 us of Python / driver launch cost when issued one by one; a replay is a single submission.
+        Returns ``(replay, out)``: ``replay()`` enqueues the episode on the current stream, ``out`` holds the per-step
+        results it overwrites -- features [T + 1, B, 84] (index 0 = after reset), rewards [T, B], done [T, B], mask
+        [T + 1, B, 6]."""
+        _require_cuda(actions, "actions")
+        if actions.dtype != torch.int32 or actions.dim() != 2 or int(actions.shape[1]) != self.n_envs:
+            raise ValueError(f"actions must be int32 [T, {self.n_envs}]")
+        T, B, dev = int(actions.shape[0]), self.n_envs, self.csr.device
+        out = {"features": torch.zeros((T + 1, B, self.FEATS), dtype=torch.float32, device=dev),
+               "mask": torch.zeros((T + 1, B, self.N_ACTIONS), dtype=torch.uint8, device=dev),
+               "rewards": torch.zeros((T, B), dtype=torch.float64, device=dev),
+               "done": torch.zeros((T, B), dtype=torch.uint8, device=dev)}
+
+        def episode():
+            f, m = self.reset(rerank, n_seeds)
+            out["features"][0].copy_(f)
+            out["mask"][0].copy_(m)
+            for t in range(T):
+                f, r, d, m = self.step(actions[t])
+                out["features"][t + 1].copy_(f)
+                out["mask"][t + 1].copy_(m)
+                out["rewards"][t].copy_(r)
+                out["done"][t].copy_(d)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            episode()  # warm-up outside the capture (first-use attribute settings, lazy module loads)
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                episode()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        return graph.replay, out
+
     def step(self, actions: torch.Tensor):
         """``actions`` int32 [B] on the device, values 0..5 (gym_env.py:14-20)."""
         if not self._ready:
@@ -487,6 +523,20 @@ class PeerExchange:
         ps, pi = ctypes.c_void_p(), ctypes.c_void_p()
         check(self.lib.ahr_comm_begin(self._h, int(nq), int(k), ctypes.byref(ps), ctypes.byref(pi)), "ahr_comm_begin")
         return int(ps.value), int(pi.value)
+
+    def topk_sharded(self, index: "VectorIndex", q: torch.Tensor, k: int, mode: str = "bf16") -> Tuple[torch.Tensor, torch.Tensor]:
+        """Local top-k over ``index`` (this rank's node range), exchange with the peers, merge -- one library call
+        (``ahr_topk_sharded``: the slab reduction of the local top-k pushes to the peers itself)."""
+        _require_cuda(q, "q")
+        if q.dim() != 2 or q.shape[1] != index.dim or q.dtype != index.dtype:
+            raise ValueError(f"q must be [nq, {index.dim}] {index.dtype}")
+        nq = int(q.shape[0])
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_topk_sharded(index._h, self._h, q.data_ptr(), nq, int(k), index._mode(mode), out_s.data_ptr(),
+                                            out_i.data_ptr(), _stream_ptr(self.device)), "ahr_topk_sharded")
+        return out_s, out_i
 
     def exchange_merge(self, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Push this rank's slot to the peers, wait for theirs, merge: [nq, k] results, identical on every rank."""

@@ -587,6 +587,8 @@ def extra_c5(dist, world, rank, dev, scale=1.0, cpu_budget_s=6.0):
             envb.step(acts[t])
 
     ms_roll = _timed_dist(dist, world, dev, rollout, steps=20)
+    replay, _ = envb.capture_rollout(rr5, 5, torch.stack(acts))
+    ms_roll_graph = _timed_dist(dist, world, dev, replay, steps=20)
     envb.check_overflow()
     out = {"workload": f"c5: synthetic hierarchical graph {a['n_nodes']} nodes / {a['n_edges']} edges, {n_env_total} environments x "
                        f"{n_seeds} seeds; graph replicated on {world} GPU(s), {n_env} environments per GPU, no collective",
@@ -600,6 +602,7 @@ def extra_c5(dist, world, rank, dev, scale=1.0, cpu_budget_s=6.0):
                              "useful_gbs_per_gpu": bw_bytes / (ms_bw * 1e-3) / 1e9,
                              "frac_of_hbm": bw_bytes / (ms_bw * 1e-3) / 1e9 / hbm},
            "gym_rollout_reset_plus_6_steps_ms": ms_roll, "gym_env_steps_per_s": n_env_total * 6 / ms_roll * 1e3,
+           "gym_rollout_cuda_graph_ms": ms_roll_graph, "gym_env_steps_per_s_cuda_graph": n_env_total * 6 / ms_roll_graph * 1e3,
            "hbm_peak_gbs": hbm, "peak_source": src}
     if rank == 0:
         from oracle import array_graph, cpu_graph_baseline  # checker + reported CPU baseline, never the measured path

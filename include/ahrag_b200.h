@@ -111,7 +111,8 @@ int ahr_topk_host(ahr_index *idx, const void *host_q, int32_t nq, int32_t k, int
 
 /*
  * k-way merge of `parts` candidate lists per query (multi-GPU: the lists all-gathered from the
- * node-range shards).  dev_scores/dev_ids: [parts, nq, k]; entries with id < 0 are ignored.
+ * node-range shards).  dev_scores/dev_ids: [parts, nq, k], every list sorted by (score desc, id asc) with its empty
+ * entries (id < 0) at the end, exactly as ahr_topk writes it.
  * Output [nq, k] sorted by (score desc, id asc) -- identical for every sharding of the same corpus.
  */
 int ahr_merge_topk(int device, const float *dev_scores, const int64_t *dev_ids, int32_t parts, int32_t nq,
@@ -207,10 +208,11 @@ int ahr_expand(ahr_graph *g, int32_t n_env, const int32_t *dev_ops, const int32_
  * Closure step of GraphEnvironment.expand_to_lca (src/ah_rag/agent/environment.py:243-299) over the belongs_to CSRs:
  * for every input node the set of nodes below it (transitive members, itself included -- what nx.ancestors yields on
  * child -> parent edges), the intersection of those sets, and of it the nodes without a belongs_to parent inside it.
- * host_ids [n_ids]: dense node ids on the HOST (a handful per call).  dev_out_flags [n_nodes] u8: 1 = result node;
- * *n_result: how many.  Synchronises the stream (one host round trip per BFS level).  The caller orders the result
- * ((level or 1, node id), environment.py:283) and checks that every input has a belongs_to edge (nx.ancestors raises
- * otherwise).
+ * host_ids [n_ids]: dense node ids on the HOST (a handful per call; copied before the call returns).  dev_out_flags
+ * [n_nodes] u8: 1 = result node.  The walk is two launches on the caller's stream (all inputs and all BFS levels in one
+ * kernel).  n_result may be NULL: the call is then fully asynchronous; otherwise the count of result nodes is read back,
+ * which synchronises the stream once.  The caller orders the result ((level or 1, node id), environment.py:283) and checks
+ * that every input has a belongs_to edge (nx.ancestors raises otherwise).
  */
 int ahr_lca_closure(ahr_graph *g, const int32_t *host_ids, int32_t n_ids, uint8_t *dev_out_flags, int64_t *n_result,
                     void *stream);
@@ -267,10 +269,21 @@ int ahr_comm_create(ahr_comm **out, int device, int rank, int world, int64_t max
 int ahr_comm_export(ahr_comm *c, void *handle_out /* AHR_IPC_HANDLE_BYTES */);
 int ahr_comm_connect(ahr_comm *c, const void *all_handles /* world x AHR_IPC_HANDLE_BYTES, rank order */);
 int ahr_comm_destroy(ahr_comm *c);
-/* start an exchange of [nq, k] lists (nq*k %% 4 == 0): returns device pointers to this rank's slot */
+/* start an exchange of [nq, k] lists (nq*k %% 4 == 0): returns device pointers to this rank's slot of the NEXT exchange
+ * (the exchange counter only advances in ahr_comm_exchange_merge / ahr_topk_sharded) */
 int ahr_comm_begin(ahr_comm *c, int32_t nq, int32_t k, float **dev_slot_scores, int64_t **dev_slot_ids);
 /* push the slot to every peer, wait for every peer's slot of this exchange, merge: out [nq, k] identical on all ranks */
 int ahr_comm_exchange_merge(ahr_comm *c, int32_t nq, int32_t k, float *dev_out_scores, int64_t *dev_out_ids, void *stream);
+/*
+ * The whole sharded query in one call: local top-k over this rank's node range (ids = id_base + row), exchange, merge;
+ * out [nq, k] identical on every rank and for every shard count.  In AHR_MODE_BF16 the kernel that reduces the slab lists
+ * of the local top-k stores its result straight into the peers' buffers and publishes the flags (no separate push
+ * launch); the merge is a rank-counting merge of the `world` sorted lists.  Arguments are validated before the exchange
+ * counter moves; a rank that fails afterwards poisons its flags so that the peers stop at once.  Every rank must call it
+ * with the same nq, k and mode.
+ */
+int ahr_topk_sharded(ahr_index *idx, ahr_comm *c, const void *dev_q, int32_t nq, int32_t k, int mode, float *dev_out_scores,
+                     int64_t *dev_out_ids, void *stream);
 
 /* ---- diagnostics used by the parity tests (not part of the reference seam) ---------------------- */
 /* full [nq, n_rows] score matrix of the tensor-core path (small inputs only) */

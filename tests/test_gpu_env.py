@@ -129,3 +129,43 @@ def test_collect_rollouts_matches_sequential_oracle_episodes(tmp_path):
         assert int(out["episode_length"][b]) == t and not alive[t:, b].any() and (acts[t:, b] == 5).all()
         assert float(out["episode_reward"][b]) == pytest.approx(total, abs=1e-12)
         assert np.array_equal(out["final_obs"][b].cpu().numpy().view(np.uint32), vec.view(np.uint32))
+
+
+def test_rollout_captured_in_a_cuda_graph_equals_step_by_step(tmp_path):
+    """EnvBatchState.capture_rollout: reset + T steps as one CUDA graph; a replay (also with NEW actions written into the
+    captured buffer) reproduces, bit for bit, what the same calls give when issued one by one."""
+    import torch
+    from ah_rag_b200 import engine
+    nl = synth.make_graph(seed=33, n_entities=300, n_l1=20, n_l2=3, n_hyperedges=200, related_density=0.3)
+    og = ref_search.OracleGraph(copy.deepcopy(nl))
+    from ah_rag_b200 import csr as csr_mod
+    arrays = csr_mod.csr_from_networkx(og.G)
+    g = engine.GraphCSR(arrays)
+    rng = np.random.default_rng(5)
+    B, T = 130, 6
+    idx_nodes = np.array([i for i, t in enumerate(arrays["node_type"]) if t in (0, 1)], dtype=np.int32)
+    seeds = torch.from_numpy(np.stack([rng.choice(idx_nodes, 5, replace=False) for _ in range(B)])).cuda()
+    scores = torch.from_numpy(np.sort(rng.uniform(0.1, 0.9, (B, 5)).astype(np.float32), axis=1)[:, ::-1].copy()).cuda()
+    rr = g.anchor_rerank(seeds, scores, engine.SearchParams(member_top_m=5), 5, want_cluster=False)
+    for trial in range(2):
+        acts = torch.from_numpy(rng.integers(0, 5, (T, B)).astype(np.int32)).cuda()
+        ref_env = engine.EnvBatchState(g, B, max_steps=T)
+        want = {"features": [], "rewards": [], "done": [], "mask": []}
+        f, m = ref_env.reset(rr, 5)
+        want["features"].append(f.clone()); want["mask"].append(m.clone())
+        for t in range(T):
+            f, r, d, m = ref_env.step(acts[t])
+            want["features"].append(f.clone()); want["mask"].append(m.clone())
+            want["rewards"].append(r.clone()); want["done"].append(d.clone())
+        if trial == 0:
+            env = engine.EnvBatchState(g, B, max_steps=T)
+            buf = acts.clone()
+            replay, out = env.capture_rollout(rr, 5, buf)
+        else:
+            buf.copy_(acts)  # a policy writing new actions into the captured buffer
+        replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out["features"].view(torch.int32), torch.stack(want["features"]).view(torch.int32))
+        assert torch.equal(out["mask"], torch.stack(want["mask"]))
+        assert torch.equal(out["rewards"], torch.stack(want["rewards"])) and torch.equal(out["done"], torch.stack(want["done"]))
+        env.check_overflow()

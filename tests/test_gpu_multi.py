@@ -33,10 +33,11 @@ def _worker(rank, world, port, q):
         full = engine.VectorIndex(X)
         sh = ShardedIndex.from_rows(X[lo:hi].contiguous(), id_base=lo)
         problems = []
-        for use_peer in (False, True):
-            if use_peer and not sh.enable_peer_exchange(512, k):
+        for use_peer in (False, "separate push launch", "push fused into the slab reduction"):
+            if use_peer and getattr(sh, "peer", None) is None and not sh.enable_peer_exchange(512, k):
                 problems.append("peer exchange not enabled")
                 break
+            os.environ["AHR_EXCHANGE_FUSED"] = "0" if use_peer == "separate push launch" else "1"
             # several exchanges back to back without host synchronisation: exercises the two buffer halves / epochs
             outs, wants = [], []
             for it, nq in enumerate((64, 300, 8, 512, 128, 4)):
@@ -87,6 +88,14 @@ def test_peer_exchange_single_rank():
         s, i = ex.exchange_merge(nq, k)
         ws, wi = idx.topk(Q, k, "bf16")
         assert torch.equal(i, wi) and torch.equal(s, ws)
+    for mode in ("bf16", "exact", "bf16"):  # the one-call form (ahr_topk_sharded)
+        s, i = ex.topk_sharded(idx, Q, k, mode)
+        ws, wi = idx.topk(Q, k, mode)
+        assert torch.equal(i, wi) and torch.equal(s, ws)
+    with pytest.raises(RuntimeError):
+        ex.topk_sharded(idx, torch.cat([Q] * 4), k, "bf16")  # refused BEFORE the exchange counter moves
+    s, i = ex.topk_sharded(idx, Q, k, "bf16")
+    assert torch.equal(i, wi)
     with pytest.raises(RuntimeError):
         ex.begin(nq * 4, k)  # record larger than the buffer
     with pytest.raises(RuntimeError):

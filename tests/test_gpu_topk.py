@@ -242,3 +242,26 @@ def test_certification_bound_holds_on_same_sign_inputs(engine, kind, dim):
     s, i = idx.topk(Q, k, mode="exact")
     rs, ri = exact.exact_topk(_bits(X), _bits(Q), k)
     assert np.array_equal(i.cpu().numpy(), ri) and np.array_equal(s.cpu().numpy().view(np.uint32), rs.view(np.uint32))
+
+
+@pytest.mark.parametrize("parts,k,nq", [(2, 50, 300), (8, 50, 64), (16, 100, 9), (3, 5, 1), (1, 50, 17)])
+def test_merge_of_sorted_lists_equals_oracle_merge(engine, parts, k, nq):
+    """ahr_merge_topk over per-shard SORTED lists takes the rank-counting merge kernel: ragged lists (empties at the end),
+    exact score ties across lists (lower id first), every list empty, k larger than the number of candidates."""
+    rng = np.random.default_rng(parts * 100 + k)
+    scores = np.full((parts, nq, k), -np.inf, dtype=np.float32)
+    ids = np.full((parts, nq, k), -1, dtype=np.int64)
+    pool = rng.choice(np.round(rng.uniform(-1, 1, 64), 2).astype(np.float32), size=(parts, nq, k))  # many ties
+    for p in range(parts):
+        for q in range(nq):
+            n = int(rng.integers(0, k + 1)) if (p + q) % 3 else k
+            if q == 0:
+                n = 0  # a query without any candidate
+            row_ids = rng.choice(10_000, size=n, replace=False).astype(np.int64) * parts + p  # unique across lists
+            order = np.lexsort((row_ids, -pool[p, q, :n].astype(np.float64)))
+            scores[p, q, :n] = pool[p, q, :n][order]
+            ids[p, q, :n] = row_ids[order]
+    ms, mi = engine.merge_topk(torch.from_numpy(scores).cuda(), torch.from_numpy(ids).cuda())
+    ws, wi = exact.merge_topk([scores[p] for p in range(parts)], [ids[p] for p in range(parts)], k)
+    assert np.array_equal(mi.cpu().numpy(), wi)
+    assert np.array_equal(ms.cpu().numpy().view(np.uint32), ws.view(np.uint32))
