@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libahrag_b200.so")
-SOURCES = ["api.cu", "topk_tc.cu", "topk_tc2.cu", "topk_exact.cu", "select.cu", "graph.cu", "env.cu", "exchange.cu", "lca.cu"]
+SOURCES = ["api.cu", "topk_tc.cu", "topk_tc2.cu", "topk_exact.cu", "select.cu", "graph.cu", "env.cu", "exchange.cu", "lca.cu", "graph_shard.cu"]
 HEADERS = ["common.cuh", "kernels.h", "tc_shared.cuh", "graph_shared.cuh", os.path.join("..", "..", "include", "ahrag_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -33,10 +33,23 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB_PATH
-    nvcc = _nvcc()
+    """Compile and link under an inter-process lock (every rank of a torchrun job may find the library stale at the
+    same moment); the library is linked to a temporary name and renamed into place, so no process ever maps a
+    half-written file."""
+    import fcntl
     os.makedirs(LIB_DIR, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another process built it while we waited
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
+    nvcc = _nvcc()
     obj_dir = os.path.join(HERE, "build")
     os.makedirs(obj_dir, exist_ok=True)
     env = dict(os.environ)
@@ -60,10 +73,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", *ccbin, "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", *ccbin, "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

@@ -19,6 +19,8 @@ NT_ENTITY, NT_SUMMARY, NT_HYPEREDGE, NT_OTHER = 0, 1, 2, 3
 EK_SEED, EK_PARENT, EK_MEMBER = 1, 2, 3
 OP_PARENTS, OP_CHILDREN, OP_RELATED = 0, 1, 2
 
+ABI_VERSION = 200  # AHR_VERSION of include/ahrag_b200.h this binding was written against
+
 # every symbol include/ahrag_b200.h declares (tests/test_abi.py checks the header against this list)
 AHR_IPC_HANDLE_BYTES = 64
 
@@ -28,6 +30,8 @@ EXPORTS = [
     "ahr_debug_tc_scores", "ahr_rescore", "ahr_debug_round4", "ahr_exact_stats", "ahr_set_profiling",
     "ahr_get_profile", "ahr_env_reset", "ahr_env_step", "ahr_comm_create", "ahr_comm_export", "ahr_comm_connect",
     "ahr_comm_destroy", "ahr_comm_begin", "ahr_comm_exchange_merge", "ahr_topk_sharded", "ahr_lca_closure",
+    "ahr_graph_shard_create", "ahr_graph_shard_destroy", "ahr_expand_shard_record_ints", "ahr_expand_shard_stage1",
+    "ahr_expand_shard_stage2", "ahr_expand_shard_merge",
 ]
 
 
@@ -83,12 +87,19 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.ahr_comm_begin.argtypes = [vp, c_int32, c_int32, POINTER(vp), POINTER(vp)]
     lib.ahr_comm_exchange_merge.argtypes = [vp, c_int32, c_int32, vp, vp, vp]
     lib.ahr_topk_sharded.argtypes = [vp, vp, vp, c_int32, c_int32, c_int, vp, vp, vp]
+    lib.ahr_graph_shard_create.argtypes = [POINTER(vp), c_int, c_int64, c_int64, c_int64, POINTER(vp), POINTER(vp), vp]
+    lib.ahr_graph_shard_destroy.argtypes = [vp]
+    lib.ahr_expand_shard_record_ints.argtypes = [c_int32, c_int32, c_int32]
+    lib.ahr_expand_shard_stage1.argtypes = [vp, c_int32, vp, vp, vp, c_int32, c_int32, vp, vp]
+    lib.ahr_expand_shard_stage2.argtypes = [vp, c_int32, c_int32, vp, vp, vp, vp, c_int32, c_int32, vp, vp, vp]
+    lib.ahr_expand_shard_merge.argtypes = [c_int, c_int64, c_int32, c_int32, vp, vp, vp, vp, c_int32, c_int32, vp, vp, vp, vp, vp]
     lib.ahr_lca_closure.argtypes = [vp, POINTER(c_int32), c_int32, vp, POINTER(c_int64), vp]
     lib.ahr_env_step.argtypes = [vp, POINTER(EnvBatch), vp, c_int32, c_double, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("ahr_last_error", "ahr_launch_count"):
+        if name not in ("ahr_last_error", "ahr_launch_count", "ahr_expand_shard_record_ints"):
             fn.restype = c_int
+    lib.ahr_expand_shard_record_ints.restype = c_int64
 
 
 _lib = None
@@ -112,6 +123,10 @@ def load() -> ctypes.CDLL:
                         f"({e}); run `python -c 'import __graft_entry__ as g; g.build()'` on a machine with nvcc. "
                         "There is no CPU fallback.") from e
         lib = ctypes.CDLL(_build.LIB_PATH)
+        lib.ahr_version.restype = c_int
+        if lib.ahr_version() != ABI_VERSION:  # a stale library against newer ctypes declarations is an ABI mismatch
+            raise ImportError(f"ah_rag_b200: {_build.LIB_PATH} is ABI version {lib.ahr_version()}, the Python side expects "
+                              f"{ABI_VERSION}; rebuild with `python -c 'import __graft_entry__ as g; g.build()'`")
         _declare(lib)
         _lib = lib
     return _lib

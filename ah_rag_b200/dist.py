@@ -120,3 +120,52 @@ class ShardedIndex:
         dist.all_gather_into_tensor(gathered, mine, group=self.group)  # the single exchange of the path
         all_s, all_i = unpack_candidates(gathered, self.world, nq, k)
         return self.merge(all_s, all_i)
+
+
+class ShardedGraph:
+    """Frontier expansion over a CSR sharded by node range (SURVEY section 8e option B; csrc/graph_shard.cu).
+
+    Rank r owns the adjacency rows of the dense ids ``[bounds[r], bounds[r + 1])``; the batch inputs are replicated.
+    ``expand`` = stage 1 on the owners of the input nodes, all-gather, stage 2 on the owners of the hyperedges (the 2-hop
+    part of ``expand_related``), all-gather, merge -- two small collectives per call (the path's real exchange steps),
+    results bit-identical to ``GraphCSR.expand`` on the whole graph, on every rank.
+
+    ``stage1(ops, ids, offs, max_ids, limit) -> records``, ``stage2(world, bounds, ops, ids, offs, max_ids, limit, g1) ->
+    records`` and ``merge(world, bounds, ops, ids, offs, max_ids, limit, g1, g2) -> (ids, counts)`` are injectable so the
+    plumbing can be tested on CPU with gloo; in production they are the methods of ``engine.GraphShard``."""
+
+    def __init__(self, stage1: Callable, stage2: Callable, merge: Callable, bounds, group: Optional[dist.ProcessGroup] = None) -> None:
+        self.stage1, self.stage2, self.merge = stage1, stage2, merge
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.bounds = bounds  # int64 [world + 1] on the compute device
+
+    @classmethod
+    def from_arrays(cls, arrays, device, group: Optional[dist.ProcessGroup] = None) -> "ShardedGraph":
+        """``arrays``: the full-graph dict of ``csr.csr_from_networkx`` (every rank loads the graph file, only its node
+        range goes to its GPU)."""
+        from . import engine
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        n = int(arrays["n_nodes"])
+        b = [shard_bounds(n, world, r)[0] for r in range(world)] + [n]
+        shard = engine.GraphShard(arrays, b[rank], b[rank + 1], device)
+        obj = cls(shard.stage1, shard.stage2, shard.merge, torch.tensor(b, dtype=torch.int64, device=shard.device), group)
+        obj.shard = shard
+        return obj
+
+    def _gather(self, rec: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return rec.reshape(1, *rec.shape)
+        flat = torch.empty(self.world * rec.numel(), dtype=rec.dtype, device=rec.device)
+        dist.all_gather_into_tensor(flat, rec.contiguous().reshape(-1), group=self.group)  # rank-major concatenation
+        return flat.reshape((self.world,) + tuple(rec.shape))
+
+    def expand(self, ops: torch.Tensor, in_ids: torch.Tensor, in_offsets: torch.Tensor, limit: int = 10, max_ids: int = 4
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """ops int32 [n_env] (0 parents / 1 children / 2 related); inputs in CSR form (int32), at most ``max_ids`` per
+        environment (the gym actions pass 1-3, gym_env.py:94-100).  -> (ids [n_env, limit] padded with -1, counts)."""
+        g1 = self._gather(self.stage1(ops, in_ids, in_offsets, max_ids, limit))
+        g2 = self._gather(self.stage2(self.world, self.bounds, ops, in_ids, in_offsets, max_ids, limit, g1))
+        return self.merge(self.world, self.bounds, ops, in_ids, in_offsets, max_ids, limit, g1, g2)

@@ -355,6 +355,85 @@ class GraphCSR:
         return out_ids, out_cnt
 
 
+class GraphShard:
+    """One rank's node range [lo, hi) of the typed CSR (``ahr_graph_shard_*``, csrc/graph_shard.cu): the adjacency rows of
+    the owned nodes (all six slots, neighbours as GLOBAL dense ids) and their node types.  ``arrays`` is the full-graph
+    dict of ``csr.csr_from_networkx``; only the owned slice is uploaded."""
+
+    def __init__(self, arrays: Dict[str, Any], lo: int, hi: int, device: torch.device | str = "cuda") -> None:
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GraphShard needs a CUDA device: the engine has no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        dev = self.device
+        self.n_nodes, self.lo, self.hi = int(arrays["n_nodes"]), int(lo), int(hi)
+        self.row_ptr, self.col_idx = [], []
+        for s_ in range(_lib.AHR_N_CSR):
+            rp = np.ascontiguousarray(arrays["row_ptr"][s_], dtype=np.int64)
+            a, b = int(rp[self.lo]), int(rp[self.hi])
+            self.row_ptr.append(torch.as_tensor(rp[self.lo:self.hi + 1] - a).to(dev))
+            self.col_idx.append(torch.as_tensor(np.ascontiguousarray(arrays["col_idx"][s_][a:b], dtype=np.int32)).to(dev))
+        self.node_type = torch.as_tensor(np.ascontiguousarray(arrays["node_type"][self.lo:self.hi], dtype=np.uint8)).to(dev)
+        rp = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in self.row_ptr])
+        ci = (ctypes.c_void_p * 6)(*[t.data_ptr() if t.numel() else None for t in self.col_idx])
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            check(self.lib.ahr_graph_shard_create(ctypes.byref(self._h), dev.index, self.n_nodes, self.lo, self.hi, rp, ci,
+                                                  self.node_type.data_ptr() if self.hi > self.lo else None),
+                  "ahr_graph_shard_create")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.ahr_graph_shard_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.row_ptr + self.col_idx + [self.node_type])
+
+    def record_ints(self, stage: int, limit: int, max_ids: int) -> int:
+        n = int(self.lib.ahr_expand_shard_record_ints(stage, int(limit), int(max_ids)))
+        if n < 0:
+            raise ValueError(f"sharded expansion: limit must be in [1, 32] and max_ids >= 1 (got {limit}, {max_ids})")
+        return n
+
+    def stage1(self, ops, in_ids, in_offsets, max_ids: int, limit: int) -> torch.Tensor:
+        n_env = int(ops.shape[0])
+        out = torch.empty((n_env, self.record_ints(1, limit, max_ids)), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_expand_shard_stage1(self._h, n_env, ops.data_ptr(), in_ids.data_ptr(), in_offsets.data_ptr(),
+                                                   int(max_ids), int(limit), out.data_ptr(), _stream_ptr(self.device)),
+                  "ahr_expand_shard_stage1")
+        return out
+
+    def stage2(self, world: int, bounds, ops, in_ids, in_offsets, max_ids: int, limit: int, gathered1) -> torch.Tensor:
+        n_env = int(ops.shape[0])
+        out = torch.empty((n_env, self.record_ints(2, limit, max_ids)), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_expand_shard_stage2(self._h, n_env, int(world), bounds.data_ptr(), ops.data_ptr(), in_ids.data_ptr(),
+                                                   in_offsets.data_ptr(), int(max_ids), int(limit), gathered1.data_ptr(),
+                                                   out.data_ptr(), _stream_ptr(self.device)), "ahr_expand_shard_stage2")
+        return out
+
+    def merge(self, world: int, bounds, ops, in_ids, in_offsets, max_ids: int, limit: int, gathered1, gathered2):
+        n_env = int(ops.shape[0])
+        out_ids = torch.empty((n_env, limit), dtype=torch.int32, device=self.device)
+        out_cnt = torch.empty((n_env,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_expand_shard_merge(self.device.index, self.n_nodes, n_env, int(world), bounds.data_ptr(),
+                                                  ops.data_ptr(), in_ids.data_ptr(), in_offsets.data_ptr(), int(max_ids), int(limit),
+                                                  gathered1.data_ptr(), gathered2.data_ptr(), out_ids.data_ptr(), out_cnt.data_ptr(),
+                                                  _stream_ptr(self.device)), "ahr_expand_shard_merge")
+        return out_ids, out_cnt
+
+
 class EnvBatchState:
     """Device-resident state of ``n_envs`` gym environments over one ``GraphCSR`` (``ahr_env_reset`` /
     ``ahr_env_step``): selection and frontier sets, the current observation, step counters.  Outputs are
@@ -399,22 +478,26 @@ class EnvBatchState:
         self._eb = eb
         self._ready = False
 
-    def reset(self, rerank: Dict[str, torch.Tensor], n_seeds: int):
-        """``rerank`` = output of ``GraphCSR.anchor_rerank`` for one query per environment (top_k <= 10)."""
+    def reset(self, rerank: Dict[str, torch.Tensor], n_seeds: int, features: Optional[torch.Tensor] = None,
+              mask: Optional[torch.Tensor] = None):
+        """``rerank`` = output of ``GraphCSR.anchor_rerank`` for one query per environment (top_k <= 10).
+        ``features`` / ``mask``: optional contiguous destinations ([B, 84] fp32 / [B, 6] u8) instead of the handle's own."""
         nodes, sem, score, count = rerank["nodes"], rerank["semantic"], rerank["score"], rerank["count"]
         if int(nodes.shape[0]) != self.n_envs:
             raise ValueError(f"expected {self.n_envs} reranked lists, got {int(nodes.shape[0])}")
         for t, name in ((nodes, "nodes"), (sem, "semantic"), (score, "score"), (count, "count")):
             _require_cuda(t, name)
+        features = self.features if features is None else features
+        mask = self.mask if mask is None else mask
         dev = self.csr.device
         if self.n_envs:
             with torch.cuda.device(dev):
                 check(self.csr.lib.ahr_env_reset(self.csr._h, ctypes.byref(self._eb), nodes.data_ptr(), sem.data_ptr(),
                                                  score.data_ptr(), count.data_ptr(), int(nodes.shape[1]), int(n_seeds),
-                                                 self.features.data_ptr(), self.mask.data_ptr(), _stream_ptr(dev)),
+                                                 features.data_ptr(), mask.data_ptr(), _stream_ptr(dev)),
                       "ahr_env_reset")
         self._ready = True
-        return self.features, self.mask
+        return features, mask
 
     def capture_rollout(self, rerank: Dict[str, torch.Tensor], n_seeds: int, actions: torch.Tensor):
         """Reset + ``T`` steps as ONE CUDA graph (``actions``: int32 [T, B] on the device, read at replay time, so a policy
@@ -432,16 +515,10 @@ class EnvBatchState:
                "rewards": torch.zeros((T, B), dtype=torch.float64, device=dev),
                "done": torch.zeros((T, B), dtype=torch.uint8, device=dev)}
 
-        def episode():
-            f, m = self.reset(rerank, n_seeds)
-            out["features"][0].copy_(f)
-            out["mask"][0].copy_(m)
+        def episode():  # every launch writes straight into its slice of `out`: 1 + T kernels, no copies
+            self.reset(rerank, n_seeds, out["features"][0], out["mask"][0])
             for t in range(T):
-                f, r, d, m = self.step(actions[t])
-                out["features"][t + 1].copy_(f)
-                out["mask"][t + 1].copy_(m)
-                out["rewards"][t].copy_(r)
-                out["done"][t].copy_(d)
+                self.step(actions[t], out["features"][t + 1], out["rewards"][t], out["done"][t], out["mask"][t + 1])
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -454,21 +531,27 @@ class EnvBatchState:
         torch.cuda.current_stream(dev).wait_stream(side)
         return graph.replay, out
 
-    def step(self, actions: torch.Tensor):
-        """``actions`` int32 [B] on the device, values 0..5 (gym_env.py:14-20)."""
+    def step(self, actions: torch.Tensor, features: Optional[torch.Tensor] = None, rewards: Optional[torch.Tensor] = None,
+             done: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None):
+        """``actions`` int32 [B] on the device, values 0..5 (gym_env.py:14-20).  Optional contiguous destinations
+        replace the handle's own output tensors (e.g. slices of a [T, B, ...] trajectory buffer)."""
         if not self._ready:
             raise RuntimeError("Call reset() first")
         _require_cuda(actions, "actions")
         if actions.dtype != torch.int32 or tuple(actions.shape) != (self.n_envs,):
             raise ValueError(f"actions must be int32 of shape ({self.n_envs},)")
+        features = self.features if features is None else features
+        rewards = self.rewards if rewards is None else rewards
+        done = self.done if done is None else done
+        mask = self.mask if mask is None else mask
         dev = self.csr.device
         if self.n_envs:
             with torch.cuda.device(dev):
                 check(self.csr.lib.ahr_env_step(self.csr._h, ctypes.byref(self._eb), actions.data_ptr(), self.max_steps,
-                                                self.repeat_penalty, self.features.data_ptr(), self.rewards.data_ptr(),
-                                                self.done.data_ptr(), self.mask.data_ptr(), _stream_ptr(dev)),
+                                                self.repeat_penalty, features.data_ptr(), rewards.data_ptr(),
+                                                done.data_ptr(), mask.data_ptr(), _stream_ptr(dev)),
                       "ahr_env_step")
-        return self.features, self.rewards, self.done, self.mask
+        return features, rewards, done, mask
 
     def check_overflow(self) -> None:
         """Raises if a selection / frontier list outgrew its capacity (synchronises)."""

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AHR_VERSION 100
+#define AHR_VERSION 200
 
 /* error codes */
 #define AHR_OK 0
@@ -284,6 +284,43 @@ int ahr_comm_exchange_merge(ahr_comm *c, int32_t nq, int32_t k, float *dev_out_s
  */
 int ahr_topk_sharded(ahr_index *idx, ahr_comm *c, const void *dev_q, int32_t nq, int32_t k, int mode, float *dev_out_scores,
                      int64_t *dev_out_ids, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Knowledge-graph CSR SHARDED BY NODE RANGE (one process per GPU): rank r owns the adjacency rows and node types of the
+ * dense ids [lo, hi).  The reference has no multi-GPU path; this is GraphEnvironment.expand_parents / expand_children /
+ * expand_related (src/ah_rag/agent/environment.py:393-480) over a graph that does not fit, or is not wanted, on every GPU.
+ * The batch inputs (ops, input ids in CSR form) are replicated on the ranks, like the queries of the sharded index.
+ *
+ *   stage1  (owner of an input node)   unique prefix of the node's first-level list, its saturated length, and for
+ *                                      expand_related on an entity its first `limit` hyperedges
+ *   -- the caller all-gathers the stage-1 records of all ranks (NCCL / gloo / peer copies: any transport) --
+ *   stage2  (owner of a hyperedge)     unique prefix of the hyperedge's other participants (the 2-hop walk, :456-467)
+ *   -- all-gather of the stage-2 records --
+ *   merge   (any rank)                 per environment, in input order: prefixes appended, stop rule, dedup, cut
+ *
+ * Records are int32: stage 1 n_env x ahr_expand_shard_record_ints(1, limit, max_ids), stage 2 n_env x
+ * ahr_expand_shard_record_ints(2, ...); gathered buffers are [world][n_env][...] in rank order.  dev_bounds [world + 1]
+ * int64: bounds[r] = lo of rank r, bounds[world] = n_nodes.  limit <= 32 (the reference uses 10), at most max_ids input
+ * nodes per environment are read.  Results are bit-identical to ahr_expand on the unsharded graph for every world size
+ * provided a participates_in row holds distinct hyperedges (true of any CSR exported from a DiGraph).
+ * row_ptr_local[s] has hi - lo + 1 entries (row v - lo), col_idx_local[s] holds GLOBAL dense ids.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ahr_graph_shard ahr_graph_shard;
+int ahr_graph_shard_create(ahr_graph_shard **out, int device, int64_t n_nodes_total, int64_t lo, int64_t hi,
+                           const int64_t *const dev_row_ptr_local[AHR_N_CSR], const int32_t *const dev_col_idx_local[AHR_N_CSR],
+                           const uint8_t *dev_node_type_local);
+int ahr_graph_shard_destroy(ahr_graph_shard *g);
+int64_t ahr_expand_shard_record_ints(int32_t stage, int32_t limit, int32_t max_ids);
+int ahr_expand_shard_stage1(ahr_graph_shard *g, int32_t n_env, const int32_t *dev_ops, const int32_t *dev_in_ids,
+                            const int32_t *dev_in_offsets, int32_t max_ids, int32_t limit, int32_t *dev_out_records,
+                            void *stream);
+int ahr_expand_shard_stage2(ahr_graph_shard *g, int32_t n_env, int32_t world, const int64_t *dev_bounds, const int32_t *dev_ops,
+                            const int32_t *dev_in_ids, const int32_t *dev_in_offsets, int32_t max_ids, int32_t limit,
+                            const int32_t *dev_gathered1, int32_t *dev_out_records, void *stream);
+int ahr_expand_shard_merge(int device, int64_t n_nodes_total, int32_t n_env, int32_t world, const int64_t *dev_bounds,
+                           const int32_t *dev_ops, const int32_t *dev_in_ids, const int32_t *dev_in_offsets, int32_t max_ids,
+                           int32_t limit, const int32_t *dev_gathered1, const int32_t *dev_gathered2, int32_t *dev_out_ids,
+                           int32_t *dev_out_counts, void *stream);
 
 /* ---- diagnostics used by the parity tests (not part of the reference seam) ---------------------- */
 /* full [nq, n_rows] score matrix of the tensor-core path (small inputs only) */

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     assert sorted(_lib.EXPORTS) == syms, "ctypes binding and header disagree"
-    assert lib.ahr_version() == 100
+    assert lib.ahr_version() == 200
     assert lib.ahr_launch_count() >= 0
 
 

@@ -49,6 +49,23 @@ def _worker(rank, world, port, q):
             for j, ((s, i), (ws, wi)) in enumerate(zip(outs, wants)):
                 if not (torch.equal(i, wi) and torch.equal(s.view(torch.int32), ws.view(torch.int32))):
                     problems.append(f"peer={use_peer} case {j} differs")
+        # the knowledge-graph CSR sharded by node range: two NCCL all-gathers per expand call (csrc/graph_shard.cu)
+        from ah_rag_b200.dist import ShardedGraph
+        from tests.graph_util import random_csr
+        from tests.test_shard_stages import _batch
+        rng = np.random.default_rng(5)
+        a = random_csr(rng, n_ent=4000, n_sum=400, n_hyp=1200, hub_deg=2000)
+        sg = ShardedGraph.from_arrays(a, dev)
+        whole = engine.GraphCSR(a, dev)
+        ops, ids, offs = _batch(np.random.default_rng(6), a, 1024, 3)
+        t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+        for limit in (10, 3, 32):
+            oi, oc = sg.expand(t(ops), t(ids), t(offs), limit=limit, max_ids=3)
+            wi, wc = whole.expand(t(ops), t(ids), t(offs), limit)
+            if not (torch.equal(oi, wi) and torch.equal(oc, wc)):
+                problems.append(f"sharded graph expand differs at limit {limit}")
+        if sg.shard.nbytes() > 0.8 * whole.nbytes() and world > 1:
+            problems.append("graph shard is not a fraction of the graph")
         q.put((rank, problems))
     except Exception as e:  # report instead of leaving the parent waiting
         q.put((rank, [repr(e)]))

@@ -1,0 +1,117 @@
+"""CPU: the staged expansion over a node-range-sharded CSR (oracle/shard_stages.py, the numpy twin of csrc/graph_shard.cu)
+equals the reference's expand_* on the whole graph (oracle/array_graph.expand, environment.py:393-480) for every shard
+count; and the same through dist.ShardedGraph at world_size 2 over gloo."""
+import copy
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import array_graph, shard_stages
+from tests.graph_util import random_csr
+
+
+def _batch(rng, a, n_env, max_ids):
+    n, s0 = a["n_nodes"], int(np.argmax(a["node_type"] == 1))
+    ops, ids, offs = [], [], [0]
+    for e in range(n_env):
+        k = int(rng.integers(0, max_ids + 1))
+        pick = [int(x) for x in rng.integers(0, n, size=k)]
+        if e % 5 == 0:
+            pick = ([s0, s0 + 1] + pick)[:max_ids]       # hub summaries first
+        if e % 7 == 0 and pick:
+            pick[-1] = -1 if e % 2 else n + 3            # ids outside the graph
+        if e % 9 == 0 and len(pick) >= 2:
+            pick[1] = pick[0]                            # the same node twice
+        ops.append(e % 3)
+        ids += pick
+        offs.append(len(ids))
+    return np.array(ops, np.int32), np.array(ids, np.int32), np.array(offs, np.int32)
+
+
+def _run_sharded(a, bounds, ops, ids, offs, max_ids, limit):
+    world = len(bounds) - 1
+    g1 = np.stack([shard_stages.stage1(a, bounds[r], bounds[r + 1], ops, ids, offs, max_ids, limit) for r in range(world)])
+    g2 = np.stack([shard_stages.stage2(a, bounds[r], bounds[r + 1], bounds, ops, ids, offs, max_ids, limit, g1) for r in range(world)])
+    return shard_stages.merge(a["n_nodes"], bounds, ops, ids, offs, max_ids, limit, g1, g2)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("limit", [1, 3, 10, 32])
+def test_staged_expansion_equals_whole_graph_expand(world, limit):
+    rng = np.random.default_rng(100 * world + limit)
+    a = random_csr(rng, n_ent=700, n_sum=90, n_hyp=260, hub_deg=400)
+    n = a["n_nodes"]
+    bounds = [n * r // world for r in range(world)] + [n]
+    max_ids = 4
+    ops, ids, offs = _batch(rng, a, 240, max_ids)
+    oi, oc = _run_sharded(a, bounds, ops, ids, offs, max_ids, limit)
+    for e in range(len(ops)):
+        want = array_graph.expand(a, int(ops[e]), ids[offs[e]:offs[e + 1]], limit)
+        assert list(oi[e, :oc[e]]) == want, (world, limit, e, int(ops[e]), list(ids[offs[e]:offs[e + 1]]))
+        assert (oi[e, oc[e]:] == -1).all()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ah_rag_b200.dist import ShardedGraph, shard_bounds
+        rng = np.random.default_rng(7)
+        a = random_csr(rng, n_ent=500, n_sum=60, n_hyp=200, hub_deg=300)
+        n = a["n_nodes"]
+        b = [shard_bounds(n, world, r)[0] for r in range(world)] + [n]
+        lo, hi = b[rank], b[rank + 1]
+        t = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+        npy = lambda x: x.numpy()
+
+        def stage1(ops, ids, offs, max_ids, limit):
+            return t(shard_stages.stage1(a, lo, hi, npy(ops), npy(ids), npy(offs), max_ids, limit))
+
+        def stage2(world_, bounds, ops, ids, offs, max_ids, limit, g1):
+            return t(shard_stages.stage2(a, lo, hi, [int(x) for x in bounds], npy(ops), npy(ids), npy(offs), max_ids, limit, npy(g1)))
+
+        def merge(world_, bounds, ops, ids, offs, max_ids, limit, g1, g2):
+            oi, oc = shard_stages.merge(n, [int(x) for x in bounds], npy(ops), npy(ids), npy(offs), max_ids, limit, npy(g1), npy(g2))
+            return t(oi), t(oc)
+
+        sg = ShardedGraph(stage1, stage2, merge, torch.tensor(b, dtype=torch.int64))
+        assert sg.world == world and sg.rank == rank
+        ops, ids, offs = _batch(np.random.default_rng(11), a, 120, 3)
+        ok = True
+        for limit in (10, 3):
+            oi, oc = sg.expand(t(ops), t(ids), t(offs), limit=limit, max_ids=3)
+            oi, oc = oi.numpy(), oc.numpy()
+            for e in range(len(ops)):
+                ok &= list(oi[e, :oc[e]]) == array_graph.expand(a, int(ops[e]), ids[offs[e]:offs[e + 1]], limit)
+        q.put((rank, bool(ok)))
+    except Exception as e:  # report instead of leaving the parent waiting on the queue
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_sharded_graph_world2_gloo():
+    """The two all-gathers of dist.ShardedGraph over gloo, world_size 2: every rank ends with the whole-graph answer."""
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=150) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+    assert res == [(0, True), (1, True)]
