@@ -10,7 +10,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libahrag_b200.so")
+DEBUG = os.environ.get("AHR_LIB_DEBUG", "0") == "1"  # the build with device-side invariant checks (common.cuh)
+LIB_PATH = os.path.join(LIB_DIR, "libahrag_b200_dbg.so" if DEBUG else "libahrag_b200.so")
 SOURCES = ["api.cu", "topk_tc.cu", "topk_tc2.cu", "topk_exact.cu", "select.cu", "graph.cu", "env.cu", "exchange.cu", "lca.cu", "graph_shard.cu"]
 HEADERS = ["common.cuh", "kernels.h", "tc_shared.cuh", "graph_shared.cuh", os.path.join("..", "..", "include", "ahrag_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -50,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
-    obj_dir = os.path.join(HERE, "build")
+    obj_dir = os.path.join(HERE, "build_dbg" if DEBUG else "build")
     os.makedirs(obj_dir, exist_ok=True)
     env = dict(os.environ)
     if os.path.exists("/usr/bin/g++"):
@@ -60,7 +61,8 @@ def _build_locked(verbose: bool) -> str:
 
     def compile_one(src: str) -> str:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *ccbin, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DAHR_DEBUG_BOUNDS"] if DEBUG else []), *ccbin, "-Xptxas", "-v", "-c",
+               os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         log = os.path.join(obj_dir, src + ".log")
         with open(log, "w") as f:

@@ -206,6 +206,7 @@ static int exact_bruteforce(ahr_index *idx, const void *dev_q, const int32_t *q_
 // per query seeds every list's admission threshold in the main pass (tc_shared.cuh: seed_threshold).
 static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, float *out_scores, int64_t *out_ids,
                    float *dbg_scores, cudaStream_t st, const PeerPush *push = nullptr) {
+  AHR_NVTX("ahr K1 fused similarity + top-k");
   AHR_REQUIRE(idx->has_map, "index is not TMA-addressable (dim %% 8 != 0 or rows not 16-byte aligned)");
   AHR_REQUIRE((reinterpret_cast<uintptr_t>(dev_q) & 15) == 0, "queries must be 16-byte aligned");
   const bool split = idx->dtype == AHR_DTYPE_F32;  // fp32 operands: hi + lo bf16 halves, 3 operand segments
@@ -317,6 +318,7 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
               total / n_lead, sum[1] / n_lead, sum[2] / n_lead, sum[0] / idx->sm_count, sum[4] / idx->sm_count,
               sum[5] / idx->sm_count, sum[6] / idx->sm_count, sum[7] / idx->sm_count);
   }
+  AHR_NVTX("ahr K1 slab-list reduction (+ peer push)");
   // per-query reduction of the S slab lists (each sorted, empties last): rank-counting merge for a few lists, bitonic
   // selection otherwise; with `push` the result also goes to the peers of the sharded index from the same launch
   if (merge_sorted_applicable(S, k, k))
@@ -362,6 +364,7 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
     return tc_topk(idx, dev_q, nq, k, dev_scores, dev_ids, nullptr, st);
   }
 
+  AHR_NVTX("ahr K1x exact mode (candidates, rescoring, certification)");
   // ---- exact mode ----
   // Tiers: (1) tensor-core candidates with a small slack (kc = 56 for k <= 50: the fast 64-slot lists), canonical
   // rescoring, certification; (2) the queries that could not be certified (near-ties, duplicated rows around rank k) again
@@ -638,6 +641,7 @@ static int anchor_rerank_common(ahr_graph *g, int32_t nq, int32_t n_seeds, const
                                 int32_t *dev_out_nodes, double *dev_out_semantic, double *dev_out_score,
                                 int32_t *dev_out_count, int32_t *dev_exp_nodes, double *dev_exp_semantic,
                                 uint8_t *dev_exp_kind, int32_t *dev_exp_count, double *dev_seed_semantic, void *stream) {
+  AHR_NVTX("ahr K2 anchor expansion + rerank");
   AHR_REQUIRE(g && params, "ahr_anchor_rerank: NULL handle or params");
   if (nq == 0) return AHR_OK;
   AHR_REQUIRE(dev_seed_scores && dev_out_nodes && dev_out_semantic && dev_out_score && dev_out_count,
@@ -681,6 +685,7 @@ int ahr_anchor_rerank_rows(ahr_graph *g, int32_t nq, int32_t n_seeds, const int6
 int ahr_expand(ahr_graph *g, int32_t n_env, const int32_t *dev_ops, const int32_t *dev_in_ids,
                const int32_t *dev_in_offsets, int32_t limit, int32_t *dev_out_ids, int32_t *dev_out_counts,
                void *stream) {
+  AHR_NVTX("ahr K2 frontier expansion");
   AHR_REQUIRE(g != nullptr, "ahr_expand: graph is NULL");
   if (n_env == 0) return AHR_OK;
   AHR_REQUIRE(dev_ops && dev_in_offsets && dev_out_ids && dev_out_counts, "ahr_expand: NULL buffer");
@@ -711,6 +716,7 @@ int ahr_lca_closure(ahr_graph *g, const int32_t *host_ids, int32_t n_ids, uint8_
 int ahr_env_reset(ahr_graph *g, const ahr_env_batch *env, const int32_t *dev_nodes, const double *dev_semantic,
                   const double *dev_score, const int32_t *dev_count, int32_t top_k, int32_t n_seeds, float *dev_features,
                   uint8_t *dev_mask, void *stream) {
+  AHR_NVTX("ahr gym reset");
   AHR_REQUIRE(g && env, "ahr_env_reset: NULL handle or env");
   AHR_REQUIRE(top_k >= 1 && top_k <= 10 && n_seeds >= 0, "ahr_env_reset: top_k must be in [1, 10] (got %d)", top_k);
   if (env->n_env == 0) return AHR_OK;
@@ -723,6 +729,7 @@ int ahr_env_reset(ahr_graph *g, const ahr_env_batch *env, const int32_t *dev_nod
 int ahr_env_step(ahr_graph *g, const ahr_env_batch *env, const int32_t *dev_actions, int32_t max_steps,
                  double repeat_penalty, float *dev_features, double *dev_rewards, uint8_t *dev_done, uint8_t *dev_mask,
                  void *stream) {
+  AHR_NVTX("ahr gym step");
   AHR_REQUIRE(g && env, "ahr_env_step: NULL handle or env");
   if (env->n_env == 0) return AHR_OK;
   AHR_REQUIRE(dev_actions && dev_features && dev_rewards && dev_done && dev_mask, "ahr_env_step: NULL buffer");

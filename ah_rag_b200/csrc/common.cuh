@@ -12,9 +12,21 @@
 #include <cstring>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/ahrag_b200.h"
 
 namespace ahr {
+
+// NVTX range over a phase of an API call (host-side enqueue; tools map it onto the kernels launched inside).  Header-only
+// NVTX v3: a no-op unless a profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define AHR_NVTX_CAT2(a, b) a##b
+#define AHR_NVTX_CAT(a, b) AHR_NVTX_CAT2(a, b)
+#define AHR_NVTX(name) ahr::NvtxRange AHR_NVTX_CAT(ahr_nvtx_range_, __LINE__)(name)
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing (thread-local message, C return codes)
@@ -59,6 +71,23 @@ struct DeviceGuard {
   }
   int target = -1;
 };
+
+// Device-side invariant checks of the debug build (python -m ah_rag_b200._build --debug -> libahrag_b200_dbg.so, selected
+// with AHR_LIB_DEBUG=1).  compute-sanitizer is closed on the GPU pool this library is developed on, so out-of-range
+// indices are caught by these assertions on small cases whose results are compared with the CPU oracle
+// (tools/sanitize_cases.py): a violated bound prints its location and traps.  Compiled out of the release build.
+#ifdef AHR_DEBUG_BOUNDS
+#define AHR_DEV_ASSERT(cond)                                                                         \
+  do {                                                                                               \
+    if (!(cond)) {                                                                                   \
+      printf("AHR_DEV_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+             (int)blockIdx.x, (int)threadIdx.x);                                                     \
+      __trap();                                                                                      \
+    }                                                                                                \
+  } while (0)
+#else
+#define AHR_DEV_ASSERT(cond) ((void)0)
+#endif
 
 // ranking comparator shared by every selection kernel: (score desc, id asc)
 __host__ __device__ __forceinline__ bool ranks_before(float s1, int64_t i1, float s2, int64_t i2) {

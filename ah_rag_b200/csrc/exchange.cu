@@ -215,6 +215,7 @@ static PeerPush make_push(const ahr_comm *c, uint64_t epoch, size_t scores_bytes
 namespace ahr {
 int peer_push_record(const PeerPush &push, size_t rec_bytes, cudaStream_t stream) {
   if (push.world <= 1) return AHR_OK;
+  AHR_NVTX("ahr K3 peer push");
   push_kernel<<<PUSH_BLOCKS_PER_PEER * (push.world - 1), PUSH_THREADS, 0, stream>>>(push, rec_bytes);
   AHR_KERNEL_CHECK();
   return AHR_OK;
@@ -226,6 +227,7 @@ extern "C" {
 // wait for every peer's record of `epoch`, then merge the world slots of that half into out
 static int wait_and_merge(ahr_comm *c, uint64_t epoch, int32_t nq, int32_t k, float *dev_out_scores, int64_t *dev_out_ids,
                           cudaStream_t st) {
+  AHR_NVTX("ahr K3 wait for peers + merge");
   const size_t sb = (size_t)nq * k * 4;
   const int half = (int)(epoch & 1);
   if (c->world > 1) {

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
     } else if (j == 0 && a.seed_sem) {
       a.seed_sem[(int64_t)q * a.n_seeds + r] = 0.0;
     }
+    AHR_DEV_ASSERT(node < g.n_nodes);
     e_node[e] = node; e_sem[e] = sem; e_kind[e] = kind; e_flag[e] = 0;
   }
   __syncthreads();
@@ -245,7 +246,9 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
   // ---- B. first-writer-wins dedup; a seed always owns the value of its node (:732) ----
   auto probe = [&](int32_t node, bool insert) {
     int slot = (int)(((uint32_t)node * 2654435761u) >> 7) & hmask;
+    int probes = 0;
     for (;;) {
+      AHR_DEV_ASSERT(slot >= 0 && slot < hsize && ++probes <= hsize);
       const int32_t k = insert ? atomicCAS(&h_key[slot], -1, node) : h_key[slot];
       if (k == node || (insert && k == -1)) return slot;
       slot = (slot + 1) & hmask;
@@ -287,6 +290,7 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
     int pos = block_exclusive_scan(mine, sm_warp, total);
     for (int e = e_lo; e < e_hi; ++e) {
       if (!(e_flag[e] & 1)) continue;
+      AHR_DEV_ASSERT(pos >= 0 && pos < cap);
       a.exp_nodes[(int64_t)q * cap + pos] = e_node[e];
       a.exp_sem[(int64_t)q * cap + pos] = e_sem[e];
       if (a.exp_kind) a.exp_kind[(int64_t)q * cap + pos] = e_kind[e];
@@ -328,6 +332,7 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
   int pos = block_exclusive_scan(mine, sm_warp, n_valid);  // its barriers also retire the last reads of the hash
   for (int e = e_lo; e < e_hi; ++e) {
     if (!(e_flag[e] & 2)) continue;
+    AHR_DEV_ASSERT(pos >= 0 && pos < cap);
     c_rs[pos] = e_rs[e];
     c_e[pos] = e;
     ++pos;
@@ -517,13 +522,16 @@ expand_wide_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, 
     int slot = 0;
     if (valid) {
       slot = (int)(((uint32_t)val * 2654435761u) >> tshift);
+      int probes = 0;
       for (;;) {
+        AHR_DEV_ASSERT(slot >= 0 && slot < T && T <= lay.T_max && ++probes <= T);
         const int32_t k = atomicCAS(&tkey[slot], -1, val);
         if (k == -1 || k == val) break;
         slot = (slot + 1) & (T - 1);
       }
       atomicMin(&tpos[slot], p);
     }
+    AHR_DEV_ASSERT(p >= 0 && p < W && W <= lay.W);
     rval[p] = valid ? val : -1;
     rslot[p] = (uint16_t)slot;
   };
@@ -552,6 +560,7 @@ expand_wide_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, 
       const uint32_t wbits = bits[p >> 5];
       if (!((wbits >> (p & 31)) & 1u)) continue;
       const int rank = out_count + pref[p >> 5] + __popc(wbits & ((1u << (p & 31)) - 1u));
+      AHR_DEV_ASSERT(rank >= 0);
       if (rank < limit) out[rank] = rval[p];
       tpos[rslot[p]] = -1;  // emitted (or beyond the limit, in which case the call ends here)
     }

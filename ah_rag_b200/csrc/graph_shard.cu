@@ -52,6 +52,7 @@ __device__ __forceinline__ bool shard_segment(ExpandState &st, const ShardView &
     bool valid = i < p1;
     if (valid) {
       val = g.col_idx[slot][i];
+      AHR_DEV_ASSERT(val >= 0 && val < g.n_nodes);
       valid = val != exclude;
     }
     if (expand_push(st, val, valid, lane)) return true;
@@ -177,6 +178,7 @@ shard_merge_kernel(ShardGeom geo, int64_t n_nodes, int32_t n_env, int32_t world,
     if (v < 0 || v >= n_nodes) continue;  // `if nid not in G: continue`
     const int64_t ei = (int64_t)env * geo.max_ids + idx;
     const int32_t *r1 = gathered1 + ((int64_t)shard_owner(bounds, world, v) * n_env * geo.max_ids + ei) * geo.rec1();
+    AHR_DEV_ASSERT(r1[2] >= 0 && r1[2] <= geo.cap && r1[3] >= 0 && r1[3] <= geo.limit);
     push_list(r1 + 4, r1[2]);
     raw += r1[0];
     if (op == AHR_OP_RELATED && (r1[1] & SH_ENTITY)) {

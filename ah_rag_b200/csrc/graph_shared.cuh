@@ -29,6 +29,7 @@ __device__ __forceinline__ bool expand_push(ExpandState &st, int32_t val, bool v
   const bool fresh = valid && !dup && first_in_batch;
   const unsigned nmask = __ballot_sync(0xffffffffu, fresh);
   const int pos = st.count + __popc(nmask & ((1u << lane) - 1u));
+  AHR_DEV_ASSERT(pos >= 0);
   if (fresh && pos < st.limit) st.out[pos] = val;
   st.count = min(st.limit, st.count + __popc(nmask));
   __syncwarp();
@@ -44,6 +45,7 @@ __device__ __forceinline__ bool expand_segment(ExpandState &st, const GraphView 
     bool valid = i < p1;
     if (valid) {
       val = g.col_idx[slot][i];  // coalesced: consecutive lanes read consecutive neighbours
+      AHR_DEV_ASSERT(val >= 0 && val < g.n_nodes);
       valid = val != exclude;
     }
     if (expand_push(st, val, valid, lane)) return true;

@@ -104,6 +104,7 @@ select_topk_kernel(const float *__restrict__ cand_scores, const int32_t *__restr
       if (ok && sm.have_thr) ok = ranks_before(s, id, sm.thr_s, sm.thr_id);
       if (ok) {
         const int slot = atomicAdd(&sm.fill, 1);
+        AHR_DEV_ASSERT(slot >= 0 && slot < SEL_N);
         sm.s[slot] = s;
         sm.id[slot] = id;
       }
@@ -205,6 +206,7 @@ merge_sorted_lists_kernel(const float *__restrict__ cand_scores, const int32_t *
       }
       rank += lo;
     }
+    AHR_DEV_ASSERT(rank >= 0);
     if (rank < k) { sm.res_s[rank] = sc; sm.res_id[rank] = id; }
   }
   __syncthreads();

@@ -314,6 +314,7 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bo
           const int j = __ffs(bits) - 1;
           bits &= bits - 1;
           const float sc = lds_f32(scratch_lane + j * 128);
+          AHR_DEV_ASSERT(cnt >= 0 && cnt < KLIST && j >= 0 && j < 32);
           sts_u64(my_list + cnt * 8, make_key(sc, id0 + j));
           cmax = fmaxf(cmax, sc);
           ++cnt;

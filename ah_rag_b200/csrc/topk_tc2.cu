@@ -145,7 +145,9 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const CUtensorMap *mx = cb.seg == 2 ? &map_x_lo : &map_x;
         const int32_t x_row0 = (int32_t)cb.ct * (p.tile_stride * T2_BN) + (int32_t)rank * T2_BN_HALF;
         if (leader) mbar_arrive_expect_tx(&full_b[sb], 2 * T2_B_BYTES);
-        tma_load_2d_2sm(b_tiles + sb * T2_B_BYTES, mx, full_b0 + sb * 8, cb.kb * TC_BK, x_row0, kEvictNormal);  // streams through
+        // normal L2 policy: the pairs sweeping the same slab for other query tiles hit these lines (evict-last / evict-first
+        // measured: no change in time or DRAM traffic, profiles/r2_k1_traffic.md)
+        tma_load_2d_2sm(b_tiles + sb * T2_B_BYTES, mx, full_b0 + sb * 8, cb.kb * TC_BK, x_row0, kEvictNormal);
         if (++sb == NB) sb = 0;
         advance(cb);
       };
