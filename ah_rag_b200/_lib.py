@@ -26,6 +26,7 @@ AHR_IPC_HANDLE_BYTES = 64
 
 EXPORTS = [
     "ahr_last_error", "ahr_version", "ahr_launch_count", "ahr_index_create", "ahr_index_destroy", "ahr_topk",
+    "ahr_topk_exact_begin", "ahr_topk_exact_finish",
     "ahr_topk_host", "ahr_merge_topk", "ahr_merge_topk_packed", "ahr_graph_create", "ahr_graph_destroy", "ahr_anchor_rerank", "ahr_anchor_rerank_rows", "ahr_expand",
     "ahr_debug_tc_scores", "ahr_rescore", "ahr_debug_round4", "ahr_exact_stats", "ahr_set_profiling",
     "ahr_get_profile", "ahr_env_reset", "ahr_env_step", "ahr_comm_create", "ahr_comm_export", "ahr_comm_connect",
@@ -63,6 +64,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.ahr_index_create.argtypes = [POINTER(vp), c_int, c_int64, c_int32, c_int, vp, c_int64]
     lib.ahr_index_destroy.argtypes = [vp]
     lib.ahr_topk.argtypes = [vp, vp, c_int32, c_int32, c_int, vp, vp, vp]
+    lib.ahr_topk_exact_begin.argtypes = [vp, vp, c_int32, c_int32, vp, vp, vp]
+    lib.ahr_topk_exact_finish.argtypes = [vp]
     lib.ahr_topk_host.argtypes = [vp, vp, c_int32, c_int32, c_int, vp, vp, vp]
     lib.ahr_merge_topk.argtypes = [c_int, vp, vp, c_int32, c_int32, c_int32, vp, vp, vp]
     lib.ahr_merge_topk_packed.argtypes = [c_int, vp, c_int64, c_int32, c_int32, c_int32, vp, vp, vp]

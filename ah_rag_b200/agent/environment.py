@@ -5,9 +5,10 @@ fused top-k + one expansion/rerank launch (``HierarchicalGraph.search_batch``) a
 ``ahr_expand`` launch over the device CSR instead of NetworkX walks.  ``VecGraphEnvironment`` is the additive
 batched form the RL rollout loop (policy_ppo.py:163-205) should drive: B environments per launch.
 
-Out of scope: ``expand_to_lca`` (not a gym action, quirky in the reference) and the
-structlog session logger -- a plain JSONL writer keeps the file layout (session.json / events.jsonl /
-summary.json) when logging is enabled.
+``expand_to_lca`` (environment.py:243-299) runs its closure on the device CSR (``ahr_lca_closure``,
+one sync-free launch) and reproduces the reference's quirk (descendant sets).  Out of scope: the
+structlog session logger -- a plain JSONL writer keeps the file layout (session.json / events.jsonl / summary.json) when
+logging is enabled.
 """
 from __future__ import annotations
 

@@ -185,6 +185,7 @@ class DeviceVecAHRAGGymEnv:
         from ..engine import EnvBatchState
         self.hg = hg
         self.csr = hg._device_graph()["csr"]
+        self._batch_args = (n_envs, max_steps, repeat_penalty, cap_selection, cap_frontier)
         self.batch = EnvBatchState(self.csr, n_envs, max_steps, repeat_penalty, cap_selection, cap_frontier)
         self.n_envs, self.max_steps, self.repeat_penalty = self.batch.n_envs, self.batch.max_steps, self.batch.repeat_penalty
 
@@ -205,6 +206,11 @@ class DeviceVecAHRAGGymEnv:
         if len(query_embeddings) != self.n_envs:
             raise ValueError(f"expected {self.n_envs} query embeddings, got {len(query_embeddings)}")
         hg = self.hg
+        csr = hg._device_graph()["csr"]
+        if csr is not self.csr:  # the graph changed since the last episode: new device graph, fresh environment state
+            from ..engine import EnvBatchState
+            self.csr = csr
+            self.batch = EnvBatchState(csr, *self._batch_args)
         # GraphEnvironment.reset -> semantic_anchor(top_k=5, member_top_m=5), no weights / filters set (:155-241)
         params = hg._resolve(5, None, None, None, None, None, None, None)
         db_path, _ = hg._resolve_index(None, "unused")

@@ -89,6 +89,16 @@ struct ahr_index {
   DevBuf hq, hs, hi;  // device staging of the *_host entry point
   float *d_max_norm = nullptr;
   int64_t n_certified = 0, n_fallback = 0;
+  struct Pending {       // an exact query between ahr_topk_exact_begin and ahr_topk_exact_finish
+    bool active = false, done = false, use_tc = false;
+    const void *q = nullptr;
+    int32_t nq = 0, k = 0;
+    float *scores = nullptr;
+    int64_t *ids = nullptr;
+    cudaStream_t stream = nullptr;
+  } pending;
+  int32_t *h_nfail = nullptr;      // pinned: number of queries tier 1 could not certify
+  cudaEvent_t ev_nfail = nullptr;  // recorded behind the copy into h_nfail
   bool profile = false;  // CUDA-event timing of the dominant kernel (K1) on its launch stream
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   int last_slabs = 0;
@@ -157,7 +167,9 @@ int ahr_index_create(ahr_index **out, int device, int64_t n_rows, int32_t dim, i
   if (const char *e = getenv("AHR_TC_STATS")) idx->tc_stats = atoi(e) != 0;
   if (const char *e = getenv("AHR_TC_SHARED_BOUND")) idx->shared_bound = atoi(e) != 0;
   cudaError_t e = cudaMalloc(&idx->d_max_norm, sizeof(float));
-  if (e != cudaSuccess) { delete idx; set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return AHR_E_NOMEM; }
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&idx->h_nfail), sizeof(int32_t), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ev_nfail, cudaEventDisableTiming);
+  if (e != cudaSuccess) { delete idx; set_error("allocation failed: %s", cudaGetErrorString(e)); return AHR_E_NOMEM; }
   int rc = row_norms_max(dev_rows, dtype, n_rows, dim, idx->d_max_norm, 0);
   if (rc != AHR_OK) { cudaFree(idx->d_max_norm); delete idx; return rc; }
   AHR_CUDA_CHECK(cudaStreamSynchronize(0));
@@ -170,6 +182,8 @@ int ahr_index_destroy(ahr_index *idx) {
   DeviceGuard guard(idx->device);
   idx->x_hi.release(); idx->x_lo.release(); idx->q_split.release(); idx->stats_buf.release(); idx->ws.release(); idx->ws2.release(); idx->hq.release(); idx->hs.release(); idx->hi.release();
   if (idx->d_max_norm) cudaFree(idx->d_max_norm);
+  if (idx->h_nfail) cudaFreeHost(idx->h_nfail);
+  if (idx->ev_nfail) cudaEventDestroy(idx->ev_nfail);
   delete idx;
   return AHR_OK;
 }
@@ -364,46 +378,57 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
     return tc_topk(idx, dev_q, nq, k, dev_scores, dev_ids, nullptr, st);
   }
 
-  AHR_NVTX("ahr K1x exact mode (candidates, rescoring, certification)");
-  // ---- exact mode ----
-  // Tiers: (1) tensor-core candidates with a small slack (kc = 56 for k <= 50: the fast 64-slot lists), canonical
-  // rescoring, certification; (2) the queries that could not be certified (near-ties, duplicated rows around rank k) again
-  // with kc = 112; (3) what still fails through the brute-force scan.  Every tier returns the exact answer or hands the
-  // query on, so the result does not depend on which tier served it.
-  idx->n_certified = 0;
-  idx->n_fallback = 0;
-  const bool use_tc = idx->has_map && k <= 96 && idx->n_rows > 4096 && (reinterpret_cast<uintptr_t>(dev_q) & 15) == 0;
-  if (!use_tc) {
-    idx->n_fallback = nq;
-    return exact_bruteforce(idx, dev_q, nullptr, nq, k, dev_scores, dev_ids, idx->ws, st);
-  }
-  const int32_t kc_small = 56, kc_big = 112;
-  const int32_t kc1 = k <= 50 ? kc_small : kc_big;
-  const size_t esz = idx->dtype == AHR_DTYPE_F32 ? 4 : 2;
-  const size_t row_bytes = (size_t)idx->dim * esz;
-  // scratch: cand scores/ids [nq,kc], exact scores [nq,kc], eps [nq], flags [nq], list [nq], count,
-  //          final (scores, ids) [nq,k] of a sub-batch, the gathered queries of tier 2, its failure list
-  const size_t nc = (size_t)nq * kc_big;
+  int rc = ahr_topk_exact_begin(idx, dev_q, nq, k, dev_scores, dev_ids, stream);
+  if (rc != AHR_OK) return rc;
+  return ahr_topk_exact_finish(idx);
+}
+
+// ---- exact mode ---------------------------------------------------------------------------------------------------
+// Tiers: (1) tensor-core candidates with a small slack (kc = 56 for k <= 50: the fast 64-slot lists), canonical rescoring,
+// certification; (2) the queries that could not be certified (near-ties, duplicated rows around rank k) again with kc = 112;
+// (3) what still fails through the brute-force scan.  Every tier returns the exact answer or hands the query on, so the
+// result does not depend on which tier served it.
+// begin = tier 1, enqueued without any host synchronisation (the count of uncertified queries travels to a pinned host word
+// behind an event); finish = wait for that word and, only if it is not zero, run tiers 2 and 3 (which do synchronise).
+namespace {
+struct ExactScratch {
+  float *cs, *ex, *eps, *fs;
+  int64_t *ci, *fi;
+  int32_t *flags, *flist, *flist2, *fcnt;
+  void *qsub;
+};
+constexpr int32_t KC_SMALL = 56, KC_BIG = 112;
+
+int exact_scratch(ahr_index *idx, int32_t nq, int32_t k, ExactScratch &x) {
+  const int32_t kc1 = k <= 50 ? KC_SMALL : KC_BIG;
+  const size_t row_bytes = (size_t)idx->dim * (idx->dtype == AHR_DTYPE_F32 ? 4 : 2);
+  // cand scores/ids [nq,kc], exact scores [nq,kc], eps [nq], flags [nq], list [nq], count, final (scores, ids) [nq,k] of a
+  // sub-batch, the gathered queries of tier 2, its failure list
+  const size_t nc = (size_t)nq * KC_BIG;
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
   const size_t o_cs = carve(nc * 4), o_ci = carve(nc * 8), o_ex = carve(nc * 4), o_eps = carve((size_t)nq * 4),
                o_flag = carve((size_t)nq * 4), o_list = carve((size_t)nq * 4), o_cnt = carve(4),
                o_fs = carve((size_t)nq * k * 4), o_fi = carve((size_t)nq * k * 8), o_list2 = carve((size_t)nq * 4),
-               o_qsub = carve(kc1 == kc_small ? (size_t)nq * row_bytes : 0);
+               o_qsub = carve(kc1 == KC_SMALL ? (size_t)nq * row_bytes : 0);
   int rc = idx->ws2.reserve(off);
   if (rc != AHR_OK) return rc;
   uint8_t *w = reinterpret_cast<uint8_t *>(idx->ws2.ptr);
-  float *cs = reinterpret_cast<float *>(w + o_cs);
-  int64_t *ci = reinterpret_cast<int64_t *>(w + o_ci);
-  float *ex = reinterpret_cast<float *>(w + o_ex);
-  float *eps = reinterpret_cast<float *>(w + o_eps);
-  int32_t *flags = reinterpret_cast<int32_t *>(w + o_flag);
-  int32_t *flist = reinterpret_cast<int32_t *>(w + o_list);
-  int32_t *flist2 = reinterpret_cast<int32_t *>(w + o_list2);
-  int32_t *fcnt = reinterpret_cast<int32_t *>(w + o_cnt);
-  float *fs = reinterpret_cast<float *>(w + o_fs);
-  int64_t *fi = reinterpret_cast<int64_t *>(w + o_fi);
-  void *qsub = w + o_qsub;
+  x.cs = reinterpret_cast<float *>(w + o_cs);
+  x.ci = reinterpret_cast<int64_t *>(w + o_ci);
+  x.ex = reinterpret_cast<float *>(w + o_ex);
+  x.eps = reinterpret_cast<float *>(w + o_eps);
+  x.flags = reinterpret_cast<int32_t *>(w + o_flag);
+  x.flist = reinterpret_cast<int32_t *>(w + o_list);
+  x.flist2 = reinterpret_cast<int32_t *>(w + o_list2);
+  x.fcnt = reinterpret_cast<int32_t *>(w + o_cnt);
+  x.fs = reinterpret_cast<float *>(w + o_fs);
+  x.fi = reinterpret_cast<int64_t *>(w + o_fi);
+  x.qsub = w + o_qsub;
+  return AHR_OK;
+}
+
+float exact_eps_rel(const ahr_index *idx) {
   // |tensor - canonical| <= eps_rel * ||q|| * ||x||.  Worst-case model of the tcgen05 accumulation (it truncates rather
   // than rounds, and aligns the 16 exact products of a K = 16 step to the largest exponent before adding them):
   //   per K-step  <= 2 ulp(acc) for the truncated add + 16 * 2^-24 * max|product| for the alignment
@@ -414,42 +439,96 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
   // dim = 1024..4096 inputs.  The only cost of a wide bound is more tier-2 / brute-force fallbacks.
   // fp32 rows go through the hi/lo split: 3x the accumulation steps plus the dropped lo*lo and residual terms
   // (|x - hi - lo| <= 2^-18 |x| per operand -> <= 3 * 2^-18, rounded up to 2^-16)
-  const float eps_rel = idx->dtype == AHR_DTYPE_F32
-                            ? (float)((3 * idx->dim / 2 + 64) * std::ldexp(1.0, -23) + std::ldexp(1.0, -16))
-                            : (float)((idx->dim / 2 + 64) * std::ldexp(1.0, -23));
-  // one tier over `n` queries at `q`: results into out_* [n, k], uncertified query indices into `fail_list`
-  auto tier = [&](const void *q, int32_t n, int32_t kc, float *out_s, int64_t *out_i, int32_t *fail_list, int32_t *n_fail) {
-    int r = tc_topk(idx, q, n, kc, cs, ci, nullptr, st);
-    if (r == AHR_OK) r = exact_rescore(idx->rows, q, idx->dtype, idx->dim, n, kc, ci, idx->id_base, ex, st);
-    if (r == AHR_OK) r = query_eps(q, idx->dtype, n, idx->dim, idx->d_max_norm, eps_rel, eps, st);
-    if (r != AHR_OK) return r;
-    AHR_CUDA_CHECK(cudaMemsetAsync(fcnt, 0, 4, st));
-    r = exact_certify(cs, ci, ex, n, kc, k, eps, out_s, out_i, flags, fcnt, fail_list, st);
-    if (r != AHR_OK) return r;
-    AHR_CUDA_CHECK(cudaMemcpyAsync(n_fail, fcnt, 4, cudaMemcpyDeviceToHost, st));
-    AHR_CUDA_CHECK(cudaStreamSynchronize(st));
-    return (int)AHR_OK;
-  };
-  int32_t n_fail = 0;
-  rc = tier(dev_q, nq, kc1, dev_scores, dev_ids, flist, &n_fail);
+  return idx->dtype == AHR_DTYPE_F32 ? (float)((3 * idx->dim / 2 + 64) * std::ldexp(1.0, -23) + std::ldexp(1.0, -16))
+                                     : (float)((idx->dim / 2 + 64) * std::ldexp(1.0, -23));
+}
+
+// one tier over `n` queries at `q`, enqueued only: results into out_* [n, k], uncertified query indices into `fail_list`,
+// their number into x.fcnt
+int exact_tier(ahr_index *idx, const ExactScratch &x, const void *q, int32_t n, int32_t kc, int32_t k, float *out_s,
+               int64_t *out_i, int32_t *fail_list, cudaStream_t st) {
+  int r = tc_topk(idx, q, n, kc, x.cs, x.ci, nullptr, st);
+  if (r == AHR_OK) r = exact_rescore(idx->rows, q, idx->dtype, idx->dim, n, kc, x.ci, idx->id_base, x.ex, st);
+  if (r == AHR_OK) r = query_eps(q, idx->dtype, n, idx->dim, idx->d_max_norm, exact_eps_rel(idx), x.eps, st);
+  if (r != AHR_OK) return r;
+  AHR_CUDA_CHECK(cudaMemsetAsync(x.fcnt, 0, 4, st));
+  return exact_certify(x.cs, x.ci, x.ex, n, kc, k, x.eps, out_s, out_i, x.flags, x.fcnt, fail_list, st);
+}
+}  // namespace
+
+int ahr_topk_exact_begin(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, float *dev_scores, int64_t *dev_ids,
+                         void *stream) {
+  AHR_NVTX("ahr K1x exact mode: tensor-core candidates, rescoring, certification");
+  AHR_REQUIRE(idx != nullptr, "ahr_topk_exact_begin: index is NULL");
+  AHR_REQUIRE(!idx->pending.active, "ahr_topk_exact_begin: the previous exact query of this index was not finished");
+  AHR_REQUIRE(nq >= 0 && k >= 1 && k <= SELECT_MAX_K, "ahr_topk_exact_begin: bad sizes nq=%d k=%d", nq, k);
+  if (nq == 0) return AHR_OK;
+  AHR_REQUIRE(dev_q && dev_scores && dev_ids, "ahr_topk_exact_begin: NULL buffer");
+  DeviceGuard guard(idx->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  idx->n_certified = 0;
+  idx->n_fallback = 0;
+  auto &pd = idx->pending;
+  pd = ahr_index::Pending();
+  pd.q = dev_q; pd.nq = nq; pd.k = k; pd.scores = dev_scores; pd.ids = dev_ids; pd.stream = st;
+  pd.use_tc = idx->has_map && k <= 96 && idx->n_rows > 4096 && (reinterpret_cast<uintptr_t>(dev_q) & 15) == 0;
+  pd.active = true;
+  if (!pd.use_tc) {  // shapes the tensor path does not take: the brute-force scan, enqueued here, nothing left for finish
+    idx->n_fallback = nq;
+    int rc = exact_bruteforce(idx, dev_q, nullptr, nq, k, dev_scores, dev_ids, idx->ws, st);
+    pd.active = rc == AHR_OK;
+    pd.done = true;
+    return rc;
+  }
+  ExactScratch x;
+  int rc = exact_scratch(idx, nq, k, x);
+  if (rc == AHR_OK) rc = exact_tier(idx, x, dev_q, nq, k <= 50 ? KC_SMALL : KC_BIG, k, dev_scores, dev_ids, x.flist, st);
+  if (rc != AHR_OK) { pd.active = false; return rc; }
+  *idx->h_nfail = -1;
+  AHR_CUDA_CHECK(cudaMemcpyAsync(idx->h_nfail, x.fcnt, 4, cudaMemcpyDeviceToHost, st));  // pinned destination
+  AHR_CUDA_CHECK(cudaEventRecord(idx->ev_nfail, st));
+  return AHR_OK;
+}
+
+int ahr_topk_exact_finish(ahr_index *idx) {
+  AHR_REQUIRE(idx != nullptr, "ahr_topk_exact_finish: index is NULL");
+  auto &pd = idx->pending;
+  if (!pd.active) return AHR_OK;  // nothing pending (nq == 0)
+  pd.active = false;
+  if (pd.done) return AHR_OK;
+  DeviceGuard guard(idx->device);
+  cudaStream_t st = pd.stream;
+  const int32_t nq = pd.nq, k = pd.k;
+  AHR_CUDA_CHECK(cudaEventSynchronize(idx->ev_nfail));  // the one wait of the common case: tier 1 has run
+  int32_t n_fail = *idx->h_nfail;
+  if (n_fail == 0) {
+    idx->n_certified = nq;
+    return AHR_OK;
+  }
+  AHR_NVTX("ahr K1x exact mode: fallback tiers");
+  ExactScratch x;
+  int rc = exact_scratch(idx, nq, k, x);  // same layout as in begin (the workspace does not move: same size)
   if (rc != AHR_OK) return rc;
-  if (n_fail > 0 && kc1 == kc_small) {
+  const size_t row_bytes = (size_t)idx->dim * (idx->dtype == AHR_DTYPE_F32 ? 4 : 2);
+  if (k <= 50) {
     // tier 2 on the sub-batch of uncertified queries
     const int32_t n1 = n_fail;
-    rc = gather_query_rows(dev_q, (int64_t)row_bytes, flist, n1, qsub, st);
+    rc = gather_query_rows(pd.q, (int64_t)row_bytes, x.flist, n1, x.qsub, st);
+    if (rc == AHR_OK) rc = exact_tier(idx, x, x.qsub, n1, KC_BIG, k, x.fs, x.fi, x.flist2, st);
     if (rc != AHR_OK) return rc;
     int32_t n2 = 0;
-    rc = tier(qsub, n1, kc_big, fs, fi, flist2, &n2);
+    AHR_CUDA_CHECK(cudaMemcpyAsync(&n2, x.fcnt, 4, cudaMemcpyDeviceToHost, st));
+    AHR_CUDA_CHECK(cudaStreamSynchronize(st));
+    // rows of tier-2 failures are overwritten by tier 3 below
+    rc = gather_rows_i64(x.fs, x.fi, x.flist, n1, k, pd.scores, pd.ids, /*scatter=*/true, st);
     if (rc != AHR_OK) return rc;
-    rc = gather_rows_i64(fs, fi, flist, n1, k, dev_scores, dev_ids, /*scatter=*/true, st);  // rows of tier-2 failures are
-    if (rc != AHR_OK) return rc;                                                          // overwritten by tier 3 below
     if (n2 > 0) {  // compose the failure list: positions in the sub-batch -> original query indices
       std::vector<int32_t> h1(n1), h2(n2);
-      AHR_CUDA_CHECK(cudaMemcpyAsync(h1.data(), flist, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
-      AHR_CUDA_CHECK(cudaMemcpyAsync(h2.data(), flist2, (size_t)n2 * 4, cudaMemcpyDeviceToHost, st));
+      AHR_CUDA_CHECK(cudaMemcpyAsync(h1.data(), x.flist, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+      AHR_CUDA_CHECK(cudaMemcpyAsync(h2.data(), x.flist2, (size_t)n2 * 4, cudaMemcpyDeviceToHost, st));
       AHR_CUDA_CHECK(cudaStreamSynchronize(st));
       for (int32_t i = 0; i < n2; ++i) h2[i] = h1[h2[i]];
-      AHR_CUDA_CHECK(cudaMemcpyAsync(flist, h2.data(), (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
+      AHR_CUDA_CHECK(cudaMemcpyAsync(x.flist, h2.data(), (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
       AHR_CUDA_CHECK(cudaStreamSynchronize(st));  // h2 goes out of scope
     }
     n_fail = n2;
@@ -457,9 +536,9 @@ int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode,
   idx->n_certified = nq - n_fail;
   idx->n_fallback = n_fail;
   if (n_fail > 0) {
-    rc = exact_bruteforce(idx, dev_q, flist, n_fail, k, fs, fi, idx->ws, st);
+    rc = exact_bruteforce(idx, pd.q, x.flist, n_fail, k, x.fs, x.fi, idx->ws, st);
     if (rc != AHR_OK) return rc;
-    rc = gather_rows_i64(fs, fi, flist, n_fail, k, dev_scores, dev_ids, /*scatter=*/true, st);
+    rc = gather_rows_i64(x.fs, x.fi, x.flist, n_fail, k, pd.scores, pd.ids, /*scatter=*/true, st);
     if (rc != AHR_OK) return rc;
   }
   return AHR_OK;

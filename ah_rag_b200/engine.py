@@ -98,6 +98,26 @@ class VectorIndex:
                                     ids.data_ptr(), _stream_ptr(self.device)), "ahr_topk")
         return scores, ids
 
+    def topk_exact_begin(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """First half of an exact query: enqueues candidates + rescoring + certification and returns WITHOUT synchronising
+        (``ahr_topk_exact_begin``).  The returned tensors are final, in stream order, once ``topk_exact_finish`` returned."""
+        _require_cuda(q, "q")
+        if q.dim() != 2 or q.shape[1] != self.dim or q.dtype != self.dtype:
+            raise ValueError(f"q must be [nq, {self.dim}] {self.dtype}")
+        nq = int(q.shape[0])
+        scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        self._pending_q = q  # keep alive until finish
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_topk_exact_begin(self._h, q.data_ptr(), nq, int(k), scores.data_ptr(), ids.data_ptr(),
+                                                _stream_ptr(self.device)), "ahr_topk_exact_begin")
+        return scores, ids
+
+    def topk_exact_finish(self) -> None:
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_topk_exact_finish(self._h), "ahr_topk_exact_finish")
+        self._pending_q = None
+
     def topk_raw(self, q: torch.Tensor, k: int, mode: str, scores_ptr: int, ids_ptr: int) -> None:
         """Top-k written to raw device pointers ([nq, k] fp32 / int64), e.g. a slot of the peer exchange buffer."""
         _require_cuda(q, "q")

@@ -505,15 +505,33 @@ class HierarchicalGraph:
         self._dev_index = None
 
     # ------------------------------------------------------------------ device residency
+    _ATTR_FINGERPRINT_MAX_NODES = 5000
+
+    def _graph_sig(self):
+        """What the cached device graph is valid for.  ``add_*`` and ``load`` reset the caches themselves; this catches a
+        replaced graph object, nodes / edges added behind the class's back and -- for graphs up to
+        ``_ATTR_FINGERPRINT_MAX_NODES`` nodes, where it costs well under a millisecond -- attributes edited in place through
+        ``hg.G.nodes[...]`` (the reference reads G on every call).  Larger graphs: call ``invalidate_device_cache()`` after
+        editing node attributes directly."""
+        n = self.G.number_of_nodes()
+        sig = (id(self.G), n, self.G.number_of_edges())
+        if n <= self._ATTR_FINGERPRINT_MAX_NODES:
+            import zlib
+            h = 0
+            for _, d in self.G.nodes(data=True):
+                h = zlib.crc32(repr((d.get("node_type"), d.get("level"), d.get("judge_scores"), d.get("confidence"))).encode(), h)
+            sig += (h,)
+        return sig
+
     def _graph_arrays(self) -> Dict[str, Any]:
         """Host copy of the CSR + attribute arrays of the current graph (cached until the graph changes)."""
-        sig = (id(self.G), self.G.number_of_nodes(), self.G.number_of_edges())
+        sig = self._graph_sig()
         if self._host_arrays is None or self._host_arrays[0] != sig:
             self._host_arrays = (sig, self._export_arrays())
         return self._host_arrays[1]
 
     def _device_graph(self) -> Dict[str, Any]:
-        sig = (id(self.G), self.G.number_of_nodes(), self.G.number_of_edges())
+        sig = self._graph_sig()
         if self._dev_graph is None or self._dev_graph["sig"] != sig:
             from .. import engine
             arrays = self._graph_arrays()
@@ -615,9 +633,12 @@ class HierarchicalGraph:
         q = query_embeddings if isinstance(query_embeddings, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(query_embeddings, dtype=np.float32))
         k_eff = min(int(top_k), len(di["store"].ids))
+        if k_eff > 1024:
+            raise ValueError(f"top_k = {top_k} over an index of {len(di['store'].ids)} rows: the device top-k returns at most 1024 seeds per query")
         if self.index_dtype == "bf16":
             qd = q.to(dev).to(torch.bfloat16).contiguous()
-            scores, rows = di["index"].topk(qd, k_eff, mode="bf16")
+            # the tensor-core lists hold up to 120 entries; wider requests take the exact scan of the same bf16 rows
+            scores, rows = di["index"].topk(qd, k_eff, mode="bf16" if k_eff <= 120 else "exact")
         else:
             qd = q.to(dev).to(torch.float32).contiguous()
             scores, rows = di["index"].topk(qd, k_eff, mode="exact")

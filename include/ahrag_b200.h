@@ -99,10 +99,24 @@ int ahr_index_destroy(ahr_index *idx);
  *                   propose k + slack candidates, which are re-scored canonically and CERTIFIED (k-th exact score
  *                   above the last candidate's tensor score + error bound); queries that cannot be certified, and
  *                   shapes the tensor path does not take (k > 96, n_rows <= 4096, dim % 8 != 0), run the brute-force
- *                   fp64 scan.  Synchronises the stream internally (certification count).
+ *                   fp64 scan.  = ahr_topk_exact_begin + ahr_topk_exact_finish: waits once for the certification count
+ *                   (and again per fallback tier when some query could not be certified).
  */
 int ahr_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, int mode, float *dev_scores,
              int64_t *dev_ids, void *stream);
+
+/*
+ * AHR_MODE_EXACT in two halves, for callers that overlap the query with other work or capture it in a CUDA graph:
+ *   begin   enqueues the tensor-core candidates, the canonical rescoring and the certification on `stream` and returns
+ *           WITHOUT synchronising (shapes the tensor path does not take: the brute-force scan, also just enqueued);
+ *           the number of uncertified queries travels to a pinned host word behind an event;
+ *   finish  waits for that event; in the common case (every query certified) that is all it does -- dev_scores / dev_ids
+ *           are final in stream order.  Otherwise it runs the wider candidate tier and the brute-force scan for the
+ *           uncertified queries (these synchronise `stream`).  One exact query per index may be pending at a time.
+ */
+int ahr_topk_exact_begin(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, float *dev_scores, int64_t *dev_ids,
+                         void *stream);
+int ahr_topk_exact_finish(ahr_index *idx);
 
 /* Same query through HOST buffers: copies host_q to the device, runs ahr_topk, copies results back and
  * synchronises the stream.  This is the call bench.py times for the end-to-end ("e2e") figure. */

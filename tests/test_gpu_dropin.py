@@ -155,3 +155,24 @@ def test_expand_to_lca_matches_reference_golden(name, tmp_path):
         info = {k: v for k, v in info.items() if k != "time_s"}
         assert gu.canon(obs) == gu.canon(case["obs"]), case["node_ids"]
         assert gu.canon(info) == gu.canon(case["info"]), case["node_ids"]
+
+
+def test_attribute_edits_in_place_reach_the_device_graph(tmp_path):
+    """the reference reads G on every call.  Editing a node attribute through hg.G.nodes[...] (no add_* call,
+    node / edge counts unchanged) must change the next search like it changes the reference's: the cached device graph is
+    keyed by an attribute fingerprint for graphs of this size."""
+    fx = gu.load("g_small_s3")
+    hg, _ = _make_hg(fx, tmp_path)
+    q = fx["queries"][0]
+    before = hg.search(q, top_k=5)
+    target = next(r["node_id"] for r in before if r["node_type"] == "summary")
+    hg.G.nodes[target]["judge_scores"] = json.dumps({"overall": 0.0})
+    hg.G.nodes[target]["confidence"] = 0.0
+    after = hg.search(q, top_k=5)
+    got = next((r for r in after if r["node_id"] == target), None)
+    old = next(r for r in before if r["node_id"] == target)
+    assert got is None or (got["judge_overall"] == 0.0 and got["score"] < old["score"])
+    # a request wider than the tensor-core lists on a bf16 index takes the exact scan instead of raising
+    hg.index_dtype = "bf16"
+    wide = hg.search(q, top_k=200)
+    assert len(wide) > 0

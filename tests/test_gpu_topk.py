@@ -265,3 +265,29 @@ def test_merge_of_sorted_lists_equals_oracle_merge(engine, parts, k, nq):
     ws, wi = exact.merge_topk([scores[p] for p in range(parts)], [ids[p] for p in range(parts)], k)
     assert np.array_equal(mi.cpu().numpy(), wi)
     assert np.array_equal(ms.cpu().numpy().view(np.uint32), ws.view(np.uint32))
+
+
+def test_exact_mode_in_two_halves_equals_the_one_call_form(engine):
+    """ahr_topk_exact_begin enqueues tier 1 without synchronising; other work can be queued before ahr_topk_exact_finish.
+    Cases: every query certified (finish only waits), near-duplicate rows (fallback tiers run inside finish), a shape the
+    tensor path does not take (brute force enqueued by begin)."""
+    rng = np.random.default_rng(3)
+    for n, dim, nq, k, dup in ((20000, 128, 300, 50, False), (9000, 64, 70, 50, True), (3000, 64, 9, 10, False)):
+        Xn, Qn = synth.unit_rows(n, dim, 71, clustered=8), synth.unit_rows(nq, dim, 72, clustered=8)
+        if dup:  # 80 copies of one row around every query's rank k: tensor-core scores tie, certification must fail
+            Xn[100:180] = Xn[100]
+            Qn[:] = Xn[100] + 0.01 * rng.standard_normal((nq, dim)).astype(np.float32)
+            Qn /= np.linalg.norm(Qn, axis=1, keepdims=True)
+        X, Q = _bf16(Xn), _bf16(Qn)
+        idx = engine.VectorIndex(X)
+        s, i = idx.topk_exact_begin(Q, k)
+        other = idx.rows.float().sum()  # unrelated work queued between the halves
+        with pytest.raises(RuntimeError):
+            idx.topk_exact_begin(Q, k)  # one pending exact query per index
+        idx.topk_exact_finish()
+        cert, fb = idx.exact_stats()
+        assert cert + fb == nq and (fb > 0) == (dup or n <= 4096), (cert, fb)
+        rs, ri = exact.exact_topk(_bits(X), _bits(Q), k)
+        assert np.array_equal(i.cpu().numpy(), ri) and np.array_equal(s.cpu().numpy().view(np.uint32), rs.view(np.uint32))
+        ws, wi = idx.topk(Q, k, mode="exact")
+        assert torch.equal(wi, i) and torch.equal(ws, s) and bool(torch.isfinite(other))
