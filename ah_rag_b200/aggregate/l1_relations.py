@@ -6,8 +6,11 @@ centroids per pair.  Here the three T x T matrices are built at once:
 
   overlap   sparse incidence product  M . M^T  (M: topics x members, scipy)                        exact integers
   jaccard   overlap / (|A| + |B| - overlap) in float64 -- the same IEEE division as len(inter) / len(union)  exact
-  cosine    all pairs of L2-normalised fp32 centroids on the GPU: ``VectorIndex.rescore`` (csrc/topk_exact.cu),
-            the canonical score float32(sum_j double(a_j) * double(b_j)) = the correctly rounded fp32 dot product.
+  cosine    the T x T contraction of the L2-normalised fp32 centroids runs on the TENSOR CORES (K1, hi/lo bf16 split of the
+            fp32 rows, ~2^-16 accurate); only the pairs that can matter -- tensor score within the error bound of
+            ``min_cosine``, or kept by the overlap / Jaccard rule -- are re-scored canonically (``VectorIndex.rescore``,
+            csrc/topk_exact.cu: float32(sum_j double(a_j) * double(b_j)) = the correctly rounded fp32 dot product), so every
+            cosine that is compared with ``min_cosine`` or reported is the canonical one.
             ``np.dot`` on fp32 vectors (BLAS sdot) accumulates in an implementation-defined order, so the two differ by a
             few fp32 ulps (<= ~2e-6 here): the 4-decimal ``cosine`` / ``weight`` fields agree except on exact rounding
             boundaries, and a pair whose cosine sits within that distance of ``min_cosine`` may fall on the other side.
@@ -36,22 +39,47 @@ def _normalised(v: Optional[List[float]]) -> Optional[np.ndarray]:
     return arr / n if n > 0 else arr
 
 
-def _device_cosines(rows: np.ndarray, device: str = "cuda") -> np.ndarray:
-    """[T, T] canonical fp32 dot products of the rows (each already L2-normalised), computed on the GPU."""
+def _device_cosines(rows: np.ndarray, device: str = "cuda", needed: Optional[np.ndarray] = None,
+                    min_cosine: Optional[float] = None) -> np.ndarray:
+    """[T, T] dot products of the rows (each already L2-normalised), computed on the GPU.
+
+    ``needed is None``: every entry is the canonical fp32 score (one thread per pair, the first implementation).
+    Otherwise (``needed``: bool [T, T], ``min_cosine``): the contraction runs on the tensor cores and only the pairs with
+    ``needed`` set or a tensor score >= min_cosine - eps are re-scored canonically; all other entries keep the tensor-core
+    value, which is provably below ``min_cosine`` (eps = the certification bound of the exact top-k mode for fp32 rows)."""
     import torch
     from .. import engine
     dev = torch.device(device)
     x = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)).to(dev)
     index = engine.VectorIndex(x)
-    t = int(x.shape[0])
-    out = np.empty((t, t), dtype=np.float32)
+    t, d = int(x.shape[0]), int(x.shape[1])
     ids = torch.arange(t, device=dev, dtype=torch.int64)
-    step = max(1, min(t, (1 << 22) // max(t, 1)))  # <= 4M (query, candidate) pairs per launch
-    for q0 in range(0, t, step):
-        q1 = min(t, q0 + step)
-        cand = ids.unsqueeze(0).expand(q1 - q0, t).contiguous()
-        out[q0:q1] = index.rescore(x[q0:q1].contiguous(), cand).cpu().numpy()
-    return out
+    if needed is None or min_cosine is None or d % 8 != 0:
+        out = np.empty((t, t), dtype=np.float32)
+        step = max(1, min(t, (1 << 22) // max(t, 1)))  # <= 4M (query, candidate) pairs per launch
+        for q0 in range(0, t, step):
+            q1 = min(t, q0 + step)
+            cand = ids.unsqueeze(0).expand(q1 - q0, t).contiguous()
+            out[q0:q1] = index.rescore(x[q0:q1].contiguous(), cand).cpu().numpy()
+        return out
+    tc = index.debug_tc_scores(x)  # [T, T] tensor-core accumulators (fp32 rows: hi/lo bf16 split, three operand segments)
+    norms = x.double().norm(dim=1)
+    eps = float(((3 * d / 2 + 64) * 2.0 ** -23 + 2.0 ** -16) * float(norms.max()) ** 2)  # api.cu: exact_eps_rel, fp32 rows
+    cand = (tc >= (min_cosine - eps)) | torch.from_numpy(np.ascontiguousarray(needed)).to(dev)
+    cand &= torch.triu(torch.ones((t, t), dtype=torch.bool, device=dev), diagonal=1)  # the rules read a < b only
+    counts = cand.sum(dim=1)
+    m = int(counts.max().item()) if t else 0
+    out = tc.clone()
+    if m > 0:
+        # ragged candidate lists, padded with -1 (re-scored as -inf and never scattered)
+        order = torch.argsort(cand.to(torch.int8), dim=1, descending=True, stable=True)[:, :m]
+        valid = torch.arange(m, device=dev)[None, :] < counts[:, None]
+        cand_ids = torch.where(valid, order, torch.full_like(order, -1)).contiguous()
+        sc = index.rescore(x, cand_ids)
+        r, c = torch.nonzero(valid, as_tuple=True)
+        out[r, cand_ids[r, c]] = sc[r, c]
+        out[cand_ids[r, c], r] = sc[r, c]
+    return out.cpu().numpy()
 
 
 def generate_l1_relations(l1_nodes: List[Dict[str, Any]], min_overlap: int = 3, min_jaccard: float = 0.2,
@@ -92,7 +120,11 @@ def generate_l1_relations(l1_nodes: List[Dict[str, Any]], min_overlap: int = 3, 
     if has_c.any():
         sel = np.flatnonzero(has_c)
         mat = np.stack([centroids[topic_ids[i]] for i in sel]).astype(np.float32)
-        c = np.asarray(cosine_fn(mat) if cosine_fn is not None else _device_cosines(mat, device), dtype=np.float32)
+        if cosine_fn is not None:
+            c = np.asarray(cosine_fn(mat), dtype=np.float32)
+        else:  # pairs kept by the set rules need their canonical cosine as well (it is reported in the edge)
+            set_rule = ((overlap >= min_overlap) | (jaccard >= min_jaccard))[np.ix_(sel, sel)]
+            c = np.asarray(_device_cosines(mat, device, needed=set_rule, min_cosine=float(min_cosine)), dtype=np.float32)
         cosine[np.ix_(sel, sel)] = c.astype(np.float64)  # float(np.float32) is exact
 
     # ---- rules on the upper triangle, in (a, b) order with a < b ------------------------------------------------

@@ -275,7 +275,7 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bo
                                                    int64_t q_global, const TcParams &p, uint32_t lists_warp,
                                                    uint32_t scratch_warp, float &thr, int &cnt,
                                                    unsigned long long *n_slow, uint32_t *bound_slot, int bound_m,
-                                                   float &best, Release release) {
+                                                   float &best, bool young, Release release) {
   const int lane = threadIdx.x & 31;
   const uint32_t my_list = lists_warp + (uint32_t)lane * (KLIST * 8);
   const uint32_t scratch_lane = scratch_warp + (uint32_t)lane * 4;
@@ -334,6 +334,10 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bo
   };
 #pragma unroll 1
   for (int c = 0; c < BN; c += 64) {  // two chunks per iteration: the register buffers alternate statically
+    // first tile of an item: no bound exists when it starts (all slabs start together), and without one its 256 columns
+    // cost ~130 appends and ~6 compactions per row -- most of what is left of the MMA's wait for TMEM.  The other slabs
+    // publish within their first chunk, so look again every 64 columns.
+    if (young && c > 0) thr = shared_bound_apply(shared_bound_peek(p, q_global, bound_slot != nullptr), thr);
     tmem_ld_wait();
     tmem_ld_32x32b_x32(t_acc + (uint32_t)(c + 32), vb);
     scan(va, c);

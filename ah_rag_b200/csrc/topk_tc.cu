@@ -163,7 +163,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int ncols = (int)min((int64_t)TC_BN, p.n_rows - col0);
         uint64_t *release_bar = &tempty[acc];
         epilogue_scan_tile<KLIST, TC_BN, DBG>(t_lane + (uint32_t)(acc * TC_BN), ncols, row_valid, k, col0, q_global, p,
-                                              lists_warp, scratch_warp, thr, cnt, nullptr, bound_slot, p.bound_m, best, [&]() {
+                                              lists_warp, scratch_warp, thr, cnt, nullptr, bound_slot, p.bound_m, best, age == 0, [&]() {
                                                 tc_fence_before();
                                                 __syncwarp();
                                                 if (lane == 0) mbar_arrive(release_bar);

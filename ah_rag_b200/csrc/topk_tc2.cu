@@ -250,7 +250,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int ncols = (int)min((int64_t)T2_BN, p.n_rows - col0);
         const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[acc]), 0);
         epilogue_scan_tile<KLIST, T2_BN, DBG>(t_lane + (uint32_t)(acc * T2_BN), ncols, row_valid, k, col0, q_global, p,
-                                              lists_warp, scratch_warp, thr, cnt, p.stats ? n_slow : nullptr, bound_slot, p.bound_m, best, [&]() {  // uniform: every lane counts
+                                              lists_warp, scratch_warp, thr, cnt, p.stats ? n_slow : nullptr, bound_slot, p.bound_m, best, age == 0, [&]() {  // uniform: every lane counts
                                                 tc_fence_before();
                                                 __syncwarp();
                                                 if (lane == 0) mbar_arrive_cluster(tempty_leader);  // leader's barrier

@@ -53,3 +53,22 @@ def test_l1_relations_on_device_against_reference_golden():
                 assert abs(e["cosine"] - min_cos) <= 2e-4, (key, e)
         else:
             assert len(edges) == len(c["edges"]) and len(odd) <= 2
+
+
+def test_tensor_core_cosines_with_sparse_canonical_rescoring():
+    """f3 on the tensor cores: the T x T contraction runs through K1 (fp32 rows as hi/lo bf16 halves); every pair that is
+    compared with min_cosine at close range or reported carries the canonical score, all others are provably below it."""
+    from ah_rag_b200.aggregate.l1_relations import _device_cosines, _normalised
+    rng = np.random.default_rng(9)
+    for t, d, min_cos in ((300, 48, 0.3), (700, 384, 0.15), (64, 16, 0.5)):
+        base = rng.normal(size=(8, d))
+        mat = np.stack([_normalised((base[i % 8] + 0.6 * rng.normal(size=d)).tolist()) for i in range(t)]).astype(np.float32)
+        needed = rng.random((t, t)) < 0.02
+        got = _device_cosines(mat, needed=needed, min_cosine=min_cos)
+        want = exact.canonical_scores(mat, mat)
+        up = np.triu(np.ones((t, t), dtype=bool), k=1)
+        must = up & (needed | (want >= min_cos))
+        assert must.sum() > 0
+        assert np.array_equal(got[must].view(np.uint32), want[must].view(np.uint32))      # canonical where it matters
+        assert np.array_equal((got >= min_cos) & up, (want >= min_cos) & up)              # same side of the threshold everywhere
+        assert np.abs(got - want).max() <= 1e-4                                           # the rest: tensor-core accuracy

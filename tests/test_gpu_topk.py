@@ -274,8 +274,8 @@ def test_exact_mode_in_two_halves_equals_the_one_call_form(engine):
     rng = np.random.default_rng(3)
     for n, dim, nq, k, dup in ((20000, 128, 300, 50, False), (9000, 64, 70, 50, True), (3000, 64, 9, 10, False)):
         Xn, Qn = synth.unit_rows(n, dim, 71, clustered=8), synth.unit_rows(nq, dim, 72, clustered=8)
-        if dup:  # 80 copies of one row around every query's rank k: tensor-core scores tie, certification must fail
-            Xn[100:180] = Xn[100]
+        if dup:  # 150 copies of one row around every query's rank k: the tensor-core scores tie at both candidate widths
+            Xn[100:250] = Xn[100]  # (56 and 112), certification must fail twice and the brute-force scan decides
             Qn[:] = Xn[100] + 0.01 * rng.standard_normal((nq, dim)).astype(np.float32)
             Qn /= np.linalg.norm(Qn, axis=1, keepdims=True)
         X, Q = _bf16(Xn), _bf16(Qn)
