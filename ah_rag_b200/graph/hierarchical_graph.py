@@ -299,7 +299,7 @@ class HierarchicalGraph:
         # node_link_graph copies the attribute dicts it reads and leaves the document untouched
         hg._source = {"dir": directory, "key": snapshot.key_of(raw), "doc": data, "edges": key}
         hg.G = nx.node_link_graph(data, directed=True, edges=key)
-        hg._source["sig"] = (hg.G.number_of_nodes(), hg.G.number_of_edges())
+        hg._source["sig"] = hg._graph_sig()[1:]  # (nodes, edges[, attribute fingerprint]) of the document as loaded
         for nid, attr in hg.G.nodes(data=True):
             if attr.get("node_type") == "entity" and attr.get("name"):
                 hg.name_to_entity_id[attr["name"]] = nid
@@ -546,7 +546,7 @@ class HierarchicalGraph:
         from .. import csr as csr_mod
         from . import snapshot
         src = self._source
-        if src is not None and src.get("sig") == (self.G.number_of_nodes(), self.G.number_of_edges()):
+        if src is not None and src.get("sig") == self._graph_sig()[1:]:  # still the document that was loaded
             arrays = snapshot.load(src["dir"], src["key"])
             if arrays is None and src.get("doc") is not None:
                 arrays = csr_mod.csr_from_node_link(src["doc"], edges=src["edges"])
@@ -580,9 +580,12 @@ class HierarchicalGraph:
         return cur
 
     def invalidate_device_cache(self) -> None:
+        """Call after editing nodes / edges / attributes behind the class's back (``hg.G...``): the next search exports the
+        graph again by walking NetworkX (the on-disk snapshot describes the document as loaded, not the edited graph)."""
         self._dev_graph = None
         self._host_arrays = None
         self._dev_index = None
+        self._source = None
 
     # ------------------------------------------------------------------ search (:675-789)
     def _resolve(self, member_top_m, alpha, beta, gamma, delta, judge_overall_min, confidence_min, type_filter):
