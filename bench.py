@@ -389,6 +389,12 @@ def main() -> int:
     qps_e2e = N_QUERIES / (ms_e2e / args.steps / 1e3)
     peaks = _peaks()
     k1_ms = prof["k1_ms_total"] / max(1, prof["k1_launches"])
+    k1_all = [k1_ms]
+    if world > 1:  # every rank's K1 time: the step waits for the slowest GPU (clocks differ under the power cap)
+        t = torch.tensor([k1_ms], device=device, dtype=torch.float64)
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        k1_all = [float(x.item()) for x in g]
     flops = 2.0 * N_QUERIES * (hi - lo) * DIM  # algorithmic flops of one K1 launch on this rank's shard
     achieved = flops / (k1_ms / 1e3) / 1e12 if k1_ms > 0 else 0.0
 
@@ -413,6 +419,8 @@ def main() -> int:
                          "algorithmic_flops_per_launch": flops,
                          "frac_of_burst_peak": (achieved / peaks["tflops_burst"]) if peaks.get("tflops_burst") else None,
                          "kernel_ms": k1_ms, "kernel_share_of_step": k1_ms / ms_step if ms_step else None,
+                         "kernel_ms_per_rank": k1_all,
+                         "slowest_rank_kernel_share_of_step": max(k1_all) / ms_step if ms_step else None,
                          "peak_source": peaks["source"],
                          "hbm_floor_ms": (hi - lo) * DIM * 2 / (peaks["hbm_gbs"] * 1e9) * 1e3},
             "clocks": clocks,
