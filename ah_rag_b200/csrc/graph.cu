@@ -436,50 +436,48 @@ expand_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const
 // HBM (profiles/r1_c5_v7.json).  Order only matters for WHICH occurrence of a value survives and WHERE it lands, and both
 // follow from positions, so the insertion itself needs no order:
 //   every neighbour gets its position p in the reference's concatenation (segment base + offset; excluded elements leave
-//   holes, which is harmless -- positions only have to be monotone);
-//   insert    all threads at once: claim the value's slot of a shared-memory hash table (atomicCAS) and atomicMin p into it;
-//   resolve   element p is the first occurrence of its value iff the table holds p: set bit p of a bitmap;
+//   holes, which is harmless -- positions only have to be monotone); thread t owns the positions p = t (mod 64) of a round
+//   and keeps their (value, table slot) in REGISTERS;
+//   insert    all threads at once: one 64-bit compare-and-swap claims the value's slot of a shared-memory hash table with
+//             (value << 32 | p + 1); a later occurrence with a lower position (rare: a duplicate) lowers it with atomicMin;
+//   resolve   element p is the first occurrence of its value iff the table holds p + 1: one ballot per warp gives the bitmap;
 //   compact   output index = number of set bits below p (prefix popcount) + what earlier rounds emitted.
-// Long inputs are processed in rounds of `W` positions against the same table (values emitted by earlier rounds stay in
-// it, marked -1); a round that brings the output to `limit` ends the call, so the table never holds more than
+// The first version kept value / slot per position in shared memory and used two 32-bit atomics per neighbour: the
+// shared-memory pipe, not HBM, bound it (l1tex 83 %, 40.8 M bank-conflict cycles, profiles/r2_k2_ncu.md).
+// Long inputs are processed in rounds of W positions against the same table (values emitted by earlier rounds stay in it,
+// position field 0); a round that brings the output to `limit` ends the call, so the table never holds more than
 // (limit - 1) + W values.  The stop rule of the reference ("un-deduplicated length >= limit after finishing an input
 // node", environment.py:404-406) is evaluated per input node on the exact count of non-excluded neighbours.
 // ---------------------------------------------------------------------------------------------
 constexpr int EW_THREADS = 64;  // small CTAs: the walk is a chain of dependent loads, what counts is environments in flight per SM
 
-struct EwLayout {
-  int W;      // positions per round (multiple of 32)
-  int T_max;  // hash slots (power of two)
-  __host__ __device__ size_t bytes() const { return (size_t)T_max * 8 + (size_t)W * 4 + (size_t)W * 2 + (size_t)(W / 32) * 8; }
-};
 __host__ __device__ inline int ew_table_slots(int values) {  // open addressing at a load factor <= 0.75
   int t = 64;
   while (3 * t < 4 * values) t <<= 1;
   return t;
 }
-__host__ __device__ inline EwLayout ew_layout(int limit) {
-  EwLayout l;
-  l.W = 256;  // a round about half as long as the limit: 9.8 KB per CTA at limit 512 -> 23 CTAs (environments) per SM
-  while (2 * l.W < limit) l.W <<= 1;
-  l.T_max = ew_table_slots(limit + l.W);
-  return l;
+// U = positions per thread and round (W = 64 * U): about half the limit, so that an SM holds ~20 environments at limit 512
+__host__ __device__ inline int ew_units(int limit) { return limit <= 512 ? 4 : (limit <= 1024 ? 8 : 16); }
+__host__ __device__ inline size_t ew_smem_bytes(int limit) {
+  const int W = 64 * ew_units(limit);
+  return (size_t)ew_table_slots(limit + W) * 8 + (size_t)(W / 32) * 8;
 }
 
+template <int U>
 __global__ void __launch_bounds__(EW_THREADS)
 expand_wide_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const int32_t *__restrict__ in_ids,
                    const int32_t *__restrict__ in_offsets, int32_t limit, int32_t *__restrict__ out_ids,
                    int32_t *__restrict__ out_counts) {
+  constexpr int W_MAX = 64 * U;
+  constexpr unsigned long long EMPTY = ~0ull;
   extern __shared__ __align__(16) uint8_t ew_smem[];
   __shared__ unsigned long long s_est;
   __shared__ int s_raw, s_total;
-  const EwLayout lay = ew_layout(limit);
-  int32_t *tkey = reinterpret_cast<int32_t *>(ew_smem);                 // [T] value, -1 = free
-  int32_t *tpos = tkey + lay.T_max;                                     // [T] lowest position this round; -1 = emitted earlier
-  int32_t *rval = tpos + lay.T_max;                                     // [W] value at round position p, -1 = hole
-  uint16_t *rslot = reinterpret_cast<uint16_t *>(rval + lay.W);         // [W] its table slot
-  uint32_t *bits = reinterpret_cast<uint32_t *>(rslot + lay.W);         // [W / 32] first-occurrence flags
-  uint32_t *pref = bits + lay.W / 32;                                   // [W / 32] exclusive prefix popcounts
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int T_max = ew_table_slots(limit + W_MAX);
+  unsigned long long *table = reinterpret_cast<unsigned long long *>(ew_smem);  // [T] value << 32 | position + 1 (0 = emitted earlier)
+  uint32_t *bits = reinterpret_cast<uint32_t *>(table + T_max);                // [W / 32] first-occurrence flags
+  uint32_t *pref = bits + W_MAX / 32;                                          // [W / 32] exclusive prefix popcounts
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int env = blockIdx.x;
   const int op = ops[env];
   const int32_t *ids = in_ids + in_offsets[env];
@@ -507,92 +505,100 @@ expand_wide_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, 
   }
   __syncthreads();
   const int est = (int)min(max(s_est, 1ull), (unsigned long long)(1 << 24));
-  const int W = min(lay.W, (est + 31) & ~31);
-  const int T = ew_table_slots(min(min(limit, est) + W, est));  // <= lay.T_max
-  const int tshift = 32 - (31 - __clz(T));        // hash = top log2(T) bits of the product
-  for (int i = tid; i < T; i += EW_THREADS) { tkey[i] = -1; tpos[i] = 0x7fffffff; }
-  for (int i = tid; i < W / 32; i += EW_THREADS) bits[i] = 0;
+  const int W = min(W_MAX, (est + 63) & ~63);                   // positions per round: whole waves of 64
+  const int T = ew_table_slots(min(min(limit, est) + W, est));  // <= T_max
+  const int tshift = 32 - (31 - __clz(T));                      // hash = top log2(T) bits of the product
+  for (int i = tid; i < T; i += EW_THREADS) table[i] = EMPTY;
   __syncthreads();
 
   int fill = 0, out_count = 0;  // uniform across the block
   int my_valid = 0;             // this thread's non-excluded neighbours of the current input node
   bool done = false;
+  int32_t r_val[U];             // the positions u * 64 + tid of the current round: value (-1 = hole / nothing) ...
+  int r_slot[U];                // ... and its table slot
+#pragma unroll
+  for (int u = 0; u < U; ++u) r_val[u] = -1;
 
-  auto insert = [&](int32_t val, bool valid, int p) {
-    int slot = 0;
-    if (valid) {
-      slot = (int)(((uint32_t)val * 2654435761u) >> tshift);
-      int probes = 0;
-      for (;;) {
-        AHR_DEV_ASSERT(slot >= 0 && slot < T && T <= lay.T_max && ++probes <= T);
-        const int32_t k = atomicCAS(&tkey[slot], -1, val);
-        if (k == -1 || k == val) break;
-        slot = (slot + 1) & (T - 1);
+  // claim the slot of `val` with position p (or lower the position an earlier claim holds); returns the slot
+  auto insert = [&](int32_t val, int p) {
+    const unsigned long long mine = ((unsigned long long)(uint32_t)val << 32) | (unsigned long long)(uint32_t)(p + 1);
+    int slot = (int)(((uint32_t)val * 2654435761u) >> tshift);
+    int probes = 0;
+    for (;;) {
+      AHR_DEV_ASSERT(slot >= 0 && slot < T && T <= T_max && ++probes <= T);
+      const unsigned long long old = atomicCAS(&table[slot], EMPTY, mine);
+      if (old == EMPTY) break;
+      if ((uint32_t)(old >> 32) == (uint32_t)val) {                    // seen before: this round (keep the lower position)
+        if ((uint32_t)old > (uint32_t)(p + 1)) atomicMin(&table[slot], mine);  // or an earlier one (position field 0 stays)
+        break;
       }
-      atomicMin(&tpos[slot], p);
+      slot = (slot + 1) & (T - 1);
     }
-    AHR_DEV_ASSERT(p >= 0 && p < W && W <= lay.W);
-    rval[p] = valid ? val : -1;
-    rslot[p] = (uint16_t)slot;
+    (void)probes;
+    return slot;
   };
   // resolve + compact the positions [0, fill) of this round
   auto flush = [&]() {
+    __syncthreads();  // every insert of the round has landed
+    uint32_t mybits[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = u * 64 + tid;
+      const bool fresh = u * 64 < W && r_val[u] >= 0 && (uint32_t)table[r_slot[u]] == (uint32_t)(p + 1);
+      mybits[u] = __ballot_sync(0xffffffffu, fresh);
+      if (lane == 0 && u * 64 < W) bits[u * 2 + warp] = mybits[u];
+    }
     __syncthreads();
-    for (int p = tid; p < fill; p += EW_THREADS)
-      if (rval[p] >= 0 && tpos[rslot[p]] == p) atomicOr(&bits[p >> 5], 1u << (p & 31));
-    __syncthreads();
-    if (tid < 32) {  // exclusive prefix popcount over the W / 32 (<= 64) words
+    if (tid < 32) {  // exclusive prefix popcount over the W / 32 (<= 32) words
       const int nw = W / 32;
-      const int c0 = lane < nw ? __popc(bits[lane]) : 0, c1 = 32 + lane < nw ? __popc(bits[32 + lane]) : 0;
-      int x0 = c0, x1 = c1;
+      const int c0 = lane < nw ? __popc(bits[lane]) : 0;
+      int x0 = c0;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const int y0 = __shfl_up_sync(0xffffffffu, x0, d), y1 = __shfl_up_sync(0xffffffffu, x1, d);
-        if (lane >= d) { x0 += y0; x1 += y1; }
+        const int y0 = __shfl_up_sync(0xffffffffu, x0, d);
+        if (lane >= d) x0 += y0;
       }
-      const int tot0 = __shfl_sync(0xffffffffu, x0, 31);
       if (lane < nw) pref[lane] = x0 - c0;
-      if (32 + lane < nw) pref[32 + lane] = tot0 + x1 - c1;
-      if (lane == 31) s_total = tot0 + x1;
+      if (lane == 31) s_total = x0;
     }
     __syncthreads();
-    for (int p = tid; p < fill; p += EW_THREADS) {
-      const uint32_t wbits = bits[p >> 5];
-      if (!((wbits >> (p & 31)) & 1u)) continue;
-      const int rank = out_count + pref[p >> 5] + __popc(wbits & ((1u << (p & 31)) - 1u));
-      AHR_DEV_ASSERT(rank >= 0);
-      if (rank < limit) out[rank] = rval[p];
-      tpos[rslot[p]] = -1;  // emitted (or beyond the limit, in which case the call ends here)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u * 64 < W && ((mybits[u] >> lane) & 1u)) {
+        const int rank = out_count + pref[u * 2 + warp] + __popc(mybits[u] & ((1u << lane) - 1u));
+        AHR_DEV_ASSERT(rank >= 0);
+        if (rank < limit) out[rank] = r_val[u];
+        table[r_slot[u]] = (unsigned long long)(uint32_t)r_val[u] << 32;  // emitted: position field 0 (or beyond the limit: the call ends)
+      }
+      r_val[u] = -1;
     }
     out_count = min(limit, out_count + s_total);
-    __syncthreads();  // the next round overwrites rval / rslot / s_total
-    for (int i = tid; i < W / 32; i += EW_THREADS) bits[i] = 0;  // next read: after the barrier that opens the next flush
     fill = 0;
     if (out_count >= limit) done = true;
+    __syncthreads();  // the next round's inserts must see the emitted marks; s_total / bits are rewritten
   };
   // one CSR segment (or, with literal >= 0, the single value `literal`) appended to the concatenation
-  auto segment = [&](int slot, int32_t v, int32_t exclude, int32_t literal) {
-    const int64_t p0 = literal >= 0 ? 0 : g.row_ptr[slot][v];
-    const int64_t len = literal >= 0 ? 1 : g.row_ptr[slot][v + 1] - p0;
+  auto segment = [&](int slot_csr, int32_t v, int32_t exclude, int32_t literal) {
+    const int64_t p0 = literal >= 0 ? 0 : g.row_ptr[slot_csr][v];
+    const int64_t len = literal >= 0 ? 1 : g.row_ptr[slot_csr][v + 1] - p0;
     int64_t off = 0;
     while (off < len && !done) {
       const int n = (int)min(len - off, (int64_t)(W - fill));
-      const int32_t *src = literal >= 0 ? nullptr : g.col_idx[slot] + p0 + off;
-      for (int i0 = 0; i0 < n; i0 += 4 * EW_THREADS) {  // four coalesced loads in flight per thread, then the inserts
-        int32_t val[4];
+      const int32_t *src = literal >= 0 ? nullptr : g.col_idx[slot_csr] + p0 + off - fill;  // src[p] for position p
+      int32_t val[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * EW_THREADS + tid;
-          val[u] = i < n ? (literal >= 0 ? literal : src[i]) : exclude;
-        }
+      for (int u = 0; u < U; ++u) {  // the loads first (coalesced: consecutive threads, consecutive positions) ...
+        const int p = u * 64 + tid;
+        val[u] = (p >= fill && p < fill + n) ? (literal >= 0 ? literal : src[p]) : -1;
+      }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * EW_THREADS + tid;
-          if (i < n) {
-            const bool valid = val[u] != exclude;
-            my_valid += valid ? 1 : 0;
-            insert(val[u], valid, fill + i);
-          }
+      for (int u = 0; u < U; ++u) {  // ... then the inserts
+        const int p = u * 64 + tid;
+        if (p >= fill && p < fill + n && val[u] != exclude) {
+          AHR_DEV_ASSERT(val[u] >= 0 && val[u] < g.n_nodes);
+          ++my_valid;
+          r_val[u] = val[u];
+          r_slot[u] = insert(val[u], p);
         }
       }
       fill += n;
@@ -601,10 +607,10 @@ expand_wide_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, 
     }
   };
   // pull a neighbour list into L2 while the lists before it are being inserted (one line per thread and step)
-  auto prefetch = [&](int slot, int32_t v) {
-    const int64_t p0 = g.row_ptr[slot][v], p1 = g.row_ptr[slot][v + 1];
-    const char *b = reinterpret_cast<const char *>(g.col_idx[slot] + p0);
-    const int64_t bytes = min((p1 - p0) * 4, (int64_t)(lay.W + limit) * 4);
+  auto prefetch = [&](int slot_csr, int32_t v) {
+    const int64_t p0 = g.row_ptr[slot_csr][v], p1 = g.row_ptr[slot_csr][v + 1];
+    const char *b = reinterpret_cast<const char *>(g.col_idx[slot_csr] + p0);
+    const int64_t bytes = min((p1 - p0) * 4, (int64_t)(W_MAX + limit) * 4);
     for (int64_t o = (int64_t)tid * 128; o < bytes; o += (int64_t)EW_THREADS * 128)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
   };
@@ -644,6 +650,16 @@ expand_wide_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, 
   if (tid == 0) out_counts[env] = out_count;
 }
 
+template <int U>
+static int launch_expand_wide(const GraphView &g, int32_t n_env, const int32_t *ops, const int32_t *in_ids,
+                              const int32_t *in_offsets, int32_t limit, int32_t *out_ids, int32_t *out_counts,
+                              cudaStream_t stream) {
+  const size_t smem = ew_smem_bytes(limit);  // <= 33 KB: no opt-in needed
+  expand_wide_kernel<U><<<n_env, EW_THREADS, smem, stream>>>(g, n_env, ops, in_ids, in_offsets, limit, out_ids, out_counts);
+  AHR_KERNEL_CHECK();
+  return AHR_OK;
+}
+
 int graph_expand(const GraphView &g, int32_t n_env, const int32_t *ops, const int32_t *in_ids,
                  const int32_t *in_offsets, int32_t limit, int32_t *out_ids, int32_t *out_counts, cudaStream_t stream) {
   AHR_REQUIRE(limit >= 1 && limit <= 2048, "expand: limit must be in [1, 2048] (got %d)", limit);
@@ -655,19 +671,10 @@ int graph_expand(const GraphView &g, int32_t n_env, const int32_t *ops, const in
     AHR_KERNEL_CHECK();
     return AHR_OK;
   }
-  const size_t smem = ew_layout(limit).bytes();
-  if (smem > 48 * 1024) {
-    static std::atomic<uint64_t> configured{0};
-    int dev = 0;
-    AHR_CUDA_CHECK(cudaGetDevice(&dev));
-    if (!((configured.load(std::memory_order_relaxed) >> (dev & 63)) & 1)) {
-      AHR_CUDA_CHECK(cudaFuncSetAttribute(expand_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      configured.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
-    }
-  }
-  expand_wide_kernel<<<n_env, EW_THREADS, smem, stream>>>(g, n_env, ops, in_ids, in_offsets, limit, out_ids, out_counts);
-  AHR_KERNEL_CHECK();
-  return AHR_OK;
+  const int U = ew_units(limit);
+  if (U == 4) return launch_expand_wide<4>(g, n_env, ops, in_ids, in_offsets, limit, out_ids, out_counts, stream);
+  if (U == 8) return launch_expand_wide<8>(g, n_env, ops, in_ids, in_offsets, limit, out_ids, out_counts, stream);
+  return launch_expand_wide<16>(g, n_env, ops, in_ids, in_offsets, limit, out_ids, out_counts, stream);
 }
 
 }  // namespace ahr
