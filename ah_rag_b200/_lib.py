@@ -32,7 +32,8 @@ EXPORTS = [
     "ahr_get_profile", "ahr_env_reset", "ahr_env_step", "ahr_comm_create", "ahr_comm_export", "ahr_comm_connect",
     "ahr_comm_destroy", "ahr_comm_begin", "ahr_comm_exchange_merge", "ahr_topk_sharded", "ahr_lca_closure",
     "ahr_graph_shard_create", "ahr_graph_shard_destroy", "ahr_expand_shard_record_ints", "ahr_expand_shard_stage1",
-    "ahr_expand_shard_stage2", "ahr_expand_shard_merge",
+    "ahr_expand_shard_stage2", "ahr_expand_shard_merge", "ahr_graph_shard_set_attrs", "ahr_anchor_shard_record_ints",
+    "ahr_anchor_shard_stage1", "ahr_anchor_shard_stage2", "ahr_anchor_shard_merge",
 ]
 
 
@@ -96,13 +97,20 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.ahr_expand_shard_stage1.argtypes = [vp, c_int32, vp, vp, vp, c_int32, c_int32, vp, vp]
     lib.ahr_expand_shard_stage2.argtypes = [vp, c_int32, c_int32, vp, vp, vp, vp, c_int32, c_int32, vp, vp, vp]
     lib.ahr_expand_shard_merge.argtypes = [c_int, c_int64, c_int32, c_int32, vp, vp, vp, vp, c_int32, c_int32, vp, vp, vp, vp, vp]
+    lib.ahr_graph_shard_set_attrs.argtypes = [vp, vp, vp, vp, vp]
+    lib.ahr_anchor_shard_record_ints.argtypes = [c_int32, c_int32, POINTER(RerankParams)]
+    lib.ahr_anchor_shard_stage1.argtypes = [vp, c_int32, c_int32, vp, POINTER(RerankParams), vp, vp]
+    lib.ahr_anchor_shard_stage2.argtypes = [vp, c_int32, c_int32, c_int32, vp, vp, POINTER(RerankParams), vp, vp, vp]
+    lib.ahr_anchor_shard_merge.argtypes = [vp, c_int32, c_int32, c_int32, vp, vp, vp, POINTER(RerankParams), c_int32, vp, vp,
+                                           vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.ahr_lca_closure.argtypes = [vp, POINTER(c_int32), c_int32, vp, POINTER(c_int64), vp]
     lib.ahr_env_step.argtypes = [vp, POINTER(EnvBatch), vp, c_int32, c_double, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("ahr_last_error", "ahr_launch_count", "ahr_expand_shard_record_ints"):
+        if name not in ("ahr_last_error", "ahr_launch_count", "ahr_expand_shard_record_ints", "ahr_anchor_shard_record_ints"):
             fn.restype = c_int
     lib.ahr_expand_shard_record_ints.restype = c_int64
+    lib.ahr_anchor_shard_record_ints.restype = c_int64
 
 
 _lib = None

@@ -20,45 +20,6 @@ void set_error(const char *fmt, ...) {
   g_error = buf;
 }
 
-// Grow-only device buffer.  Growing must not synchronise the device (cudaFree does): the superseded allocation is RETIRED
-// -- kept until the handle is destroyed -- and the new one is at least 1.5x the old, so the retired blocks of a handle add
-// up to less than twice its final workspace.  Kernels already enqueued on the old block keep a valid pointer.
-struct DevBuf {
-  void *ptr = nullptr;
-  size_t bytes = 0;
-  std::vector<void *> retired;
-  int reserve(size_t need) {
-    if (need <= bytes) return AHR_OK;
-    need = std::max(need, bytes + bytes / 2);
-    need = (need + 255) & ~(size_t)255;
-    void *fresh = nullptr;
-    cudaError_t e = cudaMalloc(&fresh, need);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      // out of memory: give the retired blocks back (this does synchronise) and try once more
-      for (void *r : retired) cudaFree(r);
-      retired.clear();
-      e = cudaMalloc(&fresh, need);
-    }
-    if (e != cudaSuccess) {
-      set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
-      cudaGetLastError();
-      return AHR_E_NOMEM;
-    }
-    if (ptr) retired.push_back(ptr);
-    ptr = fresh;
-    bytes = need;
-    return AHR_OK;
-  }
-  void release() {
-    if (ptr) cudaFree(ptr);
-    for (void *r : retired) cudaFree(r);
-    retired.clear();
-    ptr = nullptr;
-    bytes = 0;
-  }
-};
-
 }  // namespace ahr
 
 using namespace ahr;

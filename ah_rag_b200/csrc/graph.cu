@@ -103,7 +103,25 @@ struct AnchorArgs {
   int32_t *exp_count;
   double *seed_sem;
   uint8_t *workspace;  // per query anchor_ws_per_query(cap, hsize) bytes when cap > AR_SMEM_CAP
+  AnchorGathered src;  // g1 != nullptr: the graph is sharded by node range, lines come as gathered stage records
 };
+
+__device__ __forceinline__ int anchor_owner(const AnchorGathered &s, int32_t v) {
+  int r = 0;
+  while (r + 1 < s.world && v >= s.bounds[r + 1]) ++r;
+  return r;
+}
+// attributes of a record: [.., judge(2), judge_term(2), conf(2)] at int offset 4, 8-byte aligned
+__device__ __forceinline__ NodeHead anchor_head_of(const int32_t *rec) {
+  NodeHead h;
+  const double *d = reinterpret_cast<const double *>(rec + 4);
+  h.judge = d[0]; h.judge_term = d[1]; h.conf = d[2];
+  h.anchor_deg = 0;
+  h.type = (uint8_t)rec[1];
+  h.level = (uint8_t)rec[3];
+  h.pad[0] = h.pad[1] = 0;
+  return h;
+}
 
 // large maps: sem[cap] rs[cap] c_rs[cap] (fp64) | node[cap] c_e[cap] h_key[hsize] h_first[hsize] h_seed[hsize] (int32) |
 // kind[cap] flag[cap] (u8)
@@ -218,6 +236,15 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
       if (j == 0) {
         node = v; sem = sem_r; kind = EK_SEED;
         if (a.seed_sem) a.seed_sem[(int64_t)q * a.n_seeds + r] = sem_r;
+      } else if (a.src.g1 != nullptr) {
+        // sharded graph: the owner of v sent its type and the capped head of its anchor list (graph_shard.cu, stage 1)
+        const int32_t *r1 = a.src.g1 + (((int64_t)anchor_owner(a.src, v) * a.nq + q) * a.n_seeds + r) * a.src.rec1;
+        const int t = r1[1], i = j - 1;
+        if (i < r1[2]) {  // r1[2] = min(cap of this node type, degree)
+          node = r1[ANCHOR_REC_HEAD + i];
+          sem = __dmul_rn(sem_r, t == AHR_NT_ENTITY ? 0.9 : 0.85);
+          kind = t == AHR_NT_ENTITY ? EK_PARENT : EK_MEMBER;
+        }
       } else {
         const NodeLine *L = g.line + v;
         const uint8_t t = L->head.type;
@@ -306,7 +333,14 @@ __global__ void __launch_bounds__(AR_THREADS) anchor_rerank_kernel(AnchorArgs a)
   for (int e = threadIdx.x; e < cap; e += AR_THREADS) {
     if (!(e_flag[e] & 1)) continue;
     const int32_t node = e_node[e];
-    const NodeHead rec = g.line[node].head;  // one sector: type, judge, judge_term, conf
+    NodeHead rec;
+    if (a.src.g1 != nullptr) {  // sharded graph: the attributes travelled with the stage records
+      const int r = e / per, j = e % per;
+      rec = j == 0 ? anchor_head_of(a.src.g1 + (((int64_t)anchor_owner(a.src, node) * a.nq + q) * a.n_seeds + r) * a.src.rec1)
+                   : anchor_head_of(a.src.g2 + ((((int64_t)anchor_owner(a.src, node) * a.nq + q) * a.n_seeds + r) * fan + (j - 1)) * ANCHOR_REC_HEAD);
+    } else {
+      rec = g.line[node].head;  // one sector: type, judge, judge_term, conf
+    }
     const uint8_t t = rec.type;
     const double judge = rec.judge, conf = rec.conf;
     const bool has_j = judge == judge, has_c = conf == conf;  // NaN encodes None
@@ -380,7 +414,7 @@ int graph_anchor_rerank(const GraphView &g, int32_t nq, int32_t n_seeds, const i
                         const float *seed_scores, const ahr_rerank_params &prm, int32_t top_k, int32_t *out_nodes,
                         double *out_sem, double *out_score, int32_t *out_count, int32_t *exp_nodes, double *exp_sem,
                         uint8_t *exp_kind, int32_t *exp_count, double *seed_sem, void *workspace,
-                        size_t workspace_bytes, cudaStream_t stream) {
+                        size_t workspace_bytes, cudaStream_t stream, const AnchorGathered *gathered) {
   AHR_REQUIRE(nq >= 0 && n_seeds >= 1 && top_k >= 1, "anchor_rerank: bad sizes nq=%d n_seeds=%d top_k=%d", nq, n_seeds, top_k);
   AHR_REQUIRE(prm.parent_cap >= 0 && prm.member_top_m >= 0, "anchor_rerank: negative caps");
   if (nq == 0) return AHR_OK;
@@ -399,6 +433,7 @@ int graph_anchor_rerank(const GraphView &g, int32_t nq, int32_t n_seeds, const i
   a.exp_nodes = exp_nodes; a.exp_sem = exp_sem; a.exp_count = exp_count; a.seed_sem = seed_sem;
   a.exp_kind = exp_kind;
   a.workspace = reinterpret_cast<uint8_t *>(workspace);
+  a.src = gathered ? *gathered : AnchorGathered{};
   if (cap > AR_SMEM_CAP) {
     AHR_REQUIRE(workspace && workspace_bytes >= (size_t)nq * anchor_ws_per_query((int)cap, a.hsize), "anchor_rerank: workspace too small");
     anchor_rerank_kernel<true><<<nq, AR_THREADS, 0, stream>>>(a);

@@ -32,6 +32,9 @@ struct ShardView {
   const int64_t *row_ptr[AHR_N_CSR];  // local: row v - lo
   const int32_t *col_idx[AHR_N_CSR];
   const uint8_t *node_type;           // local
+  // local attribute slices (anchor expansion over the sharded graph; optional)
+  const uint8_t *level = nullptr;
+  const double *judge = nullptr, *judge_term = nullptr, *conf = nullptr;
 };
 
 // record geometry shared by the three kernels and the host wrappers
@@ -197,6 +200,64 @@ shard_merge_kernel(ShardGeom geo, int64_t n_nodes, int32_t n_env, int32_t world,
   if (lane == 0) out_counts[env] = st.count;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Anchor expansion + rerank (hierarchical_graph.py:719-789) over the sharded graph: the two stages that replace the
+// NodeLine reads of anchor_rerank_kernel (graph.cu); the rerank itself is that same kernel, fed with the gathered records.
+//   stage 1 (owner of seed v)        type, attributes, and the first parent_cap parents (entity) / member_top_m members
+//                                    (summary) of v, in adjacency order
+//   stage 2 (owner of neighbour u)   type and attributes of every node stage 1 emitted
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void shard_write_head(int32_t *rec, const ShardView &g, int32_t v, int n_nbr) {
+  const int64_t r = v - g.lo;
+  rec[0] = SH_PRESENT;
+  rec[1] = g.node_type[r];
+  rec[2] = n_nbr;
+  rec[3] = g.level[r];
+  double *d = reinterpret_cast<double *>(rec + 4);
+  d[0] = g.judge[r]; d[1] = g.judge_term[r]; d[2] = g.conf[r];
+}
+
+__global__ void shard_anchor_stage1_kernel(ShardView g, int32_t nq, int32_t n_seeds, int32_t fan, int32_t rec1, int32_t parent_cap,
+                                           int32_t member_top_m, const int32_t *__restrict__ seeds, int32_t *__restrict__ out) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (int64_t)nq * n_seeds) return;
+  int32_t *rec = out + item * rec1;
+  const int32_t v = seeds[item];
+  if (v < g.lo || v >= g.hi) {
+    rec[0] = 0; rec[1] = AHR_NT_OTHER; rec[2] = 0; rec[3] = 0;
+    return;
+  }
+  const int64_t r = v - g.lo;
+  const int t = g.node_type[r];
+  const int slot = t == AHR_NT_ENTITY ? AHR_CSR_BEL_OUT : AHR_CSR_BEL_IN;
+  const int want = t == AHR_NT_ENTITY ? parent_cap : (t == AHR_NT_SUMMARY ? member_top_m : 0);
+  const int64_t p0 = g.row_ptr[slot][r], p1 = g.row_ptr[slot][r + 1];
+  const int n_nbr = (int)min((int64_t)min(want, fan), p1 - p0);
+  for (int j = 0; j < n_nbr; ++j) rec[ANCHOR_REC_HEAD + j] = g.col_idx[slot][p0 + j];
+  shard_write_head(rec, g, v, n_nbr);
+}
+
+__global__ void shard_anchor_stage2_kernel(ShardView g, int32_t nq, int32_t n_seeds, int32_t fan, int32_t rec1, int32_t world,
+                                           const int64_t *__restrict__ bounds, const int32_t *__restrict__ seeds,
+                                           const int32_t *__restrict__ gathered1, int32_t *__restrict__ out) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (int64_t)nq * n_seeds * fan) return;
+  const int j = (int)(item % fan);
+  const int64_t qr = item / fan;  // (query, seed)
+  int32_t *rec = out + item * ANCHOR_REC_HEAD;
+  const int32_t v = seeds[qr];
+  int32_t u = -1;
+  if (v >= 0 && v < g.n_nodes) {
+    const int32_t *r1 = gathered1 + ((int64_t)shard_owner(bounds, world, v) * nq * n_seeds + qr) * rec1;
+    if (j < r1[2]) u = r1[ANCHOR_REC_HEAD + j];
+  }
+  if (u < g.lo || u >= g.hi) {
+    rec[0] = 0; rec[1] = AHR_NT_OTHER; rec[2] = 0; rec[3] = 0;
+    return;
+  }
+  shard_write_head(rec, g, u, 0);
+}
+
 }  // namespace ahr
 
 using namespace ahr;
@@ -204,7 +265,10 @@ using namespace ahr;
 struct ahr_graph_shard {
   int device = 0;
   ShardView view;
+  DevBuf ws;  // workspace of the rerank over large expanded maps
 };
+
+static int anchor_rec1_ints(int32_t fan) { return ANCHOR_REC_HEAD + fan + (fan & 1); }  // even: the doubles stay 8-byte aligned
 
 static ShardGeom make_geom(int32_t limit, int32_t max_ids) {
   ShardGeom g;
@@ -239,8 +303,90 @@ int ahr_graph_shard_create(ahr_graph_shard **out, int device, int64_t n_nodes_to
 }
 
 int ahr_graph_shard_destroy(ahr_graph_shard *g) {
+  if (!g) return AHR_OK;
+  DeviceGuard guard(g->device);
+  g->ws.release();
   delete g;
   return AHR_OK;
+}
+
+int ahr_graph_shard_set_attrs(ahr_graph_shard *g, const uint8_t *dev_level_local, const double *dev_judge_local,
+                              const double *dev_judge_term_local, const double *dev_conf_local) {
+  AHR_REQUIRE(g != nullptr, "ahr_graph_shard_set_attrs: shard is NULL");
+  AHR_REQUIRE(g->view.hi == g->view.lo || (dev_level_local && dev_judge_local && dev_judge_term_local && dev_conf_local),
+              "ahr_graph_shard_set_attrs: NULL attribute array");
+  g->view.level = dev_level_local;
+  g->view.judge = dev_judge_local;
+  g->view.judge_term = dev_judge_term_local;
+  g->view.conf = dev_conf_local;
+  return AHR_OK;
+}
+
+int64_t ahr_anchor_shard_record_ints(int32_t stage, int32_t n_seeds, const ahr_rerank_params *params) {
+  if (!params || n_seeds < 1 || params->parent_cap < 0 || params->member_top_m < 0) return -1;
+  const int fan = std::max(params->parent_cap, params->member_top_m);
+  return stage == 1 ? (int64_t)n_seeds * anchor_rec1_ints(fan) : (stage == 2 ? (int64_t)n_seeds * fan * ANCHOR_REC_HEAD : -1);
+}
+
+int ahr_anchor_shard_stage1(ahr_graph_shard *g, int32_t nq, int32_t n_seeds, const int32_t *dev_seed_nodes,
+                            const ahr_rerank_params *params, int32_t *dev_out_records, void *stream) {
+  AHR_REQUIRE(g && params, "ahr_anchor_shard_stage1: NULL handle or params");
+  AHR_REQUIRE(g->view.hi == g->view.lo || g->view.judge != nullptr, "ahr_anchor_shard_stage1: call ahr_graph_shard_set_attrs first");
+  AHR_REQUIRE(nq >= 0 && n_seeds >= 1 && params->parent_cap >= 0 && params->member_top_m >= 0, "ahr_anchor_shard_stage1: bad sizes");
+  if (nq == 0) return AHR_OK;
+  AHR_REQUIRE(dev_seed_nodes && dev_out_records, "ahr_anchor_shard_stage1: NULL buffer");
+  DeviceGuard guard(g->device);
+  const int fan = std::max(params->parent_cap, params->member_top_m);
+  const int64_t items = (int64_t)nq * n_seeds;
+  shard_anchor_stage1_kernel<<<(unsigned)((items + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      g->view, nq, n_seeds, fan, anchor_rec1_ints(fan), params->parent_cap, params->member_top_m, dev_seed_nodes, dev_out_records);
+  AHR_KERNEL_CHECK();
+  return AHR_OK;
+}
+
+int ahr_anchor_shard_stage2(ahr_graph_shard *g, int32_t nq, int32_t n_seeds, int32_t world, const int64_t *dev_bounds,
+                            const int32_t *dev_seed_nodes, const ahr_rerank_params *params, const int32_t *dev_gathered1,
+                            int32_t *dev_out_records, void *stream) {
+  AHR_REQUIRE(g && params, "ahr_anchor_shard_stage2: NULL handle or params");
+  AHR_REQUIRE(g->view.hi == g->view.lo || g->view.judge != nullptr, "ahr_anchor_shard_stage2: call ahr_graph_shard_set_attrs first");
+  AHR_REQUIRE(nq >= 0 && n_seeds >= 1 && world >= 1, "ahr_anchor_shard_stage2: bad sizes");
+  const int fan = std::max(params->parent_cap, params->member_top_m);
+  if (nq == 0 || fan == 0) return AHR_OK;
+  AHR_REQUIRE(dev_bounds && dev_seed_nodes && dev_gathered1 && dev_out_records, "ahr_anchor_shard_stage2: NULL buffer");
+  DeviceGuard guard(g->device);
+  const int64_t items = (int64_t)nq * n_seeds * fan;
+  shard_anchor_stage2_kernel<<<(unsigned)((items + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      g->view, nq, n_seeds, fan, anchor_rec1_ints(fan), world, dev_bounds, dev_seed_nodes, dev_gathered1, dev_out_records);
+  AHR_KERNEL_CHECK();
+  return AHR_OK;
+}
+
+int ahr_anchor_shard_merge(ahr_graph_shard *g, int32_t nq, int32_t n_seeds, int32_t world, const int64_t *dev_bounds,
+                           const int32_t *dev_seed_nodes, const float *dev_seed_scores, const ahr_rerank_params *params,
+                           int32_t top_k, const int32_t *dev_gathered1, const int32_t *dev_gathered2, int32_t *dev_out_nodes,
+                           double *dev_out_semantic, double *dev_out_score, int32_t *dev_out_count, int32_t *dev_exp_nodes,
+                           double *dev_exp_semantic, uint8_t *dev_exp_kind, int32_t *dev_exp_count, double *dev_seed_semantic,
+                           void *stream) {
+  AHR_REQUIRE(g && params, "ahr_anchor_shard_merge: NULL handle or params");
+  if (nq == 0) return AHR_OK;
+  AHR_REQUIRE(world >= 1 && dev_bounds && dev_seed_nodes && dev_seed_scores && dev_gathered1 && dev_out_nodes && dev_out_semantic &&
+                  dev_out_score && dev_out_count, "ahr_anchor_shard_merge: NULL buffer");
+  AHR_REQUIRE(!dev_exp_nodes || dev_exp_semantic, "ahr_anchor_shard_merge: exp_nodes needs exp_semantic");
+  const int fan = std::max(params->parent_cap, params->member_top_m);
+  AHR_REQUIRE(fan == 0 || dev_gathered2, "ahr_anchor_shard_merge: stage-2 records are NULL");
+  DeviceGuard guard(g->device);
+  const size_t need = graph_anchor_workspace_bytes(nq, n_seeds, *params);
+  if (need) {
+    int rc = g->ws.reserve(need);
+    if (rc != AHR_OK) return rc;
+  }
+  GraphView view{};
+  view.n_nodes = g->view.n_nodes;  // lines / CSR are not read in gathered mode
+  AnchorGathered src;
+  src.g1 = dev_gathered1; src.g2 = dev_gathered2; src.bounds = dev_bounds; src.world = world; src.rec1 = anchor_rec1_ints(fan);
+  return graph_anchor_rerank(view, nq, n_seeds, dev_seed_nodes, nullptr, nullptr, 0, dev_seed_scores, *params, top_k, dev_out_nodes,
+                             dev_out_semantic, dev_out_score, dev_out_count, dev_exp_nodes, dev_exp_semantic, dev_exp_kind,
+                             dev_exp_count, dev_seed_semantic, g->ws.ptr, g->ws.bytes, reinterpret_cast<cudaStream_t>(stream), &src);
 }
 
 int64_t ahr_expand_shard_record_ints(int32_t stage, int32_t limit, int32_t max_ids) {

@@ -5,10 +5,53 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "../../include/ahrag_b200.h"
 
 namespace ahr {
+
+void set_error(const char *fmt, ...);
+
+// Grow-only device buffer.  Growing must not synchronise the device (cudaFree does): the superseded allocation is RETIRED
+// -- kept until the handle is destroyed -- and the new one is at least 1.5x the old, so the retired blocks of a handle add
+// up to less than twice its final workspace.  Kernels already enqueued on the old block keep a valid pointer.
+struct DevBuf {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  std::vector<void *> retired;
+  int reserve(size_t need) {
+    if (need <= bytes) return AHR_OK;
+    need = std::max(need, bytes + bytes / 2);
+    need = (need + 255) & ~(size_t)255;
+    void *fresh = nullptr;
+    cudaError_t e = cudaMalloc(&fresh, need);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      // out of memory: give the retired blocks back (this does synchronise) and try once more
+      for (void *r : retired) cudaFree(r);
+      retired.clear();
+      e = cudaMalloc(&fresh, need);
+    }
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+      cudaGetLastError();
+      return AHR_E_NOMEM;
+    }
+    if (ptr) retired.push_back(ptr);
+    ptr = fresh;
+    bytes = need;
+    return AHR_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    for (void *r : retired) cudaFree(r);
+    retired.clear();
+    ptr = nullptr;
+    bytes = 0;
+  }
+};
+
 
 // ---- topk_tc.cu (K1) ----
 int tc_make_corpus_map(CUtensorMap *map, const void *dev_rows, int64_t n_rows, int32_t dim);
@@ -118,12 +161,22 @@ struct GraphView {
   const int32_t *col_idx[AHR_N_CSR];
   const NodeLine *line;  // [n_nodes], library-owned
 };
+// Anchor expansion over a graph SHARDED by node range: instead of NodeLines the kernel reads the all-gathered records of
+// graph_shard.cu.  Stage 1 (owner of a seed), per (query, seed): [present, type, n_nbr, level, judge(2), judge_term(2),
+// conf(2)] + nbr[fan] (+ pad to an even count); stage 2 (owner of an emitted neighbour), per (query, seed, j): the same
+// 10-int head.  Buffers are [world][nq][n_seeds][...] in rank order.
+constexpr int ANCHOR_REC_HEAD = 10;
+struct AnchorGathered {
+  const int32_t *g1 = nullptr, *g2 = nullptr;
+  const int64_t *bounds = nullptr;  // [world + 1] first node id of every rank
+  int32_t world = 1, rec1 = 0;      // ints per stage-1 record
+};
 // seeds: dense node ids (seed_nodes), or index rows + the row -> node table (seed_rows / row_to_node / n_rows)
 int graph_anchor_rerank(const GraphView &g, int32_t nq, int32_t n_seeds, const int32_t *seed_nodes,
                         const int64_t *seed_rows, const int32_t *row_to_node, int64_t n_rows, const float *seed_scores, const ahr_rerank_params &prm, int32_t top_k, int32_t *out_nodes,
                         double *out_sem, double *out_score, int32_t *out_count, int32_t *exp_nodes, double *exp_sem,
                         uint8_t *exp_kind, int32_t *exp_count, double *seed_sem, void *workspace, size_t workspace_bytes,
-                        cudaStream_t stream);
+                        cudaStream_t stream, const AnchorGathered *gathered = nullptr);
 size_t graph_anchor_workspace_bytes(int32_t nq, int32_t n_seeds, const ahr_rerank_params &prm);
 int graph_expand(const GraphView &g, int32_t n_env, const int32_t *ops, const int32_t *in_ids,
                  const int32_t *in_offsets, int32_t limit, int32_t *out_ids, int32_t *out_counts, cudaStream_t stream);

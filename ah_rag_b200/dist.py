@@ -134,8 +134,11 @@ class ShardedGraph:
     records`` and ``merge(world, bounds, ops, ids, offs, max_ids, limit, g1, g2) -> (ids, counts)`` are injectable so the
     plumbing can be tested on CPU with gloo; in production they are the methods of ``engine.GraphShard``."""
 
-    def __init__(self, stage1: Callable, stage2: Callable, merge: Callable, bounds, group: Optional[dist.ProcessGroup] = None) -> None:
+    def __init__(self, stage1: Callable, stage2: Callable, merge: Callable, bounds, group: Optional[dist.ProcessGroup] = None,
+                 anchor_stage1: Optional[Callable] = None, anchor_stage2: Optional[Callable] = None,
+                 anchor_merge: Optional[Callable] = None) -> None:
         self.stage1, self.stage2, self.merge = stage1, stage2, merge
+        self.anchor_stage1, self.anchor_stage2, self.anchor_merge = anchor_stage1, anchor_stage2, anchor_merge
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -151,7 +154,8 @@ class ShardedGraph:
         n = int(arrays["n_nodes"])
         b = [shard_bounds(n, world, r)[0] for r in range(world)] + [n]
         shard = engine.GraphShard(arrays, b[rank], b[rank + 1], device)
-        obj = cls(shard.stage1, shard.stage2, shard.merge, torch.tensor(b, dtype=torch.int64, device=shard.device), group)
+        obj = cls(shard.stage1, shard.stage2, shard.merge, torch.tensor(b, dtype=torch.int64, device=shard.device), group,
+                  shard.anchor_stage1, shard.anchor_stage2, shard.anchor_merge)
         obj.shard = shard
         return obj
 
@@ -169,3 +173,12 @@ class ShardedGraph:
         g1 = self._gather(self.stage1(ops, in_ids, in_offsets, max_ids, limit))
         g2 = self._gather(self.stage2(self.world, self.bounds, ops, in_ids, in_offsets, max_ids, limit, g1))
         return self.merge(self.world, self.bounds, ops, in_ids, in_offsets, max_ids, limit, g1, g2)
+
+    def anchor_rerank(self, seed_nodes: torch.Tensor, seed_scores: torch.Tensor, params, top_k: int, want_cluster: bool = True):
+        """``GraphCSR.anchor_rerank`` (hierarchical_graph.py:719-789) over the sharded graph: seeds (dense node ids int32
+        [nq, n_seeds], e.g. the merged top-k of ``ShardedIndex``, identical on every rank) replicated; stage 1 on the owners
+        of the seeds, all-gather, stage 2 on the owners of the emitted neighbours, all-gather, the rerank kernel over the
+        gathered records.  Same dict of tensors, bit-identical to the unsharded call, on every rank."""
+        g1 = self._gather(self.anchor_stage1(seed_nodes, params))
+        g2 = self._gather(self.anchor_stage2(self.world, self.bounds, seed_nodes, params, g1))
+        return self.anchor_merge(self.world, self.bounds, seed_nodes, seed_scores, params, top_k, g1, g2, want_cluster)

@@ -396,6 +396,9 @@ class GraphShard:
             self.row_ptr.append(torch.as_tensor(rp[self.lo:self.hi + 1] - a).to(dev))
             self.col_idx.append(torch.as_tensor(np.ascontiguousarray(arrays["col_idx"][s_][a:b], dtype=np.int32)).to(dev))
         self.node_type = torch.as_tensor(np.ascontiguousarray(arrays["node_type"][self.lo:self.hi], dtype=np.uint8)).to(dev)
+        own = lambda key, dt: torch.as_tensor(np.ascontiguousarray(arrays[key][self.lo:self.hi], dtype=dt)).to(dev)
+        self.level, self.judge = own("level", np.uint8), own("judge", np.float64)
+        self.judge_term, self.conf = own("judge_term", np.float64), own("conf", np.float64)
         rp = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in self.row_ptr])
         ci = (ctypes.c_void_p * 6)(*[t.data_ptr() if t.numel() else None for t in self.col_idx])
         self._h = ctypes.c_void_p()
@@ -403,6 +406,9 @@ class GraphShard:
             check(self.lib.ahr_graph_shard_create(ctypes.byref(self._h), dev.index, self.n_nodes, self.lo, self.hi, rp, ci,
                                                   self.node_type.data_ptr() if self.hi > self.lo else None),
                   "ahr_graph_shard_create")
+            if self.hi > self.lo:
+                check(self.lib.ahr_graph_shard_set_attrs(self._h, self.level.data_ptr(), self.judge.data_ptr(),
+                                                         self.judge_term.data_ptr(), self.conf.data_ptr()), "ahr_graph_shard_set_attrs")
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
@@ -416,7 +422,60 @@ class GraphShard:
             pass
 
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in self.row_ptr + self.col_idx + [self.node_type])
+        ts = self.row_ptr + self.col_idx + [self.node_type, self.level, self.judge, self.judge_term, self.conf]
+        return sum(t.numel() * t.element_size() for t in ts)
+
+    # ---- anchor expansion + rerank over the sharded graph (ahr_anchor_shard_*) ----
+    def anchor_record_ints(self, stage: int, n_seeds: int, cp) -> int:
+        n = int(self.lib.ahr_anchor_shard_record_ints(stage, int(n_seeds), ctypes.byref(cp)))
+        if n < 0:
+            raise ValueError("sharded anchor expansion: bad n_seeds / params")
+        return n
+
+    def anchor_stage1(self, seed_nodes: torch.Tensor, params: "SearchParams") -> torch.Tensor:
+        nq, ns = int(seed_nodes.shape[0]), int(seed_nodes.shape[1])
+        cp = params.to_c()
+        out = torch.empty((nq, self.anchor_record_ints(1, ns, cp)), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_anchor_shard_stage1(self._h, nq, ns, seed_nodes.data_ptr(), ctypes.byref(cp), out.data_ptr(),
+                                                   _stream_ptr(self.device)), "ahr_anchor_shard_stage1")
+        return out
+
+    def anchor_stage2(self, world: int, bounds, seed_nodes: torch.Tensor, params: "SearchParams", gathered1) -> torch.Tensor:
+        nq, ns = int(seed_nodes.shape[0]), int(seed_nodes.shape[1])
+        cp = params.to_c()
+        out = torch.empty((nq, max(1, self.anchor_record_ints(2, ns, cp))), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ahr_anchor_shard_stage2(self._h, nq, ns, int(world), bounds.data_ptr(), seed_nodes.data_ptr(),
+                                                   ctypes.byref(cp), gathered1.data_ptr(), out.data_ptr(),
+                                                   _stream_ptr(self.device)), "ahr_anchor_shard_stage2")
+        return out
+
+    def anchor_merge(self, world: int, bounds, seed_nodes: torch.Tensor, seed_scores: torch.Tensor, params: "SearchParams",
+                     top_k: int, gathered1, gathered2, want_cluster: bool = True) -> Dict[str, torch.Tensor]:
+        nq, ns = int(seed_nodes.shape[0]), int(seed_nodes.shape[1])
+        dev = self.device
+        cp = params.to_c()
+        cap = ns * (1 + max(cp.parent_cap, cp.member_top_m))
+        out = {"nodes": torch.empty((nq, top_k), dtype=torch.int32, device=dev),
+               "semantic": torch.empty((nq, top_k), dtype=torch.float64, device=dev),
+               "score": torch.empty((nq, top_k), dtype=torch.float64, device=dev),
+               "count": torch.empty((nq,), dtype=torch.int32, device=dev)}
+        if want_cluster:
+            out["exp_nodes"] = torch.empty((nq, cap), dtype=torch.int32, device=dev)
+            out["exp_semantic"] = torch.empty((nq, cap), dtype=torch.float64, device=dev)
+            out["exp_kind"] = torch.empty((nq, cap), dtype=torch.uint8, device=dev)
+            out["exp_count"] = torch.empty((nq,), dtype=torch.int32, device=dev)
+            out["seed_semantic"] = torch.empty((nq, ns), dtype=torch.float64, device=dev)
+        ptr = lambda k_: out[k_].data_ptr() if want_cluster else None
+        with torch.cuda.device(dev):
+            check(self.lib.ahr_anchor_shard_merge(self._h, nq, ns, int(world), bounds.data_ptr(), seed_nodes.data_ptr(),
+                                                  seed_scores.data_ptr(), ctypes.byref(cp), int(top_k), gathered1.data_ptr(),
+                                                  gathered2.data_ptr(), out["nodes"].data_ptr(), out["semantic"].data_ptr(),
+                                                  out["score"].data_ptr(), out["count"].data_ptr(), ptr("exp_nodes"),
+                                                  ptr("exp_semantic"), ptr("exp_kind"), ptr("exp_count"), ptr("seed_semantic"),
+                                                  _stream_ptr(dev)), "ahr_anchor_shard_merge")
+        return out
 
     def record_ints(self, stage: int, limit: int, max_ids: int) -> int:
         n = int(self.lib.ahr_expand_shard_record_ints(stage, int(limit), int(max_ids)))

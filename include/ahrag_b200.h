@@ -336,6 +336,33 @@ int ahr_expand_shard_merge(int device, int64_t n_nodes_total, int32_t n_env, int
                            int32_t limit, const int32_t *dev_gathered1, const int32_t *dev_gathered2, int32_t *dev_out_ids,
                            int32_t *dev_out_counts, void *stream);
 
+/*
+ * Anchor expansion + rerank (ahr_anchor_rerank, hierarchical_graph.py:719-789) over the SHARDED graph.  The seeds
+ * (dense node ids, the merged top-k of the sharded index, identical on every rank) are replicated.
+ *   ahr_graph_shard_set_attrs   the owned slices of level / judge / judge_term / conf (see ahr_graph_create), borrowed
+ *   stage1  (owner of a seed)        its type + attributes + the first parent_cap parents / member_top_m members
+ *   -- all-gather --
+ *   stage2  (owner of a neighbour)   type + attributes of every node stage 1 emitted
+ *   -- all-gather --
+ *   merge   (any rank)               the rerank kernel of ahr_anchor_rerank fed with the gathered records: same outputs,
+ *                                    bit-identical to the unsharded call for every world size
+ * Records are int32, n_q x ahr_anchor_shard_record_ints(stage, n_seeds, params) per rank.
+ */
+int ahr_graph_shard_set_attrs(ahr_graph_shard *g, const uint8_t *dev_level_local, const double *dev_judge_local,
+                              const double *dev_judge_term_local, const double *dev_conf_local);
+int64_t ahr_anchor_shard_record_ints(int32_t stage, int32_t n_seeds, const ahr_rerank_params *params);
+int ahr_anchor_shard_stage1(ahr_graph_shard *g, int32_t nq, int32_t n_seeds, const int32_t *dev_seed_nodes,
+                            const ahr_rerank_params *params, int32_t *dev_out_records, void *stream);
+int ahr_anchor_shard_stage2(ahr_graph_shard *g, int32_t nq, int32_t n_seeds, int32_t world, const int64_t *dev_bounds,
+                            const int32_t *dev_seed_nodes, const ahr_rerank_params *params, const int32_t *dev_gathered1,
+                            int32_t *dev_out_records, void *stream);
+int ahr_anchor_shard_merge(ahr_graph_shard *g, int32_t nq, int32_t n_seeds, int32_t world, const int64_t *dev_bounds,
+                           const int32_t *dev_seed_nodes, const float *dev_seed_scores, const ahr_rerank_params *params,
+                           int32_t top_k, const int32_t *dev_gathered1, const int32_t *dev_gathered2, int32_t *dev_out_nodes,
+                           double *dev_out_semantic, double *dev_out_score, int32_t *dev_out_count, int32_t *dev_exp_nodes,
+                           double *dev_exp_semantic, uint8_t *dev_exp_kind, int32_t *dev_exp_count, double *dev_seed_semantic,
+                           void *stream);
+
 /* ---- diagnostics used by the parity tests (not part of the reference seam) ---------------------- */
 /* full [nq, n_rows] score matrix of the tensor-core path (small inputs only) */
 int ahr_debug_tc_scores(ahr_index *idx, const void *dev_q, int32_t nq, float *dev_out, void *stream);

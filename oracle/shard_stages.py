@@ -120,3 +120,99 @@ def merge(n_nodes: int, bounds, ops, in_ids, in_offsets, max_ids: int, limit: in
         out_ids[e, :len(res)] = res
         out_cnt[e] = len(res)
     return out_ids, out_cnt
+
+
+# ---------------------------------------------------------------------------------------------
+# anchor expansion + rerank over the sharded graph (csrc/graph_shard.cu: shard_anchor_stage1/2; merge = the rerank of
+# oracle/array_graph.anchor_rerank fed from the records).  Record: [present, type, n_nbr, level, judge, judge_term, conf
+# (3 float64 as 6 int32)] + nbr[fan] (+ pad to an even count); stage 2: the 10-int head only.
+# ---------------------------------------------------------------------------------------------
+HEAD = 10
+
+
+def anchor_geom(n_seeds: int, parent_cap: int, member_top_m: int) -> Tuple[int, int, int]:
+    fan = max(parent_cap, member_top_m)
+    return fan, HEAD + fan + (fan & 1), HEAD
+
+
+def _write_head(rec: np.ndarray, g: Dict, v: int, n_nbr: int) -> None:
+    rec[0], rec[1], rec[2], rec[3] = PRESENT, int(g["node_type"][v]), n_nbr, int(g["level"][v])
+    rec[4:10] = np.array([g["judge"][v], g["judge_term"][v], g["conf"][v]], dtype=np.float64).view(np.int32)
+
+
+def anchor_stage1(g: Dict, lo: int, hi: int, seeds: np.ndarray, parent_cap: int, member_top_m: int) -> np.ndarray:
+    nq, ns = seeds.shape
+    fan, r1, _ = anchor_geom(ns, parent_cap, member_top_m)
+    out = np.zeros((nq, ns * r1), dtype=np.int32)
+    for q in range(nq):
+        for r in range(ns):
+            v = int(seeds[q, r])
+            rec = out[q, r * r1:(r + 1) * r1]
+            if not (lo <= v < hi):
+                rec[1] = 3
+                continue
+            t = int(g["node_type"][v])
+            nb = _nbrs(g, BEL_OUT, v)[:parent_cap] if t == 0 else (_nbrs(g, BEL_IN, v)[:member_top_m] if t == 1 else [])
+            rec[HEAD:HEAD + len(nb)] = nb
+            _write_head(rec, g, v, len(nb))
+    return out
+
+
+def anchor_stage2(g: Dict, lo: int, hi: int, bounds, seeds: np.ndarray, parent_cap: int, member_top_m: int, g1: np.ndarray) -> np.ndarray:
+    nq, ns = seeds.shape
+    fan, r1, r2 = anchor_geom(ns, parent_cap, member_top_m)
+    n = len(g["node_type"])
+    out = np.zeros((nq, max(1, ns * fan * r2)), dtype=np.int32)
+    for q in range(nq):
+        for r in range(ns):
+            v = int(seeds[q, r])
+            if v < 0 or v >= n:
+                continue
+            rec1 = g1[_owner(bounds, v), q, r * r1:(r + 1) * r1]
+            for j in range(int(rec1[2])):
+                u = int(rec1[HEAD + j])
+                rec = out[q, (r * fan + j) * r2:(r * fan + j + 1) * r2]
+                if lo <= u < hi:
+                    _write_head(rec, g, u, 0)
+                else:
+                    rec[1] = 3
+    return out
+
+
+def anchor_merge(n_nodes: int, bounds, seeds: np.ndarray, scores: np.ndarray, top_k: int, parent_cap: int, member_top_m: int,
+                 g1: np.ndarray, g2: np.ndarray, params=None):
+    """Per query the reranked [(node, round(sem, 4), round(score, 4))] list, exactly as array_graph.anchor_rerank builds it."""
+    from . import array_graph
+    P = params or array_graph.DEFAULTS
+    nq, ns = seeds.shape
+    fan, r1, r2 = anchor_geom(ns, parent_cap, member_top_m)
+    res = []
+    for q in range(nq):
+        E: Dict[int, float] = {}
+        attr: Dict[int, np.ndarray] = {}
+        for r in range(ns):
+            v, s = int(seeds[q, r]), scores[q, r]
+            if v < 0 or v >= n_nodes:
+                continue
+            sem = 1.0 - float(np.float32(1.0) - np.float32(s))
+            rec1 = g1[_owner(bounds, v), q, r * r1:(r + 1) * r1]
+            E[v] = sem
+            attr.setdefault(v, rec1[:HEAD])
+            t = int(rec1[1])
+            for j in range(int(rec1[2])):
+                u = int(rec1[HEAD + j])
+                if u not in E:
+                    E[u] = sem * (0.9 if t == 0 else 0.85)
+                    attr[u] = g2[_owner(bounds, u), q, (r * fan + j) * r2:(r * fan + j + 1) * r2]
+        out = []
+        for node, sem in E.items():
+            h = attr[node]
+            judge, jt, conf = h[4:10].view(np.float64)
+            t = int(h[1])
+            jterm = float(jt) if judge == judge else 0.0
+            ct = float(conf) / 10.0 if conf == conf else 0.0
+            score = P["alpha"] * sem + P["beta"] * jterm + P["gamma"] * ct + P["delta"] * P["boost"][t]
+            out.append((node, round(sem, 4), round(float(score), 4)))
+        out.sort(key=lambda x: x[2], reverse=True)
+        res.append(out[:top_k])
+    return res

@@ -64,6 +64,21 @@ def _worker(rank, world, port, q):
             wi, wc = whole.expand(t(ops), t(ids), t(offs), limit)
             if not (torch.equal(oi, wi) and torch.equal(oc, wc)):
                 problems.append(f"sharded graph expand differs at limit {limit}")
+        # hop 1 (anchor expansion + rerank) over the same sharded graph
+        ns, top_k = 16, 20
+        seeds = np.stack([rng.choice(4400, ns, replace=False) for _ in range(256)]).astype(np.int32)
+        scores = np.sort(rng.uniform(0.1, 0.9, (256, ns)).astype(np.float32), axis=1)[:, ::-1].copy()
+        prm = engine.SearchParams(member_top_m=5)
+        got = sg.anchor_rerank(t(seeds), t(scores), prm, top_k)
+        want = whole.anchor_rerank(t(seeds), t(scores), prm, top_k)
+        cnt = want["count"].cpu().numpy()
+        if not torch.equal(got["count"], want["count"]):
+            problems.append("sharded anchor rerank: counts differ")
+        else:
+            for key in ("nodes", "semantic", "score"):
+                g_, w_ = got[key].cpu().numpy(), want[key].cpu().numpy()
+                if any(not np.array_equal(g_[q_, :cnt[q_]].view(np.uint8), w_[q_, :cnt[q_]].view(np.uint8)) for q_ in range(256)):
+                    problems.append(f"sharded anchor rerank: {key} differs")
         if sg.shard.nbytes() > 0.8 * whole.nbytes() and world > 1:
             problems.append("graph shard is not a fraction of the graph")
         q.put((rank, problems))

@@ -61,3 +61,61 @@ def test_sharded_expand_rejects_large_limits():
     sh = engine.GraphShard(a, 0, a["n_nodes"], torch.device("cuda", 0))
     with pytest.raises(ValueError):
         sh.record_ints(1, 33, 4)
+
+
+@pytest.mark.parametrize("world", [1, 2, 5])
+@pytest.mark.parametrize("caps", [(2, 5), (0, 3), (4, 12)])
+def test_sharded_anchor_rerank_equals_unsharded(world, caps):
+    """Hop 1 (hierarchical_graph.py:719-789) over the sharded graph: stage records equal the numpy twin, the rerank fed
+    from them equals the unsharded kernel output for output (every tensor, bit for bit) and the array oracle."""
+    from ah_rag_b200 import engine
+    parent_cap, m = caps
+    rng = np.random.default_rng(77 * world + m)
+    a = random_csr(rng, n_ent=3000, n_sum=300, n_hyp=400, hub_deg=600)
+    n = a["n_nodes"]
+    a["judge"][3000:3300] = np.round(rng.uniform(0, 10, 300), 1)
+    a["conf"][3000:3300] = np.round(rng.uniform(0, 10, 300), 2)
+    a["judge_term"][3000:3300] = [1.0 / (1.0 + np.exp(-(x / 10.0))) for x in a["judge"][3000:3300]]
+    bounds = [n * r // world for r in range(world)] + [n]
+    nq, ns, top_k = 96, 20, 30
+    seeds = np.stack([rng.choice(3300, ns, replace=False) for _ in range(nq)]).astype(np.int32)
+    seeds[3, 4] = -1
+    seeds[5, 0] = seeds[5, 7]
+    scores = np.sort(rng.uniform(0.1, 0.9, (nq, ns)).astype(np.float32), axis=1)[:, ::-1].copy()
+    dev = torch.device("cuda", 0)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    d_seeds, d_scores, d_bounds = t(seeds), t(scores), t(np.array(bounds, np.int64))
+    prm = engine.SearchParams(member_top_m=m, parent_cap=parent_cap)
+    shards = [engine.GraphShard(a, bounds[r], bounds[r + 1], dev) for r in range(world)]
+    g1 = torch.stack([s.anchor_stage1(d_seeds, prm) for s in shards])
+    g2 = torch.stack([s.anchor_stage2(world, d_bounds, d_seeds, prm, g1) for s in shards])
+    got = shards[-1].anchor_merge(world, d_bounds, d_seeds, d_scores, prm, top_k, g1, g2)
+    want = engine.GraphCSR(a).anchor_rerank(d_seeds, d_scores, prm, top_k)
+    cnt, ecnt = want["count"].cpu().numpy(), want["exp_count"].cpu().numpy()
+    assert torch.equal(got["count"], want["count"]) and torch.equal(got["exp_count"], want["exp_count"])
+    assert torch.equal(got["seed_semantic"].view(torch.int64), want["seed_semantic"].view(torch.int64))
+    for key, c in (("nodes", cnt), ("semantic", cnt), ("score", cnt), ("exp_nodes", ecnt), ("exp_semantic", ecnt), ("exp_kind", ecnt)):
+        g, w = got[key].cpu().numpy(), want[key].cpu().numpy()
+        for q in range(nq):
+            assert np.array_equal(g[q, :c[q]].view(np.uint8), w[q, :c[q]].view(np.uint8)), (key, q)
+    # the reference semantics through the array oracle
+    gn, gs, gc = got["nodes"].cpu().numpy(), got["semantic"].cpu().numpy(), got["score"].cpu().numpy()
+    for q in range(0, nq if parent_cap == 2 else 0, 5):  # the reference's parent cap is the literal 2 (:742)
+        ref = array_graph.anchor_rerank(a, seeds[q], scores[q], top_k, m)
+        assert [(int(x), float(y), float(z)) for x, y, z in zip(gn[q, :cnt[q]], gs[q, :cnt[q]], gc[q, :cnt[q]])] == ref, q
+    # records against the numpy twin
+    fan, r1, r2 = shard_stages.anchor_geom(ns, parent_cap, m)
+    n1 = np.stack([shard_stages.anchor_stage1(a, bounds[r], bounds[r + 1], seeds, parent_cap, m) for r in range(world)])
+    h1 = g1.cpu().numpy().reshape(world, nq, ns, r1)
+    w1 = n1.reshape(world, nq, ns, r1)
+    assert np.array_equal(h1[..., :4], w1[..., :4])
+    for r, q, i in zip(*np.nonzero(w1[..., 0])):
+        assert np.array_equal(h1[r, q, i, 4:10], w1[r, q, i, 4:10])
+        assert np.array_equal(h1[r, q, i, 10:10 + w1[r, q, i, 2]], w1[r, q, i, 10:10 + w1[r, q, i, 2]])
+    if fan:
+        n2 = np.stack([shard_stages.anchor_stage2(a, bounds[r], bounds[r + 1], bounds, seeds, parent_cap, m, n1) for r in range(world)])
+        h2 = g2.cpu().numpy().reshape(world, nq, ns * fan, r2)
+        w2 = n2.reshape(world, nq, ns * fan, r2)
+        assert np.array_equal(h2[..., 0], w2[..., 0])  # presence; absent records carry no meaning beyond it
+        for r, q, i in zip(*np.nonzero(w2[..., 0])):
+            assert np.array_equal(h2[r, q, i], w2[r, q, i])

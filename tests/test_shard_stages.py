@@ -85,7 +85,16 @@ def _worker(rank, world, port, q):
             oi, oc = shard_stages.merge(n, [int(x) for x in bounds], npy(ops), npy(ids), npy(offs), max_ids, limit, npy(g1), npy(g2))
             return t(oi), t(oc)
 
-        sg = ShardedGraph(stage1, stage2, merge, torch.tensor(b, dtype=torch.int64))
+        def a_stage1(seeds, prm):
+            return t(shard_stages.anchor_stage1(a, lo, hi, npy(seeds), 2, prm))
+
+        def a_stage2(world_, bounds, seeds, prm, g1):
+            return t(shard_stages.anchor_stage2(a, lo, hi, [int(x) for x in bounds], npy(seeds), 2, prm, npy(g1)))
+
+        def a_merge(world_, bounds, seeds, scores, prm, top_k, g1, g2, want_cluster=True):
+            return shard_stages.anchor_merge(n, [int(x) for x in bounds], npy(seeds), npy(scores), top_k, 2, prm, npy(g1), npy(g2))
+
+        sg = ShardedGraph(stage1, stage2, merge, torch.tensor(b, dtype=torch.int64), None, a_stage1, a_stage2, a_merge)
         assert sg.world == world and sg.rank == rank
         ops, ids, offs = _batch(np.random.default_rng(11), a, 120, 3)
         ok = True
@@ -94,6 +103,12 @@ def _worker(rank, world, port, q):
             oi, oc = oi.numpy(), oc.numpy()
             for e in range(len(ops)):
                 ok &= list(oi[e, :oc[e]]) == array_graph.expand(a, int(ops[e]), ids[offs[e]:offs[e + 1]], limit)
+        # hop 1 over the sharded graph (the injected `params` is just member_top_m here)
+        seeds = np.stack([rng.choice(560, 8, replace=False) for _ in range(30)]).astype(np.int32)
+        scores = np.sort(rng.uniform(0.1, 0.9, (30, 8)).astype(np.float32), axis=1)[:, ::-1].copy()
+        got = sg.anchor_rerank(t(seeds), t(scores), 5, 12)
+        for e in range(30):
+            ok &= got[e] == array_graph.anchor_rerank(a, seeds[e], scores[e], 12, 5)
         q.put((rank, bool(ok)))
     except Exception as e:  # report instead of leaving the parent waiting on the queue
         q.put((rank, repr(e)))
@@ -115,3 +130,26 @@ def test_sharded_graph_world2_gloo():
     for p in procs:
         p.join(timeout=30)
     assert res == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_staged_anchor_rerank_equals_whole_graph(world):
+    """Hop 1 over the sharded graph (numpy twin of shard_anchor_stage1/2 + the rerank): equal to the reference's anchor
+    expansion + rerank on the whole graph (oracle/array_graph.anchor_rerank, hierarchical_graph.py:719-789)."""
+    rng = np.random.default_rng(40 + world)
+    a = random_csr(rng, n_ent=600, n_sum=80, n_hyp=100, hub_deg=300)
+    n = a["n_nodes"]
+    a["judge"][600:680] = np.round(rng.uniform(0, 10, 80), 1)
+    a["conf"][600:680] = np.round(rng.uniform(0, 10, 80), 2)
+    a["judge_term"][600:680] = [1.0 / (1.0 + np.exp(-(x / 10.0))) for x in a["judge"][600:680]]
+    bounds = [n * r // world for r in range(world)] + [n]
+    nq, ns, top_k, m = 40, 12, 20, 5
+    seeds = np.stack([rng.choice(680, ns, replace=False) for _ in range(nq)]).astype(np.int32)
+    seeds[3, 4] = -1
+    seeds[5, 0] = seeds[5, 7]  # the same node twice: the later seed owns the value, the first the position
+    scores = np.sort(rng.uniform(0.1, 0.9, (nq, ns)).astype(np.float32), axis=1)[:, ::-1].copy()
+    g1 = np.stack([shard_stages.anchor_stage1(a, bounds[r], bounds[r + 1], seeds, 2, m) for r in range(world)])
+    g2 = np.stack([shard_stages.anchor_stage2(a, bounds[r], bounds[r + 1], bounds, seeds, 2, m, g1) for r in range(world)])
+    got = shard_stages.anchor_merge(n, bounds, seeds, scores, top_k, 2, m, g1, g2)
+    for q in range(nq):
+        assert got[q] == array_graph.anchor_rerank(a, seeds[q], scores[q], top_k, m), (world, q)
