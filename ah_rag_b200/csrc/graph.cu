@@ -464,235 +464,169 @@ expand_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// frontier expansion, large limits: one CTA per environment, EDGE-parallel.
+// frontier expansion, large limits (65-2048): one WARP per environment, hash-set dedup WITHOUT atomics.
 //
-// The warp walker above inserts neighbours in order, 32 at a time, with two votes, a match and a scan of the list (or a
-// hash probe) per batch: ~200 warp instructions per 32 neighbours, 0.52 ms for the 273 MB bandwidth view on c5 = 0.08 of
-// HBM (profiles/r1_c5_v7.json).  Order only matters for WHICH occurrence of a value survives and WHERE it lands, and both
-// follow from positions, so the insertion itself needs no order:
-//   every neighbour gets its position p in the reference's concatenation (segment base + offset; excluded elements leave
-//   holes, which is harmless -- positions only have to be monotone); thread t owns the positions p = t (mod 64) of a round
-//   and keeps their (value, table slot) in REGISTERS;
-//   insert    all threads at once: one 64-bit compare-and-swap claims the value's slot of a shared-memory hash table with
-//             (value << 32 | p + 1); a later occurrence with a lower position (rare: a duplicate) lowers it with atomicMin;
-//   resolve   element p is the first occurrence of its value iff the table holds p + 1: one ballot per warp gives the bitmap;
-//   compact   output index = number of set bits below p (prefix popcount) + what earlier rounds emitted.
-// The first version kept value / slot per position in shared memory and used two 32-bit atomics per neighbour: the
-// shared-memory pipe, not HBM, bound it (l1tex 83 %, 40.8 M bank-conflict cycles, profiles/r2_k2_ncu.md).
-// Long inputs are processed in rounds of W positions against the same table (values emitted by earlier rounds stay in it,
-// position field 0); a round that brings the output to `limit` ends the call, so the table never holds more than
-// (limit - 1) + W values.  The stop rule of the reference ("un-deduplicated length >= limit after finishing an input
-// node", environment.py:404-406) is evaluated per input node on the exact count of non-excluded neighbours.
+// History (profiles/r2_k2_ncu.md): the r1 warp walker scanned / probed per batch with two votes and a match (0.52 ms for
+// the 273 MB bandwidth view on c5); the first r2 version was edge-parallel over a 64-thread CTA with one 64-bit
+// compare-and-swap per neighbour: 0.38 ms, and the counters showed why it could not go further -- shared-memory atomics
+// retire ~1 lane every 2 cycles per SM (B300_MICROARCH.md "ATOMS spread-addr"), 6.8 M ATOMS warp instructions were the
+// floor, the probe loop around them 46 % of all instructions.  Plain shared loads / stores are ~10x cheaper on that pipe,
+// and one warp owning the table needs no atomicity, only agreement:
+//   per batch of 32 consecutive positions of the reference's concatenation (coalesced col_idx loads, U batches in flight)
+//   probe    every lane walks its value's probe sequence with plain loads until it meets the value (seen in an earlier
+//            batch: duplicate) or an empty slot;
+//   claim    lanes at an empty slot store their value, __syncwarp, read back: the lane whose value stands has inserted
+//            it, the others (a different value won the slot) probe on.  Lanes carrying the SAME value see the same table
+//            and therefore travel together: they all "win"; a byte written to owner[slot] by the winners tells them
+//            apart, and only then (never on a DiGraph's duplicate-free adjacency rows, but the ABI accepts any CSR) a
+//            __match_any makes the lowest lane the first occurrence;
+//   emit     ballot of the fresh lanes -> output index = emitted so far + prefix popcount; ids go straight to global.
+// Batches of one warp are sequential, so "first occurrence" across batches needs no positions in the table: 4 bytes of
+// value + 1 byte of owner per slot (5 KB per environment at limit 512: ~44 environments in flight per SM).
+// The stop rule of the reference ("un-deduplicated length >= limit after finishing an input node", environment.py:404-406)
+// and the cut at `limit` unique values are those of expand_walk (graph_shared.cuh).
 // ---------------------------------------------------------------------------------------------
-constexpr int EW_THREADS = 64;  // small CTAs: the walk is a chain of dependent loads, what counts is environments in flight per SM
+constexpr int EW_UNROLL = 4;  // batches of 32 neighbours loaded ahead of the inserts
 
 __host__ __device__ inline int ew_table_slots(int values) {  // open addressing at a load factor <= 0.75
   int t = 64;
   while (3 * t < 4 * values) t <<= 1;
   return t;
 }
-// U = positions per thread and round (W = 64 * U): about half the limit, so that an SM holds ~20 environments at limit 512
-__host__ __device__ inline int ew_units(int limit) { return limit <= 512 ? 4 : (limit <= 1024 ? 8 : 16); }
-__host__ __device__ inline size_t ew_smem_bytes(int limit) {
-  const int W = 64 * ew_units(limit);
-  return (size_t)ew_table_slots(limit + W) * 8 + (size_t)(W / 32) * 8;
+// environments (warps) per CTA: 20 KB of tables per CTA at limit 512, 40 KB at limits 1024 / 2048 (no opt-in needed)
+__host__ __device__ inline int ew_warps(int limit) { return limit <= 1024 ? 4 : 2; }
+__host__ __device__ inline size_t ew_smem_bytes(int limit) { return (size_t)ew_warps(limit) * ew_table_slots(limit + 32) * 5; }
+
+struct WideState {
+  int32_t *table;  // [T] value, -1 = empty
+  uint8_t *owner;  // [T] lane that inserted the value (meaningful within the inserting batch only)
+  int32_t *out;    // this environment's row of out_ids (global)
+  uint32_t mask;   // T - 1
+  int tshift;      // hash = top log2(T) bits of the product
+  int count, raw, limit;
+};
+
+// one batch of 32 positions; returns true once `limit` unique values have been emitted
+__device__ __forceinline__ bool wide_push(WideState &st, int32_t val, bool valid, int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const unsigned vmask = __ballot_sync(FULL, valid);
+  if (vmask == 0) return false;
+  st.raw += __popc(vmask);
+  uint32_t slot = ((uint32_t)val * 2654435761u) >> st.tshift;
+  bool active = valid, fresh = false, tied = false;
+  while (__any_sync(FULL, active)) {
+    int32_t e = 0;
+    if (active) {
+      e = st.table[slot];
+      while (e != -1 && e != val) {
+        slot = (slot + 1) & st.mask;
+        e = st.table[slot];
+      }
+      if (e == val) active = false;  // inserted by an earlier batch: duplicate
+    }
+    __syncwarp();  // every probe of this pass has read the table before anyone writes
+    if (active) st.table[slot] = val;
+    __syncwarp();
+    const bool won = active && st.table[slot] == val;
+    if (won) st.owner[slot] = (uint8_t)lane;
+    else if (active) slot = (slot + 1) & st.mask;  // another value took the slot
+    __syncwarp();
+    if (won) {
+      active = false;
+      if (st.owner[slot] == (uint8_t)lane) fresh = true;
+      else tied = true;  // the same value sits in several lanes of this batch
+    }
+  }
+  if (__any_sync(FULL, tied)) {  // first occurrence = lowest lane of the group that inserted the value
+    const bool in = fresh || tied;
+    const unsigned grp = __match_any_sync(FULL, in ? val : (int32_t)(-2 - lane));
+    fresh = in && (__ffs(grp) - 1) == lane;
+  }
+  const unsigned nmask = __ballot_sync(FULL, fresh);
+  const int pos = st.count + __popc(nmask & ((1u << lane) - 1u));
+  AHR_DEV_ASSERT(pos >= 0);
+  if (fresh && pos < st.limit) st.out[pos] = val;
+  st.count = min(st.limit, st.count + __popc(nmask));
+  return st.count >= st.limit;
 }
 
-template <int U>
-__global__ void __launch_bounds__(EW_THREADS)
+// one CSR row appended to the concatenation, optionally preceded by the single value `literal` (the hyperedge itself,
+// environment.py:459) and without the participants equal to `exclude`
+__device__ __forceinline__ bool wide_segment(WideState &st, const GraphView &g, int slot_csr, int32_t v, int32_t exclude,
+                                             int32_t literal, int lane) {
+  const int64_t p0 = g.row_ptr[slot_csr][v], p1 = g.row_ptr[slot_csr][v + 1];
+  const int32_t *__restrict__ col = g.col_idx[slot_csr];
+  for (int64_t b = p0 - (literal >= 0 ? 1 : 0); b < p1; b += 32 * EW_UNROLL) {
+    int32_t val[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {  // the loads first (coalesced: consecutive lanes, consecutive neighbours) ...
+      const int64_t i = b + u * 32 + lane;
+      val[u] = i < p1 ? (i < p0 ? literal : col[i]) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {  // ... then the inserts, in order
+      const int64_t i = b + u * 32 + lane;
+      if (b + u * 32 >= p1) break;
+      AHR_DEV_ASSERT(i >= p1 || (val[u] >= 0 && val[u] < g.n_nodes));
+      if (wide_push(st, val[u], i < p1 && (i < p0 || val[u] != exclude), lane)) return true;
+    }
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(128)
 expand_wide_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const int32_t *__restrict__ in_ids,
-                   const int32_t *__restrict__ in_offsets, int32_t limit, int32_t *__restrict__ out_ids,
+                   const int32_t *__restrict__ in_offsets, int32_t limit, int32_t T, int32_t *__restrict__ out_ids,
                    int32_t *__restrict__ out_counts) {
-  constexpr int W_MAX = 64 * U;
-  constexpr unsigned long long EMPTY = ~0ull;
   extern __shared__ __align__(16) uint8_t ew_smem[];
-  __shared__ unsigned long long s_est;
-  __shared__ int s_raw, s_total;
-  const int T_max = ew_table_slots(limit + W_MAX);
-  unsigned long long *table = reinterpret_cast<unsigned long long *>(ew_smem);  // [T] value << 32 | position + 1 (0 = emitted earlier)
-  uint32_t *bits = reinterpret_cast<uint32_t *>(table + T_max);                // [W / 32] first-occurrence flags
-  uint32_t *pref = bits + W_MAX / 32;                                          // [W / 32] exclusive prefix popcounts
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int env = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  const int env = blockIdx.x * n_warps + w;
+  if (env >= n_env) return;  // warps are independent: no block-wide barrier below
+  WideState st;
+  st.table = reinterpret_cast<int32_t *>(ew_smem) + (size_t)w * T;
+  st.owner = ew_smem + (size_t)n_warps * T * 4 + (size_t)w * T;
+  st.out = out_ids + (int64_t)env * limit;
+  st.mask = (uint32_t)T - 1u;
+  st.tshift = 32 - (31 - __clz(T));
+  st.count = 0; st.raw = 0; st.limit = limit;
   const int op = ops[env];
   const int32_t *ids = in_ids + in_offsets[env];
   const int n_ids = in_offsets[env + 1] - in_offsets[env];
-  int32_t *out = out_ids + (int64_t)env * limit;
-  auto deg = [&](int slot, int32_t v) { return g.row_ptr[slot][v + 1] - g.row_ptr[slot][v]; };
-
-  // ---- size the table for THIS environment: an upper bound of the positions it can produce ----
-  if (tid == 0) { s_est = 0; s_raw = 0; }
-  __syncthreads();
-  for (int i = tid; i < n_ids; i += EW_THREADS) {
-    const int32_t v = ids[i];
-    if (v < 0 || v >= g.n_nodes) continue;
-    int64_t d;
-    if (op == AHR_OP_PARENTS) d = deg(AHR_CSR_BEL_OUT, v);
-    else if (op == AHR_OP_CHILDREN) d = deg(AHR_CSR_BEL_IN, v);
-    else {
-      d = deg(AHR_CSR_REL_OUT, v) + deg(AHR_CSR_REL_IN, v);
-      if (g.line[v].head.type == AHR_NT_ENTITY) {
-        const int64_t h0 = g.row_ptr[AHR_CSR_PART_OUT][v], h1 = g.row_ptr[AHR_CSR_PART_OUT][v + 1];
-        for (int64_t hi = h0; hi < h1 && d < (1 << 24); ++hi) d += 1 + deg(AHR_CSR_PART_IN, g.col_idx[AHR_CSR_PART_OUT][hi]);
-      }
-    }
-    atomicAdd(&s_est, (unsigned long long)min(d, (int64_t)(1 << 24)));
-  }
-  __syncthreads();
-  const int est = (int)min(max(s_est, 1ull), (unsigned long long)(1 << 24));
-  const int W = min(W_MAX, (est + 63) & ~63);                   // positions per round: whole waves of 64
-  const int T = ew_table_slots(min(min(limit, est) + W, est));  // <= T_max
-  const int tshift = 32 - (31 - __clz(T));                      // hash = top log2(T) bits of the product
-  for (int i = tid; i < T; i += EW_THREADS) table[i] = EMPTY;
-  __syncthreads();
-
-  int fill = 0, out_count = 0;  // uniform across the block
-  int my_valid = 0;             // this thread's non-excluded neighbours of the current input node
-  bool done = false;
-  int32_t r_val[U];             // the positions u * 64 + tid of the current round: value (-1 = hole / nothing) ...
-  int r_slot[U];                // ... and its table slot
-#pragma unroll
-  for (int u = 0; u < U; ++u) r_val[u] = -1;
-
-  // claim the slot of `val` with position p (or lower the position an earlier claim holds); returns the slot
-  auto insert = [&](int32_t val, int p) {
-    const unsigned long long mine = ((unsigned long long)(uint32_t)val << 32) | (unsigned long long)(uint32_t)(p + 1);
-    int slot = (int)(((uint32_t)val * 2654435761u) >> tshift);
-    int probes = 0;
-    for (;;) {
-      AHR_DEV_ASSERT(slot >= 0 && slot < T && T <= T_max && ++probes <= T);
-      const unsigned long long old = atomicCAS(&table[slot], EMPTY, mine);
-      if (old == EMPTY) break;
-      if ((uint32_t)(old >> 32) == (uint32_t)val) {                    // seen before: this round (keep the lower position)
-        if ((uint32_t)old > (uint32_t)(p + 1)) atomicMin(&table[slot], mine);  // or an earlier one (position field 0 stays)
-        break;
-      }
-      slot = (slot + 1) & (T - 1);
-    }
-    (void)probes;
-    return slot;
-  };
-  // resolve + compact the positions [0, fill) of this round
-  auto flush = [&]() {
-    __syncthreads();  // every insert of the round has landed
-    uint32_t mybits[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = u * 64 + tid;
-      const bool fresh = u * 64 < W && r_val[u] >= 0 && (uint32_t)table[r_slot[u]] == (uint32_t)(p + 1);
-      mybits[u] = __ballot_sync(0xffffffffu, fresh);
-      if (lane == 0 && u * 64 < W) bits[u * 2 + warp] = mybits[u];
-    }
-    __syncthreads();
-    if (tid < 32) {  // exclusive prefix popcount over the W / 32 (<= 32) words
-      const int nw = W / 32;
-      const int c0 = lane < nw ? __popc(bits[lane]) : 0;
-      int x0 = c0;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int y0 = __shfl_up_sync(0xffffffffu, x0, d);
-        if (lane >= d) x0 += y0;
-      }
-      if (lane < nw) pref[lane] = x0 - c0;
-      if (lane == 31) s_total = x0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (u * 64 < W && ((mybits[u] >> lane) & 1u)) {
-        const int rank = out_count + pref[u * 2 + warp] + __popc(mybits[u] & ((1u << lane) - 1u));
-        AHR_DEV_ASSERT(rank >= 0);
-        if (rank < limit) out[rank] = r_val[u];
-        table[r_slot[u]] = (unsigned long long)(uint32_t)r_val[u] << 32;  // emitted: position field 0 (or beyond the limit: the call ends)
-      }
-      r_val[u] = -1;
-    }
-    out_count = min(limit, out_count + s_total);
-    fill = 0;
-    if (out_count >= limit) done = true;
-    __syncthreads();  // the next round's inserts must see the emitted marks; s_total / bits are rewritten
-  };
-  // one CSR segment (or, with literal >= 0, the single value `literal`) appended to the concatenation
-  auto segment = [&](int slot_csr, int32_t v, int32_t exclude, int32_t literal) {
-    const int64_t p0 = literal >= 0 ? 0 : g.row_ptr[slot_csr][v];
-    const int64_t len = literal >= 0 ? 1 : g.row_ptr[slot_csr][v + 1] - p0;
-    int64_t off = 0;
-    while (off < len && !done) {
-      const int n = (int)min(len - off, (int64_t)(W - fill));
-      const int32_t *src = literal >= 0 ? nullptr : g.col_idx[slot_csr] + p0 + off - fill;  // src[p] for position p
-      int32_t val[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {  // the loads first (coalesced: consecutive threads, consecutive positions) ...
-        const int p = u * 64 + tid;
-        val[u] = (p >= fill && p < fill + n) ? (literal >= 0 ? literal : src[p]) : -1;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {  // ... then the inserts
-        const int p = u * 64 + tid;
-        if (p >= fill && p < fill + n && val[u] != exclude) {
-          AHR_DEV_ASSERT(val[u] >= 0 && val[u] < g.n_nodes);
-          ++my_valid;
-          r_val[u] = val[u];
-          r_slot[u] = insert(val[u], p);
-        }
-      }
-      fill += n;
-      off += n;
-      if (fill == W) flush();
-    }
-  };
-  // pull a neighbour list into L2 while the lists before it are being inserted (one line per thread and step)
+  for (int i = lane * 4; i < T; i += 128) *reinterpret_cast<int4 *>(st.table + i) = make_int4(-1, -1, -1, -1);
+  __syncwarp();
+  // pull a neighbour list into L2 while the list before it is being inserted (one line per lane and step)
   auto prefetch = [&](int slot_csr, int32_t v) {
     const int64_t p0 = g.row_ptr[slot_csr][v], p1 = g.row_ptr[slot_csr][v + 1];
     const char *b = reinterpret_cast<const char *>(g.col_idx[slot_csr] + p0);
-    const int64_t bytes = min((p1 - p0) * 4, (int64_t)(W_MAX + limit) * 4);
-    for (int64_t o = (int64_t)tid * 128; o < bytes; o += (int64_t)EW_THREADS * 128)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+    const int64_t bytes = min((p1 - p0) * 4, (int64_t)(limit + 32) * 4);
+    for (int64_t o = (int64_t)lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
   };
-
-  for (int idx = 0; idx < n_ids && !done; ++idx) {
+  bool full = false;
+  for (int idx = 0; idx < n_ids && !full; ++idx) {
     const int32_t v = ids[idx];
     if (v < 0 || v >= g.n_nodes) continue;  // `if nid not in G: continue`
-    my_valid = 0;
     if (op == AHR_OP_PARENTS) {
-      segment(AHR_CSR_BEL_OUT, v, -1, -1);
+      full = wide_segment(st, g, AHR_CSR_BEL_OUT, v, -1, -1, lane);
     } else if (op == AHR_OP_CHILDREN) {
-      segment(AHR_CSR_BEL_IN, v, -1, -1);
+      full = wide_segment(st, g, AHR_CSR_BEL_IN, v, -1, -1, lane);
     } else {
       prefetch(AHR_CSR_REL_IN, v);
-      segment(AHR_CSR_REL_OUT, v, -1, -1);
-      segment(AHR_CSR_REL_IN, v, -1, -1);
-      if (g.line[v].head.type == AHR_NT_ENTITY) {
+      full = wide_segment(st, g, AHR_CSR_REL_OUT, v, -1, -1, lane);
+      if (!full) full = wide_segment(st, g, AHR_CSR_REL_IN, v, -1, -1, lane);
+      if (!full && g.line[v].head.type == AHR_NT_ENTITY) {
         // second hop: every hyperedge h of v, then the other participants of h  (environment.py:456-467)
         const int64_t h0 = g.row_ptr[AHR_CSR_PART_OUT][v], h1 = g.row_ptr[AHR_CSR_PART_OUT][v + 1];
-        for (int64_t hi = h0; hi < h1 && !done; ++hi) {
+        for (int64_t hi = h0; hi < h1 && !full; ++hi) {
           const int32_t h = g.col_idx[AHR_CSR_PART_OUT][hi];
-          segment(0, 0, -1, h);
-          segment(AHR_CSR_PART_IN, h, v, -1);
+          AHR_DEV_ASSERT(h >= 0 && h < g.n_nodes);
+          full = wide_segment(st, g, AHR_CSR_PART_IN, h, v, h, lane);
         }
       }
     }
-    if (done) break;
-    // stop rule on the UN-deduplicated length, checked after finishing v
-    if (my_valid) atomicAdd(&s_raw, my_valid);
-    __syncthreads();
-    const int raw = s_raw;
-    __syncthreads();
-    if (raw >= limit) break;
+    if (st.raw >= limit) break;  // stop rule on the UN-deduplicated length, checked after finishing v
   }
-  if (!done && fill > 0) flush();
-  for (int j = out_count + tid; j < limit; j += EW_THREADS) out[j] = -1;
-  if (tid == 0) out_counts[env] = out_count;
-}
-
-template <int U>
-static int launch_expand_wide(const GraphView &g, int32_t n_env, const int32_t *ops, const int32_t *in_ids,
-                              const int32_t *in_offsets, int32_t limit, int32_t *out_ids, int32_t *out_counts,
-                              cudaStream_t stream) {
-  const size_t smem = ew_smem_bytes(limit);  // <= 33 KB: no opt-in needed
-  expand_wide_kernel<U><<<n_env, EW_THREADS, smem, stream>>>(g, n_env, ops, in_ids, in_offsets, limit, out_ids, out_counts);
-  AHR_KERNEL_CHECK();
-  return AHR_OK;
+  for (int j = st.count + lane; j < limit; j += 32) st.out[j] = -1;
+  if (lane == 0) out_counts[env] = st.count;
 }
 
 int graph_expand(const GraphView &g, int32_t n_env, const int32_t *ops, const int32_t *in_ids,
@@ -706,10 +640,11 @@ int graph_expand(const GraphView &g, int32_t n_env, const int32_t *ops, const in
     AHR_KERNEL_CHECK();
     return AHR_OK;
   }
-  const int U = ew_units(limit);
-  if (U == 4) return launch_expand_wide<4>(g, n_env, ops, in_ids, in_offsets, limit, out_ids, out_counts, stream);
-  if (U == 8) return launch_expand_wide<8>(g, n_env, ops, in_ids, in_offsets, limit, out_ids, out_counts, stream);
-  return launch_expand_wide<16>(g, n_env, ops, in_ids, in_offsets, limit, out_ids, out_counts, stream);
+  const int warps = ew_warps(limit);
+  expand_wide_kernel<<<(n_env + warps - 1) / warps, warps * 32, ew_smem_bytes(limit), stream>>>(
+      g, n_env, ops, in_ids, in_offsets, limit, ew_table_slots(limit + 32), out_ids, out_counts);
+  AHR_KERNEL_CHECK();
+  return AHR_OK;
 }
 
 }  // namespace ahr

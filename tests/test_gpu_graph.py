@@ -139,9 +139,9 @@ def test_batched_random_graph_vs_oracle(engine, seed):
 
 @pytest.mark.parametrize("limit", [65, 100, 512, 1024, 2048])
 def test_expand_large_limits_edge_parallel_kernel(limit):
-    """Limits above 64 take the edge-parallel kernel (one CTA per environment, rounds of 1024 / 2048 positions): hub nodes
-    with lists longer than a round, several input ids, duplicates across segments and rounds, the 2-hop related walk with
-    the excluded input node, ids outside the graph, empty inputs -- against the array oracle (environment.py:393-480)."""
+    """Limits above 64 take the hash-set kernel (one warp per environment, batches of 32 positions): hub nodes with long
+    lists, several input ids, duplicates across segments and batches, the 2-hop related walk with the excluded input node,
+    ids outside the graph, empty inputs -- against the array oracle (environment.py:393-480)."""
     from ah_rag_b200 import engine
     from oracle import array_graph
     rng = np.random.default_rng(limit)
@@ -167,3 +167,37 @@ def test_expand_large_limits_edge_parallel_kernel(limit):
         want = array_graph.expand(a, ops[e], ids[offs[e]:offs[e + 1]], limit)
         assert list(oi[e, :oc[e]]) == want, (limit, e, ops[e])
         assert (oi[e, oc[e]:] == -1).all()
+
+
+@pytest.mark.parametrize("limit", [65, 300, 2048])
+def test_expand_large_limits_rows_with_repeated_neighbours(limit):
+    """The C ABI accepts any CSR: rows that repeat a neighbour (impossible in a DiGraph, so never in the reference's data)
+    must still yield the FIRST occurrence in concatenation order -- inside one batch of 32 positions (the lanes of one
+    claim tie on the same slot), across batches, and across segments."""
+    from ah_rag_b200 import engine
+    from oracle import array_graph
+    rng = np.random.default_rng(900 + limit)
+    a = _random_csr(rng, n_ent=3000, n_sum=600, n_hyp=400, hub_deg=2000)
+    n = a["n_nodes"]
+    for s_ in range(6):  # rewrite every CSR with ~40 % of the entries replaced by a copy of a nearby earlier entry
+        rp, ci = a["row_ptr"][s_], a["col_idx"][s_].copy()
+        for v in range(n):
+            p0, p1 = int(rp[v]), int(rp[v + 1])
+            for i in range(p0 + 1, p1):
+                if rng.random() < 0.4:
+                    ci[i] = ci[int(rng.integers(max(p0, i - 40), i))]
+        a["col_idx"][s_] = ci
+    g = engine.GraphCSR(a)
+    ops, ids, offs = [], [], [0]
+    for e in range(240):
+        pick = [int(x) for x in rng.integers(0, n, size=int(rng.integers(1, 5)))]
+        if e % 5 == 0:
+            pick = [3000, 3001] + pick  # the hubs
+        ops.append(e % 3)
+        ids += pick
+        offs.append(len(ids))
+    oi, oc = g.expand(torch.tensor(ops, dtype=torch.int32).cuda(), torch.tensor(ids, dtype=torch.int32).cuda(),
+                      torch.tensor(offs, dtype=torch.int32).cuda(), limit)
+    oi, oc = oi.cpu().numpy(), oc.cpu().numpy()
+    for e in range(240):
+        assert list(oi[e, :oc[e]]) == array_graph.expand(a, ops[e], ids[offs[e]:offs[e + 1]], limit), (limit, e, ops[e])
