@@ -477,9 +477,10 @@ expand_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, const
 //            batch: duplicate) or an empty slot;
 //   claim    lanes at an empty slot store their value, __syncwarp, read back: the lane whose value stands has inserted
 //            it, the others (a different value won the slot) probe on.  Lanes carrying the SAME value see the same table
-//            and therefore travel together: they all "win"; a byte written to owner[slot] by the winners tells them
-//            apart, and only then (never on a DiGraph's duplicate-free adjacency rows, but the ABI accepts any CSR) a
-//            __match_any makes the lowest lane the first occurrence;
+//            and therefore travel together: they all "win"; at the end of the batch a byte written to owner[slot] by
+//            the inserting lanes tells them apart, and only then (never on a DiGraph's duplicate-free adjacency rows,
+//            but the ABI accepts any CSR) a __match_any -- 64 cycles of a shared unit per use, tools/ub/ub_match.cu --
+//            makes the lowest lane the first occurrence;
 //   emit     ballot of the fresh lanes -> output index = emitted so far + prefix popcount; ids go straight to global.
 // Batches of one warp are sequential, so "first occurrence" across batches needs no positions in the table: 4 bytes of
 // value + 1 byte of owner per slot (5 KB per environment at limit 512: ~44 environments in flight per SM).
@@ -498,49 +499,76 @@ __host__ __device__ inline int ew_warps(int limit) { return limit <= 1024 ? 4 : 
 __host__ __device__ inline size_t ew_smem_bytes(int limit) { return (size_t)ew_warps(limit) * ew_table_slots(limit + 32) * 5; }
 
 struct WideState {
-  int32_t *table;  // [T] value, -1 = empty
-  uint8_t *owner;  // [T] lane that inserted the value (meaningful within the inserting batch only)
-  int32_t *out;    // this environment's row of out_ids (global)
-  uint32_t mask;   // T - 1
-  int tshift;      // hash = top log2(T) bits of the product
+  uint32_t tbase;   // shared-memory byte address of table[T] (int32 value, -1 = empty)
+  uint32_t obase;   // shared-memory byte address of owner[T] (u8: lane that inserted the value; meaningful within the batch)
+  uint32_t mask4;   // (T - 1) * 4: byte offsets into the table wrap with one AND
+  int tshift2;      // byte offset of the home slot = (hash >> tshift2) & mask4
+  int32_t *out;     // this environment's row of out_ids (global)
   int count, raw, limit;
 };
 
-// one batch of 32 positions; returns true once `limit` unique values have been emitted
-__device__ __forceinline__ bool wide_push(WideState &st, int32_t val, bool valid, int lane) {
+// 32-bit shared-window addresses + ld/st.shared: through a generic pointer held in a struct every access paid
+// S2R SR_CgaCtaId + LEA + IMAD for the window base (70 instructions per claim pass in the first version's SASS)
+__device__ __forceinline__ int32_t ew_lds(uint32_t a) {
+  int32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ew_sts(uint32_t a, int32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ew_lds8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ew_sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// predicated forms: a load / store inside an `if` costs a BSSY / BRA / BSYNC triple per use in the claim pass
+__device__ __forceinline__ int32_t ew_lds_if(bool p, uint32_t a, int32_t otherwise) {
+  int32_t v = otherwise;
+  asm volatile("{ .reg .pred p; setp.ne.s32 p, %2, 0; @p ld.shared.b32 %0, [%1]; }" : "+r"(v) : "r"(a), "r"((int)p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ew_sts_if(bool p, uint32_t a, int32_t v) {
+  asm volatile("{ .reg .pred p; setp.ne.s32 p, %2, 0; @p st.shared.b32 [%0], %1; }" ::"r"(a), "r"(v), "r"((int)p) : "memory");
+}
+
+// one batch of 32 positions (valid = val >= 0 and not the excluded node); returns true once `limit` unique values are out
+__device__ __forceinline__ bool wide_push(WideState &st, int32_t val, int32_t exclude, int lane) {
   constexpr unsigned FULL = 0xffffffffu;
+  const bool valid = val >= 0 && val != exclude;
   const unsigned vmask = __ballot_sync(FULL, valid);
   if (vmask == 0) return false;
   st.raw += __popc(vmask);
-  uint32_t slot = ((uint32_t)val * 2654435761u) >> st.tshift;
-  bool active = valid, fresh = false, tied = false;
-  while (__any_sync(FULL, active)) {
-    int32_t e = 0;
-    if (active) {
-      e = st.table[slot];
-      while (e != -1 && e != val) {
-        slot = (slot + 1) & st.mask;
-        e = st.table[slot];
-      }
-      if (e == val) active = false;  // inserted by an earlier batch: duplicate
+  // double hashing: linear probing piles every lane that enters a cluster onto the cluster's one free slot; an odd
+  // per-value stride keeps different values on different sequences (measured: 1.37 claim passes, 1.9 extra probes a batch)
+  const uint32_t h = (uint32_t)val * 2654435761u;
+  const uint32_t step4 = ((h >> 5) & ~3u) | 4u;  // odd slot stride, in bytes
+  uint32_t off = (h >> st.tshift2) & st.mask4;
+  bool looking = valid, ins = false;  // looking for its slot | inserted by this lane
+  do {
+    int32_t e = ew_lds_if(looking, st.tbase + off, val);  // (lanes that are not looking fall through the loop)
+    while (e != -1 && e != val) {
+      off = (off + step4) & st.mask4;
+      e = ew_lds(st.tbase + off);
     }
-    __syncwarp();  // every probe of this pass has read the table before anyone writes
-    if (active) st.table[slot] = val;
+    looking = looking && e != val;  // found: inserted by an earlier batch, a duplicate
+    __syncwarp();  // every probe of this pass (and every read-back of the last one) is done before anyone writes
+    ew_sts_if(looking, st.tbase + off, val);
     __syncwarp();
-    const bool won = active && st.table[slot] == val;
-    if (won) st.owner[slot] = (uint8_t)lane;
-    else if (active) slot = (slot + 1) & st.mask;  // another value took the slot
-    __syncwarp();
-    if (won) {
-      active = false;
-      if (st.owner[slot] == (uint8_t)lane) fresh = true;
-      else tied = true;  // the same value sits in several lanes of this batch
-    }
-  }
+    const bool won = ew_lds_if(looking, st.tbase + off, ~val) == val;  // lanes carrying the same value all win together
+    ins = ins || won;
+    if (looking && !won) off = (off + step4) & st.mask4;  // another value took the slot
+    looking = looking && !won;
+  } while (__any_sync(FULL, looking));
+  // the same value in several lanes of this batch: they share the slot, the owner byte tells them apart
+  const uint32_t oa = st.obase + (off >> 2);
+  if (ins) ew_sts8(oa, (uint32_t)lane);
+  __syncwarp();
+  const bool tied = ins && ew_lds8(oa) != (uint32_t)lane;
+  bool fresh = ins;
   if (__any_sync(FULL, tied)) {  // first occurrence = lowest lane of the group that inserted the value
-    const bool in = fresh || tied;
-    const unsigned grp = __match_any_sync(FULL, in ? val : (int32_t)(-2 - lane));
-    fresh = in && (__ffs(grp) - 1) == lane;
+    const unsigned grp = __match_any_sync(FULL, ins ? val : (int32_t)(-2 - lane));
+    fresh = ins && (__ffs(grp) - 1) == lane;
   }
   const unsigned nmask = __ballot_sync(FULL, fresh);
   const int pos = st.count + __popc(nmask & ((1u << lane) - 1u));
@@ -552,23 +580,29 @@ __device__ __forceinline__ bool wide_push(WideState &st, int32_t val, bool valid
 
 // one CSR row appended to the concatenation, optionally preceded by the single value `literal` (the hyperedge itself,
 // environment.py:459) and without the participants equal to `exclude`
-__device__ __forceinline__ bool wide_segment(WideState &st, const GraphView &g, int slot_csr, int32_t v, int32_t exclude,
+__device__ __forceinline__ bool wide_segment(WideState &st, const GraphView &g, const int64_t *__restrict__ row_ptr,
+                                             const int32_t *__restrict__ col_idx, int32_t v, int32_t exclude,
                                              int32_t literal, int lane) {
-  const int64_t p0 = g.row_ptr[slot_csr][v], p1 = g.row_ptr[slot_csr][v + 1];
-  const int32_t *__restrict__ col = g.col_idx[slot_csr];
-  for (int64_t b = p0 - (literal >= 0 ? 1 : 0); b < p1; b += 32 * EW_UNROLL) {
+  const int64_t p0 = row_ptr[v], p1 = row_ptr[v + 1];
+  const int32_t *__restrict__ src = col_idx + p0;
+  bool lit_here = literal >= 0 && lane == 0;  // lane 0 of the first batch carries the literal, not a column entry
+  if (literal >= 0) --src;
+  for (int64_t left = p1 - p0 + (literal >= 0 ? 1 : 0); left > 0; left -= 32 * EW_UNROLL, src += 32 * EW_UNROLL) {
+    const int rem = (int)min(left, (int64_t)(32 * EW_UNROLL));
     int32_t val[EW_UNROLL];
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {  // the loads first (coalesced: consecutive lanes, consecutive neighbours) ...
-      const int64_t i = b + u * 32 + lane;
-      val[u] = i < p1 ? (i < p0 ? literal : col[i]) : -1;
+      const int li = u * 32 + lane;
+      val[u] = (li < rem && !(u == 0 && lit_here)) ? src[li] : -1;
     }
+    const int32_t excl0 = lit_here ? -1 : exclude;  // the literal is not subject to the exclusion
+    if (lit_here) val[0] = literal;
+    lit_here = false;
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {  // ... then the inserts, in order
-      const int64_t i = b + u * 32 + lane;
-      if (b + u * 32 >= p1) break;
-      AHR_DEV_ASSERT(i >= p1 || (val[u] >= 0 && val[u] < g.n_nodes));
-      if (wide_push(st, val[u], i < p1 && (i < p0 || val[u] != exclude), lane)) return true;
+      if (u * 32 >= rem) break;
+      AHR_DEV_ASSERT(val[u] < g.n_nodes && (val[u] >= 0 || u * 32 + lane >= rem));
+      if (wide_push(st, val[u], u == 0 ? excl0 : exclude, lane)) return true;
     }
   }
   return false;
@@ -583,16 +617,18 @@ expand_wide_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, 
   const int env = blockIdx.x * n_warps + w;
   if (env >= n_env) return;  // warps are independent: no block-wide barrier below
   WideState st;
-  st.table = reinterpret_cast<int32_t *>(ew_smem) + (size_t)w * T;
-  st.owner = ew_smem + (size_t)n_warps * T * 4 + (size_t)w * T;
+  int32_t *table = reinterpret_cast<int32_t *>(ew_smem) + (size_t)w * T;
+  st.tbase = (uint32_t)__cvta_generic_to_shared(table);
+  st.obase = (uint32_t)__cvta_generic_to_shared(ew_smem + (size_t)n_warps * T * 4 + (size_t)w * T);
   st.out = out_ids + (int64_t)env * limit;
-  st.mask = (uint32_t)T - 1u;
-  st.tshift = 32 - (31 - __clz(T));
+  asm volatile("" : "+l"(st.out));  // keep the row pointer in registers (it was re-derived from env * limit at every store)
+  st.mask4 = ((uint32_t)T - 1u) << 2;
+  st.tshift2 = 32 - (31 - __clz(T)) - 2;  // T >= 64: at least 6 hash bits, the shift stays positive
   st.count = 0; st.raw = 0; st.limit = limit;
   const int op = ops[env];
   const int32_t *ids = in_ids + in_offsets[env];
   const int n_ids = in_offsets[env + 1] - in_offsets[env];
-  for (int i = lane * 4; i < T; i += 128) *reinterpret_cast<int4 *>(st.table + i) = make_int4(-1, -1, -1, -1);
+  for (int i = lane * 4; i < T; i += 128) *reinterpret_cast<int4 *>(table + i) = make_int4(-1, -1, -1, -1);
   __syncwarp();
   // pull a neighbour list into L2 while the list before it is being inserted (one line per lane and step)
   auto prefetch = [&](int slot_csr, int32_t v) {
@@ -605,23 +641,30 @@ expand_wide_kernel(GraphView g, int32_t n_env, const int32_t *__restrict__ ops, 
   for (int idx = 0; idx < n_ids && !full; ++idx) {
     const int32_t v = ids[idx];
     if (v < 0 || v >= g.n_nodes) continue;  // `if nid not in G: continue`
-    if (op == AHR_OP_PARENTS) {
-      full = wide_segment(st, g, AHR_CSR_BEL_OUT, v, -1, -1, lane);
-    } else if (op == AHR_OP_CHILDREN) {
-      full = wide_segment(st, g, AHR_CSR_BEL_IN, v, -1, -1, lane);
-    } else {
+    // The segments of v, walked by ONE copy of the segment code (five inlined copies x EW_UNROLL pushes were 157 KB of SASS:
+    // instruction-cache misses showed up as no_instruction / branch_resolving stalls):
+    //   parents: belongs_to out | children: belongs_to in | related: related_to out, related_to in, then for an entity every
+    //   hyperedge h of v followed by the other participants of h (environment.py:456-467)
+    int64_t h0 = 0, n_seg = 1;
+    if (op != AHR_OP_PARENTS && op != AHR_OP_CHILDREN) {
       prefetch(AHR_CSR_REL_IN, v);
-      full = wide_segment(st, g, AHR_CSR_REL_OUT, v, -1, -1, lane);
-      if (!full) full = wide_segment(st, g, AHR_CSR_REL_IN, v, -1, -1, lane);
-      if (!full && g.line[v].head.type == AHR_NT_ENTITY) {
-        // second hop: every hyperedge h of v, then the other participants of h  (environment.py:456-467)
-        const int64_t h0 = g.row_ptr[AHR_CSR_PART_OUT][v], h1 = g.row_ptr[AHR_CSR_PART_OUT][v + 1];
-        for (int64_t hi = h0; hi < h1 && !full; ++hi) {
-          const int32_t h = g.col_idx[AHR_CSR_PART_OUT][hi];
-          AHR_DEV_ASSERT(h >= 0 && h < g.n_nodes);
-          full = wide_segment(st, g, AHR_CSR_PART_IN, h, v, h, lane);
-        }
+      n_seg = 2;
+      if (g.line[v].head.type == AHR_NT_ENTITY) {
+        h0 = g.row_ptr[AHR_CSR_PART_OUT][v];
+        n_seg += g.row_ptr[AHR_CSR_PART_OUT][v + 1] - h0;
       }
+    }
+    for (int64_t sg = 0; sg < n_seg && !full; ++sg) {
+      // (pointers picked by selects: indexing the kernel parameter with a runtime slot would copy it to local memory)
+      const int64_t *rp = op == AHR_OP_PARENTS ? g.row_ptr[AHR_CSR_BEL_OUT] : (op == AHR_OP_CHILDREN ? g.row_ptr[AHR_CSR_BEL_IN] : (sg == 0 ? g.row_ptr[AHR_CSR_REL_OUT] : g.row_ptr[AHR_CSR_REL_IN]));
+      const int32_t *ci = op == AHR_OP_PARENTS ? g.col_idx[AHR_CSR_BEL_OUT] : (op == AHR_OP_CHILDREN ? g.col_idx[AHR_CSR_BEL_IN] : (sg == 0 ? g.col_idx[AHR_CSR_REL_OUT] : g.col_idx[AHR_CSR_REL_IN]));
+      int32_t node = v, exclude = -1, literal = -1;
+      if (sg >= 2) {
+        const int32_t h = g.col_idx[AHR_CSR_PART_OUT][h0 + sg - 2];
+        AHR_DEV_ASSERT(h >= 0 && h < g.n_nodes);
+        rp = g.row_ptr[AHR_CSR_PART_IN]; ci = g.col_idx[AHR_CSR_PART_IN]; node = h; exclude = v; literal = h;
+      }
+      full = wide_segment(st, g, rp, ci, node, exclude, literal, lane);
     }
     if (st.raw >= limit) break;  // stop rule on the UN-deduplicated length, checked after finishing v
   }
