@@ -375,10 +375,13 @@ class GraphCSR:
         return out_ids, out_cnt
 
 
+_NP_OF = {torch.int64: np.int64, torch.int32: np.int32, torch.uint8: np.uint8, torch.float64: np.float64}
+
+
 class GraphShard:
     """One rank's node range [lo, hi) of the typed CSR (``ahr_graph_shard_*``, csrc/graph_shard.cu): the adjacency rows of
     the owned nodes (all six slots, neighbours as GLOBAL dense ids) and their node types.  ``arrays`` is the full-graph
-    dict of ``csr.csr_from_networkx``; only the owned slice is uploaded."""
+    dict of ``csr.csr_from_networkx`` (numpy, or torch tensors on the host or the device); only the owned slice is kept."""
 
     def __init__(self, arrays: Dict[str, Any], lo: int, hi: int, device: torch.device | str = "cuda") -> None:
         self.lib = _lib.load()
@@ -390,15 +393,22 @@ class GraphShard:
         dev = self.device
         self.n_nodes, self.lo, self.hi = int(arrays["n_nodes"]), int(lo), int(hi)
         self.row_ptr, self.col_idx = [], []
+
+        def own(x, lo_, hi_, dt):
+            """the slice [lo_, hi_) of a numpy array or of a torch tensor (host or device) as its own device tensor"""
+            if isinstance(x, torch.Tensor):
+                return x[lo_:hi_].to(device=dev, dtype=dt).clone().contiguous()
+            return torch.as_tensor(np.ascontiguousarray(x[lo_:hi_], dtype=_NP_OF[dt])).to(dev)
+
         for s_ in range(_lib.AHR_N_CSR):
-            rp = np.ascontiguousarray(arrays["row_ptr"][s_], dtype=np.int64)
+            rp = arrays["row_ptr"][s_]
             a, b = int(rp[self.lo]), int(rp[self.hi])
-            self.row_ptr.append(torch.as_tensor(rp[self.lo:self.hi + 1] - a).to(dev))
-            self.col_idx.append(torch.as_tensor(np.ascontiguousarray(arrays["col_idx"][s_][a:b], dtype=np.int32)).to(dev))
-        self.node_type = torch.as_tensor(np.ascontiguousarray(arrays["node_type"][self.lo:self.hi], dtype=np.uint8)).to(dev)
-        own = lambda key, dt: torch.as_tensor(np.ascontiguousarray(arrays[key][self.lo:self.hi], dtype=dt)).to(dev)
-        self.level, self.judge = own("level", np.uint8), own("judge", np.float64)
-        self.judge_term, self.conf = own("judge_term", np.float64), own("conf", np.float64)
+            self.row_ptr.append(own(rp, self.lo, self.hi + 1, torch.int64) - a)
+            self.col_idx.append(own(arrays["col_idx"][s_], a, b, torch.int32))
+        self.node_type = own(arrays["node_type"], self.lo, self.hi, torch.uint8)
+        self.level, self.judge = own(arrays["level"], self.lo, self.hi, torch.uint8), own(arrays["judge"], self.lo, self.hi, torch.float64)
+        self.judge_term = own(arrays["judge_term"], self.lo, self.hi, torch.float64)
+        self.conf = own(arrays["conf"], self.lo, self.hi, torch.float64)
         rp = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in self.row_ptr])
         ci = (ctypes.c_void_p * 6)(*[t.data_ptr() if t.numel() else None for t in self.col_idx])
         self._h = ctypes.c_void_p()

@@ -525,9 +525,16 @@ def extra_c4(dist, world, rank, dev, steps=10):
         prof = sh.index.get_profile()
         sh.index.set_profiling(False)
         k1 = prof["k1_ms_total"] / max(1, prof["k1_launches"])
+        k1_all = [k1]
+        if world > 1:  # the step ends when the slowest rank's list arrives: every rank's K1 time goes into the line
+            t_k1 = torch.tensor([k1], dtype=torch.float64, device=dev)
+            t_all = [torch.zeros_like(t_k1) for _ in range(world)]
+            dist.all_gather(t_all, t_k1)
+            k1_all = [float(x.item()) for x in t_all]
         t_mem = 2.0 * n * dim / (hbm * 1e9) * 1e3
         t_mma = 2.0 * max(nq, 128) * n * dim / (tf * 1e12) * 1e3  # the tensor core works on whole 128-row query tiles
         out["batches"].append({"nq": nq, "ms_per_batch": ms, "queries_per_s": nq / ms * 1e3, "k1_ms_rank0": k1,
+                               "k1_ms_per_rank": k1_all, "slowest_rank_k1_share_of_batch": max(k1_all) / ms,
                                "hbm_gbs": 2.0 * n * dim / (k1 * 1e-3) / 1e9, "hbm_frac": t_mem / k1,
                                "t_mem_ms": t_mem, "t_mma_ms": t_mma, "binding": "tensor" if t_mma > t_mem else "hbm",
                                "frac_of_binding_roofline": max(t_mem, t_mma) / k1, "n_slabs": prof["n_slabs"]})
@@ -638,9 +645,47 @@ def extra_c5(dist, world, rank, dev, scale=1.0, cpu_budget_s=6.0):
                                         "sample": f"oracle/ref_search.py (the reference's algorithm over NetworkX, as the reference holds its "
                                                   f"graph) sequential loop, {nxr['envs']} environments on a reduced graph of {nxr['nodes']} nodes / "
                                                   f"{nxr['edges']} edges, {nxr['seconds']:.1f} s (+ {nxr['graph_build_s']:.1f} s to build the DiGraph)"}
+    if world > 1:
+        out["sharded_csr"] = c5_sharded(dist, world, rank, dev, a, g, seeds, scores, ops, prm, top_k, limit)
     del g, a
     torch.cuda.empty_cache()
     return out
+
+
+def c5_sharded(dist, world, rank, dev, a, g, seeds, scores, ops, prm, top_k, limit):
+    """SURVEY 8e option B on c5: the CSR (and the node attributes) sharded by node range over the ranks, the batch of 1024
+    environments replicated; hop 1 = owner-routed records + the rerank kernel (two NCCL all-gathers), hop 2 = staged expansion
+    (two all-gathers).  Every rank ends with the whole batch's answer; checked here against the replicated graph `g`."""
+    from ah_rag_b200.dist import ShardedGraph
+    sg = ShardedGraph.from_arrays(a, dev)
+    n_env = int(seeds.shape[0])
+    want1 = g.anchor_rerank(seeds, scores, prm, top_k)
+    got1 = sg.anchor_rerank(seeds, scores, prm, top_k)
+    cnt = want1["count"]
+    live = torch.arange(top_k, device=dev)[None, :] < cnt[:, None]
+    ok1 = bool(torch.equal(got1["count"], cnt) and torch.equal(got1["nodes"][live], want1["nodes"][live]) and
+               torch.equal(got1["score"][live].view(torch.int64), want1["score"][live].view(torch.int64)) and
+               torch.equal(got1["semantic"][live].view(torch.int64), want1["semantic"][live].view(torch.int64)))
+    take = torch.where(ops == 2, 1, 2)
+    offs = torch.zeros(n_env + 1, dtype=torch.int32, device=dev)
+    offs[1:] = torch.cumsum(take, 0).to(torch.int32)
+    keep = torch.arange(2, device=dev)[None, :] < take[:, None]
+    flat = want1["nodes"][:, :2][keep].to(torch.int32).contiguous()
+    wi, wc = g.expand(ops, flat, offs, limit)
+    oi, oc = sg.expand(ops, flat, offs, limit=limit, max_ids=2)
+    ok2 = bool(torch.equal(oi, wi) and torch.equal(oc, wc))
+    ms1 = _timed_dist(dist, world, dev, lambda: sg.anchor_rerank(seeds, scores, prm, top_k, want_cluster=False), steps=20)
+    ms2 = _timed_dist(dist, world, dev, lambda: sg.expand(ops, flat, offs, limit=limit, max_ids=2), steps=20)
+    cp = prm.to_c()
+    rec = [sg.shard.anchor_record_ints(1, int(seeds.shape[1]), cp), sg.shard.anchor_record_ints(2, int(seeds.shape[1]), cp),
+           sg.shard.record_ints(1, limit, 2), sg.shard.record_ints(2, limit, 2)]
+    res = {"what": f"CSR + node attributes sharded by node range over {world} GPUs ({sg.shard.nbytes()} bytes on rank 0 of "
+                   f"{g.nbytes()} replicated), {n_env} environments replicated, results on every rank",
+           "hop1_anchor_rerank_ms": ms1, "hop2_expand_limit10_ms": ms2, "envs_per_s_two_hops": n_env / (ms1 + ms2) * 1e3,
+           "allgather_bytes_per_rank": {"hop1": [4 * n_env * rec[0], 4 * n_env * rec[1]], "hop2": [4 * n_env * rec[2], 4 * n_env * rec[3]]},
+           "equal_to_replicated": {"hop1": ok1, "hop2": ok2}}
+    del sg
+    return res
 
 
 def c5_inputs(a, n_env, n_seeds, dev, seed=7):
