@@ -543,6 +543,53 @@ def extra_c4(dist, world, rank, dev, steps=10):
     return out
 
 
+def extra_c2(dist, world, rank, dev):
+    """configs[1] substitute (the shipped hotpotqa_distractor graph is empty): a HotpotQA-scale synthetic graph
+    (500k nodes), a 450k x 384 fp32 index (MiniLM-shaped rows, entities + summaries), all 7405 dev questions in one batch,
+    top_k = 5: NaiveRAG's retrieval (fp32-exact top-k) + HierarchicalGraph.search's anchor expansion and rerank.  One GPU
+    per replica ("1 B200" in the config): every rank runs it, rank 0 checks a sample against the oracle on the host."""
+    a = make_c5_graph(dev, scale=0.025, seed=3)  # 400k entities, 45k L1, 5k L2, 50k hyperedges
+    g = DeviceGraph(a, dev)
+    n_index = a["ranges"]["l2"][1]  # entities + all summaries are indexed (hierarchical_graph.py:629-649), rows in node order
+    dim, nq, k = 384, 7405, 5
+    gen = torch.Generator(device=dev).manual_seed(11)
+    X = torch.randn((n_index, dim), generator=gen, device=dev)
+    X /= X.norm(dim=1, keepdim=True)
+    Q = torch.randn((nq, dim), generator=gen, device=dev)
+    Q /= Q.norm(dim=1, keepdim=True)
+    X, Q = X.contiguous(), Q.contiguous()
+    idx = engine.VectorIndex(X)
+    prm = engine.SearchParams(member_top_m=5)
+
+    def step():
+        s, i = idx.topk(Q, k, mode="exact")
+        return s, i, g.anchor_rerank(i.to(torch.int32), s, prm, k, want_cluster=False)
+
+    s, i, out = step()
+    ms = _timed_dist(dist, world, dev, step, steps=5, warmup=2)
+    res = {"workload": f"c2 substitute: synthetic graph {a['n_nodes']} nodes / {a['n_edges']} edges, index {n_index} x {dim} fp32, "
+                       f"{nq} queries in one batch, top_k={k}, fp32-exact top-k + anchor expansion + rerank; one replica per GPU",
+           "n_gpus": world, "ms_per_batch": ms, "queries_per_s_per_gpu": nq / ms * 1e3, "queries_per_s": world * nq / ms * 1e3}
+    if rank == 0:
+        from oracle import array_graph, exact  # the checker, never the measured path
+        sample = [0, 1, nq // 2, nq - 1]
+        rs, ri = exact.exact_topk_rowpar(X.cpu().numpy(), Q[sample].cpu().numpy(), k)
+        ih, sh = i.cpu().numpy(), s.cpu().numpy()
+        ok_ids = bool(np.array_equal(ih[sample], ri)) and bool(np.array_equal(sh[sample].view(np.uint32), rs.view(np.uint32)))
+        host = {"row_ptr": [t.cpu().numpy() for t in a["row_ptr"]], "col_idx": [t.cpu().numpy() for t in a["col_idx"]],
+                "node_type": a["node_type"].cpu().numpy(), "judge": a["judge"].cpu().numpy(),
+                "judge_term": a["judge_term"].cpu().numpy(), "conf": a["conf"].cpu().numpy()}
+        o = {k_: v.cpu().numpy() for k_, v in out.items()}
+        ok_rr = all(array_graph.anchor_rerank(host, ri[j].astype(np.int32), rs[j], k, 5) ==
+                    [(int(o["nodes"][q, t]), float(o["semantic"][q, t]), float(o["score"][q, t])) for t in range(o["count"][q])]
+                    for j, q in enumerate(sample))
+        res["parity_check"] = {"queries": sample, "exact_ids_and_score_bits_equal": ok_ids, "anchor_rerank_bit_exact": bool(ok_rr),
+                               "oracle": "oracle/exact_topk.c full scan + oracle/array_graph.py on the host"}
+    del idx, g, a, X, Q
+    torch.cuda.empty_cache()
+    return res
+
+
 def extra_c5(dist, world, rank, dev, scale=1.0, cpu_budget_s=6.0):
     """c5 = synthetic hierarchical graph 20M nodes / 500M edges, 1024 environments x 50 seeds: hop 1 (anchor expansion +
     rerank), hop 2 (one expand_* per environment), the uncapped-walk bandwidth view, the device gym rollout; graph
