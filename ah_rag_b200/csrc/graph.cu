@@ -546,10 +546,13 @@ __device__ __forceinline__ bool wide_push(WideState &st, int32_t val, int32_t ex
   bool looking = valid, ins = false;  // looking for its slot | inserted by this lane
   do {
     int32_t e = ew_lds_if(looking, st.tbase + off, val);  // (lanes that are not looking fall through the loop)
+    int probes = 0;
     while (e != -1 && e != val) {
+      AHR_DEV_ASSERT(++probes <= (int)(st.mask4 >> 2) && off <= st.mask4 && (off & 3u) == 0);  // the table is never full
       off = (off + step4) & st.mask4;
       e = ew_lds(st.tbase + off);
     }
+    (void)probes;
     looking = looking && e != val;  // found: inserted by an earlier batch, a duplicate
     __syncwarp();  // every probe of this pass (and every read-back of the last one) is done before anyone writes
     ew_sts_if(looking, st.tbase + off, val);
