@@ -383,8 +383,13 @@ def main() -> int:
         del sharded, index, rows
         torch.cuda.empty_cache()
         import bench_workloads as bw
-        extra = {"c2": bw.extra_c2(dist, world, rank, device), "c4": bw.extra_c4(dist, world, rank, device),
-                 "c5": bw.extra_c5(dist, world, rank, device)}
+        extra = {}
+        for name, fn in (("c2", bw.extra_c2), ("c4", bw.extra_c4), ("c5", bw.extra_c5)):
+            try:  # a failing side block must not take the headline line with it; the error is reported in its place
+                extra[name] = fn(dist, world, rank, device)
+            except Exception as e:  # noqa: BLE001
+                extra[name] = {"error": repr(e)}
+                torch.cuda.empty_cache()
 
     ms_step = ms_total / args.steps
     qps = N_QUERIES / (ms_step / 1e3)
