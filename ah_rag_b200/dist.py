@@ -208,3 +208,33 @@ class ShardedGraph:
         g1 = self._gather(self.anchor_stage1(seed_nodes, params))
         g2 = self._gather(self.anchor_stage2(self.world, self.bounds, seed_nodes, params, g1))
         return self.anchor_merge(self.world, self.bounds, seed_nodes, seed_scores, params, top_k, g1, g2, want_cluster)
+
+
+class ShardedGraphCSR:
+    """``engine.GraphCSR``'s call surface over a ``ShardedGraph`` -- what ``HierarchicalGraph`` / ``GraphEnvironment`` hold as
+    their device graph once ``HierarchicalGraph.enable_sharding(shard_graph=True)`` is on.  Every method is a collective:
+    all ranks call it with the same (replicated) batch and all get the whole answer."""
+
+    def __init__(self, sg: ShardedGraph) -> None:
+        self.sg = sg
+        self.device = sg.shard.device
+        self.n_nodes = sg.shard.n_nodes
+
+    def nbytes(self) -> int:
+        return self.sg.shard.nbytes()
+
+    def anchor_rerank(self, seeds: torch.Tensor, seed_scores: torch.Tensor, params, top_k: int, want_cluster: bool = True,
+                      row_to_node: Optional[torch.Tensor] = None):
+        if row_to_node is not None:  # index rows -> dense node ids (-1: padding or a row that is no node any more)
+            rows = seeds.to(torch.int64)
+            ok = (rows >= 0) & (rows < row_to_node.numel())
+            seeds = torch.where(ok, row_to_node[rows.clamp(0, max(0, row_to_node.numel() - 1))], torch.full_like(rows, -1, dtype=torch.int32))
+        return self.sg.anchor_rerank(seeds.to(torch.int32).contiguous(), seed_scores.contiguous(), params, int(top_k), want_cluster)
+
+    def expand(self, ops: torch.Tensor, in_ids: torch.Tensor, in_offsets: torch.Tensor, limit: int = 10):
+        lens = in_offsets[1:] - in_offsets[:-1]
+        max_ids = max(1, int(lens.max().item())) if lens.numel() else 1
+        return self.sg.expand(ops, in_ids, in_offsets, limit=int(limit), max_ids=max_ids)
+
+    def lca_closure(self, *a, **k):
+        raise NotImplementedError("expand_to_lca runs on a replicated graph: enable_sharding(shard_graph=False)")

@@ -58,6 +58,7 @@ class HierarchicalGraph:
         self._host_arrays: Optional[Tuple[Any, Dict[str, Any]]] = None
         self._st_model = None
         self._st_name: Optional[str] = None
+        self._shard: Optional[Dict[str, Any]] = None  # set by enable_sharding(): multi-GPU form of the same API
 
     # ------------------------------------------------------------------ ids (hierarchical_graph.py:56-69)
     @staticmethod
@@ -530,12 +531,38 @@ class HierarchicalGraph:
             self._host_arrays = (sig, self._export_arrays())
         return self._host_arrays[1]
 
+    def enable_sharding(self, group=None, shard_graph: bool = False, peer_exchange: bool = True) -> None:
+        """Multi-GPU form of the SAME API (one process per GPU under ``torchrun``, ``torch.distributed`` initialised, every
+        rank holding the same graph directory and vector index): the embedding index is sharded by row range over the ranks
+        (K1 on the local rows, one candidate exchange, device merge -- ``dist.ShardedIndex``), and with ``shard_graph`` the
+        CSR and the node attributes by node range as well (``dist.ShardedGraph``; otherwise the graph stays replicated).
+        ``search`` / ``search_batch`` / ``GraphEnvironment`` / ``NaiveRAG`` then are collectives: every rank calls them with
+        the same arguments and gets the same, unsharded-identical result."""
+        self._shard = {"group": group, "graph": bool(shard_graph), "peer": bool(peer_exchange)}
+        self._dev_graph = None
+        self._dev_index = None
+
+    @staticmethod
+    def _world(shard: Dict[str, Any]) -> int:
+        import torch.distributed as tdist
+        if not tdist.is_initialized():
+            raise RuntimeError("enable_sharding needs torch.distributed to be initialised (one process per GPU, torchrun)")
+        return tdist.get_world_size(shard["group"])
+
     def _device_graph(self) -> Dict[str, Any]:
         sig = self._graph_sig()
         if self._dev_graph is None or self._dev_graph["sig"] != sig:
             from .. import engine
             arrays = self._graph_arrays()
-            self._dev_graph = {"sig": sig, "arrays": arrays, "csr": engine.GraphCSR(arrays, self.device)}
+            shard = getattr(self, "_shard", None)
+            if shard is not None and shard["graph"]:
+                from .. import dist as dist_mod
+                import torch
+                dev = torch.device(self.device) if self.device != "cuda" else torch.device("cuda", torch.cuda.current_device())
+                csr = dist_mod.ShardedGraphCSR(dist_mod.ShardedGraph.from_arrays(arrays, dev, shard["group"]))
+            else:
+                csr = engine.GraphCSR(arrays, self.device)
+            self._dev_graph = {"sig": sig, "arrays": arrays, "csr": csr}
             self._dev_index = None  # row -> node map depends on dense ids
         return self._dev_graph
 
@@ -573,7 +600,19 @@ class HierarchicalGraph:
                 rows_dev = rows.to(dev).contiguous()
             dense = dg["arrays"]["dense"]
             row_to_node = torch.tensor([dense.get(n, -1) for n in store.ids], dtype=torch.int32, device=dev)
-            index = engine.VectorIndex(rows_dev) if len(store.ids) else None
+            shard = getattr(self, "_shard", None)
+            if shard is not None and len(store.ids) >= 2 * self._world(shard):  # (a handful of rows stays replicated)
+                # this rank keeps rows [lo, hi) only; ids stay global (id_base), the merge restores the unsharded order
+                from .. import dist as dist_mod
+                import torch.distributed as tdist
+                world, rank = self._world(shard), tdist.get_rank(shard["group"])
+                lo, hi = dist_mod.shard_bounds(len(store.ids), world, rank)
+                index = dist_mod.ShardedIndex.from_rows(rows_dev[lo:hi].clone().contiguous(), id_base=lo, group=shard["group"])
+                if shard["peer"]:
+                    index.enable_peer_exchange(4096, 128)
+                del rows_dev
+            else:
+                index = engine.VectorIndex(rows_dev) if len(store.ids) else None
             cur = {"db_path": db_path, "stamp": stamp, "dtype": self.index_dtype, "store": store, "index": index,
                    "row_to_node": row_to_node}
             self._dev_index = cur
