@@ -206,7 +206,8 @@ class DeviceVecAHRAGGymEnv:
         if len(query_embeddings) != self.n_envs:
             raise ValueError(f"expected {self.n_envs} query embeddings, got {len(query_embeddings)}")
         hg = self.hg
-        csr = hg._device_graph()["csr"]
+        dg = hg._device_graph()
+        csr = dg["csr"]
         if csr is not self.csr:  # the graph changed since the last episode: new device graph, fresh environment state
             from ..engine import EnvBatchState
             self.csr = csr
@@ -214,7 +215,8 @@ class DeviceVecAHRAGGymEnv:
         # GraphEnvironment.reset -> semantic_anchor(top_k=5, member_top_m=5), no weights / filters set (:155-241)
         params = hg._resolve(5, None, None, None, None, None, None, None)
         db_path, _ = hg._resolve_index(None, "unused")
-        n_index = len(hg._device_index(db_path)["store"].ids)
+        di = hg._device_index(db_path, dg)
+        n_index = len(di["store"].ids)
         top_k = 5
         dev = self.csr.device
         if n_index == 0:  # un-built index: empty anchor, as the reference's empty collection returns
@@ -224,7 +226,7 @@ class DeviceVecAHRAGGymEnv:
                    "count": torch.zeros((self.n_envs,), dtype=torch.int32, device=dev)}
             n_seeds = 0
         else:
-            out, rows = hg._device_search(query_embeddings, top_k, params, False, db_path)
+            out, rows = hg._device_search(query_embeddings, top_k, params, False, db_path, dg, di)
             n_seeds = int(rows.shape[1])
         return self.batch.reset(out, n_seeds)
 

@@ -20,7 +20,8 @@ all-gather + device k-way merge.
   parity_check : after the timed loops, at every N: sampled queries of the timed batch (bf16 mode: recall@k and score
              tolerance; fp32-exact mode: ids and score bits) against oracle/exact_topk.c scanning ALL corpus rows on
              the host (every rank scans its own shard, rank 0 merges with the same total order).
-  extra    : driver-timed figures for the other BASELINE configurations -- c2 (substitute: 450k x 384 fp32 index, 7405
+  extra    : driver-timed figures for the other BASELINE configurations -- c1 (the hotpotqa_mini graph through the drop-in
+             Python API, B = 64 and B = 1, the reference's algorithm on one host core beside it), c2 (substitute: 450k x 384 fp32 index, 7405
              queries, fp32-exact top-5 + anchor expansion + rerank, one replica per GPU), c4 (100M x 768, 256-query batch: the real
              sharded configuration at N > 1, the per-GPU shard of the 8-GPU case at N = 1) and c5 (20M-node / 500M-edge
              graph, 1024 environments: hop 1, hop 2, uncapped-walk bandwidth, gym rollout) with the graph-half CPU
@@ -384,7 +385,7 @@ def main() -> int:
         torch.cuda.empty_cache()
         import bench_workloads as bw
         extra = {}
-        for name, fn in (("c2", bw.extra_c2), ("c4", bw.extra_c4), ("c5", bw.extra_c5)):
+        for name, fn in (("c1", bw.extra_c1), ("c2", bw.extra_c2), ("c4", bw.extra_c4), ("c5", bw.extra_c5)):
             try:  # a failing side block must not take the headline line with it; the error is reported in its place
                 extra[name] = fn(dist, world, rank, device)
             except Exception as e:  # noqa: BLE001

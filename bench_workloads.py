@@ -583,6 +583,89 @@ def extra_c4(dist, world, rank, dev, steps=10):
     return out
 
 
+def extra_c1(dist, world, rank, dev):
+    """configs[0]: the samples/hotpotqa_mini.txt graph (413 nodes; fixture tests/golden/g_c1_hotpotqa_mini.*, every expected
+    value written by the unmodified reference) on the test_graph_search path, THROUGH THE DROP-IN Python API: the 64 queries
+    of the fixture as one `search_batch` (B = 64) + the 2-hop step (`expand_related` on each query's best node), and
+    `search("Tim Burton", top_k=3)` alone (B = 1) -- host in, Python dicts out.  Beside it the same calls through the oracle's
+    restatement of the reference (NetworkX walks + per-query loop, one host core).  One replica per GPU; rank 0 reports."""
+    import copy
+    import shutil
+    import tempfile
+    from ah_rag_b200 import synth
+    from ah_rag_b200.graph.hierarchical_graph import HierarchicalGraph
+    from tests import golden_util as gu
+    fx = gu.load("g_c1_hotpotqa_mini")
+    tmp = tempfile.mkdtemp(prefix=f"ahr_c1_r{rank}_")
+    try:
+        gdir, db = os.path.join(tmp, "graph"), os.path.join(tmp, "vector_db")
+        nl = copy.deepcopy(fx["node_link"])
+        nl["graph"]["vector_index"]["db_path"] = db
+        synth.write_graph_dir(gdir, nl)
+        hg = HierarchicalGraph.load(gdir)
+        hg.device = str(dev)
+        qmap = {q_: fx["query_vecs"][i] for i, q_ in enumerate(fx["queries"])}
+        hg.set_embedder(lambda texts: np.stack([qmap[t] for t in texts]))
+        hg.build_vector_index(db, layers={0, 1, 2}, reset=True, embeddings={nid: fx["index_rows"][r] for r, nid in enumerate(fx["index_ids"])})
+        dg = hg._device_graph()
+        dense, names, csr = dg["arrays"]["dense"], dg["arrays"]["node_ids"], dg["csr"]
+        nq = len(fx["queries"])
+        ops = torch.full((nq,), 2, dtype=torch.int32, device=dev)
+        offs = torch.arange(nq + 1, dtype=torch.int32, device=dev)
+
+        def two_hops():
+            outs = hg.search_batch(fx["query_vecs"], top_k=5)
+            first = torch.tensor([dense[o[0]["node_id"]] if o else -1 for o in outs], dtype=torch.int32, device=dev)
+            oi, oc = csr.expand(ops, first, offs, 10)
+            oi, oc = oi.tolist(), oc.tolist()
+            return outs, [[names[v] for v in oi[b][:oc[b]]] for b in range(nq)]
+
+        def wall(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps
+
+        outs, hop2 = two_hops()
+        t_b64 = wall(two_hops, 20)
+        t_b1 = wall(lambda: hg.search("Tim Burton", top_k=3), 50)
+        res = {"workload": f"c1: samples/hotpotqa_mini.txt graph ({len(names)} nodes, {len(fx['index_ids'])} index rows x {fx['index_rows'].shape[1]} fp32), "
+                           f"{nq} queries, top_k=5 + expand_related of the best node, through HierarchicalGraph.search_batch (fp32-exact mode)",
+               "n_gpus": world, "b64_two_hops_ms": t_b64 * 1e3, "b64_queries_per_s": nq / t_b64,
+               "b1_search_tim_burton_top3_ms": t_b1 * 1e3, "timing": "wall clock around the Python call (host vectors in, Python dicts out)"}
+        if rank == 0:
+            from oracle import ref_search  # checker + reported CPU baseline, never the measured path
+            want = {c["query"]: c["out"]["reranked"] for c in fx["search"] if c["kwargs"] == {"top_k": 5}}
+            ok1 = all(gu.canon(outs[q_]) == gu.canon(w) for q_, w in want.items())
+            og = ref_search.OracleGraph(copy.deepcopy(fx["node_link"]))
+            env = ref_search.OracleEnv(og, fx["index_ids"], fx["index_rows"])
+
+            def cpu_pass():
+                out = []
+                for b in range(nq):
+                    rr = env.search(fx["query_vecs"][b], 5)["reranked"]
+                    out.append(ref_search.expand(og, "related", [rr[0]["node_id"]] if rr else [], 10))
+                return out
+
+            cpu_hop2 = cpu_pass()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                cpu_pass()
+            t_cpu = (time.perf_counter() - t0) / 3
+            res["parity_check"] = {"search_equals_reference_goldens": bool(ok1), "golden_cases": len(want),
+                                   "expand_related_equals_oracle": bool(cpu_hop2 == hop2)}
+            res["cpu_baseline"] = {"value": nq / t_cpu, "unit": "queries/s (search top_k=5 + expand_related)", "cores": 1, "kind": "port",
+                                   "sample": f"oracle/ref_search.py (the reference's algorithm over NetworkX, brute-force cosine in numpy) "
+                                             f"sequential loop over the {nq} queries, {t_cpu * 1e3:.1f} ms per pass"}
+        del hg
+        return res
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def extra_c2(dist, world, rank, dev):
     """configs[1] substitute (the shipped hotpotqa_distractor graph is empty): a HotpotQA-scale synthetic graph
     (500k nodes), a 450k x 384 fp32 index (MiniLM-shaped rows, entities + summaries), all 7405 dev questions in one batch,
