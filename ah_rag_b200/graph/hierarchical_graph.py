@@ -618,6 +618,19 @@ class HierarchicalGraph:
             self._dev_index = cur
         return cur
 
+    def _stage(self, key: str, t):
+        """Asynchronous device -> host copy of ``t`` into a pinned buffer kept per output name (grown when needed); valid
+        after the caller synchronises the stream, overwritten by the next call."""
+        import torch
+        pool = self.__dict__.setdefault("_pinned", {})
+        buf = pool.get(key)
+        n = t.numel()
+        if buf is None or buf.dtype != t.dtype or buf.numel() < n:
+            buf = pool[key] = torch.empty((max(n, 64),), dtype=t.dtype).pin_memory()
+        view = buf[:n].view(t.shape)
+        view.copy_(t, non_blocking=True)
+        return view
+
     def invalidate_device_cache(self) -> None:
         """Call after editing nodes / edges / attributes behind the class's back (``hg.G...``): the next search exports the
         graph again by walking NetworkX (the on-disk snapshot describes the document as loaded, not the edited graph)."""
@@ -710,9 +723,14 @@ class HierarchicalGraph:
             return [dict(empty) if return_cluster else [] for _ in range(B)]
         k_eff = min(int(top_k), n_index)  # Chroma returns at most the collection size
         out, rows = self._device_search(query_embeddings, int(top_k), params, return_cluster, db_path, dg, di)
-        # one device -> host copy per output, then plain Python lists (numpy scalar indexing would dominate the loop)
-        host = {k: v.cpu().numpy().tolist() for k, v in out.items()}
-        rows_h = rows.cpu().numpy().tolist() if return_cluster else None
+        # every output into its pinned staging buffer without waiting, ONE synchronisation for the lot (a `.cpu()` per
+        # tensor is a 16 us round trip each), then plain Python lists (numpy scalar indexing would dominate the loop)
+        import torch
+        staged = {k: self._stage(k, v) for k, v in out.items()}
+        rows_st = self._stage("rows", rows) if return_cluster else None
+        torch.cuda.current_stream(rows.device).synchronize()
+        host = {k: v.numpy().tolist() for k, v in staged.items()}
+        rows_h = rows_st.numpy().tolist() if return_cluster else None
         node_ids, nodes_view = arrays["node_ids"], self.G.nodes
         judge_arr = arrays["judge"]  # float(js["overall"]) per node, NaN = None: the value `search` re-parses per result
         results: List[Any] = []
