@@ -756,6 +756,16 @@ def extra_c5(dist, world, rank, dev, scale=1.0, cpu_budget_s=6.0):
     bi = big_in.long()
     deg = (rp_o[bi + 1] - rp_o[bi]) + (rp_i[bi + 1] - rp_i[bi])
     bw_bytes = int(deg.sum().item()) * 4 + nb * (2 * 16 + 4) + nb * 512 * 4  # col_idx + row_ptr pairs + ids in + ids out
+    # hop 1 at a batch that fills the machine (bandwidth view of the anchor kernel): 65536 queries x 50 seeds
+    nb1 = 65536 // world
+    seeds_b, scores_b, _ = c5_inputs(a, nb1, n_seeds, dev, seed=17 + rank)
+    outb = g.anchor_rerank(seeds_b, scores_b, prm, top_k, want_cluster=False)
+    ms_h1_bw = _timed_dist(dist, world, dev, lambda: g.anchor_rerank(seeds_b, scores_b, prm, top_k, want_cluster=False), steps=10)
+    # algorithmic bytes: seed id + score in, one 64-byte line per seed, one 32-byte head per first occurrence, results out
+    h1_bytes = nb1 * n_seeds * (4 + 4 + 64) + int(outb["count"].sum().item()) * 0 + nb1 * top_k * (4 + 8 + 8) + nb1 * 4
+    h1_heads = int((g.anchor_rerank(seeds_b[:4096], scores_b[:4096], prm, top_k)["exp_count"]).sum().item()) * (nb1 // 4096)
+    h1_bytes += h1_heads * 32
+    del outb
     # device gym rollout: reset from a top-5 anchor + 6 steps
     envb = engine.EnvBatchState(g, n_env, max_steps=6)
     rr5 = g.anchor_rerank(seeds_l[:, :5].contiguous(), scores_l[:, :5].contiguous(), prm, 5, want_cluster=False)
@@ -781,6 +791,10 @@ def extra_c5(dist, world, rank, dev, scale=1.0, cpu_budget_s=6.0):
            "uncapped_walk": {"frontier_nodes_per_gpu": nb, "ms": ms_bw, "algorithmic_bytes_per_gpu": bw_bytes,
                              "useful_gbs_per_gpu": bw_bytes / (ms_bw * 1e-3) / 1e9,
                              "frac_of_hbm": bw_bytes / (ms_bw * 1e-3) / 1e9 / hbm},
+           "hop1_bandwidth_view": {"queries_per_gpu": nb1, "seeds": n_seeds, "ms": ms_h1_bw, "seeds_per_s_per_gpu": nb1 * n_seeds / ms_h1_bw * 1e3,
+                                   "algorithmic_bytes_per_gpu": h1_bytes, "useful_gbs_per_gpu": h1_bytes / (ms_h1_bw * 1e-3) / 1e9,
+                                   "frac_of_hbm": h1_bytes / (ms_h1_bw * 1e-3) / 1e9 / hbm,
+                                   "note": "random 64-byte lines + 32-byte heads: the binding roofline is the random-sector rate of HBM, not the copy bandwidth"},
            "gym_rollout_reset_plus_6_steps_ms": ms_roll, "gym_env_steps_per_s": n_env_total * 6 / ms_roll * 1e3,
            "gym_rollout_cuda_graph_ms": ms_roll_graph, "gym_env_steps_per_s_cuda_graph": n_env_total * 6 / ms_roll_graph * 1e3,
            "hbm_peak_gbs": hbm, "peak_source": src}
