@@ -201,3 +201,26 @@ def test_expand_large_limits_rows_with_repeated_neighbours(limit):
     oi, oc = oi.cpu().numpy(), oc.cpu().numpy()
     for e in range(240):
         assert list(oi[e, :oc[e]]) == array_graph.expand(a, ops[e], ids[offs[e]:offs[e + 1]], limit), (limit, e, ops[e])
+
+
+@pytest.mark.parametrize("alpha,delta", [(0.6, 0.1), (250.0, 0.1), (3.0e6, -4.0e5), (-0.6, 2000.0)])
+def test_anchor_rerank_sort_keys_small_and_large_scores(engine, alpha, delta):
+    """The stable sort of the rerank uses one 32-bit key per entry while every rounded score is below 2^20 / 1e4 in
+    magnitude and the general (double, position) comparison beyond it: weights that put scores inside the fast range, right
+    across its edge (alpha = 250: a few entries above 104.8576), far outside and negative -- same order as the reference's
+    `sorted(..., key=score, reverse=True)` (hierarchical_graph.py:781), many ties included (expansions share their seed's
+    semantic, so equal rounded scores are common)."""
+    rng = np.random.default_rng(int(abs(alpha)) + 7)
+    nl = synth.make_graph(seed=77, n_entities=500, n_l1=10, n_l2=3, n_hyperedges=200, related_density=0.3)
+    og, arrays, g = _setup(engine, nl)
+    nodes = arrays["node_ids"]
+    nq, ns, top_k = 48, 40, 60
+    sn = np.stack([rng.permutation(len(nodes))[:ns] for _ in range(nq)]).astype(np.int32)
+    ss = np.round(np.sort(rng.uniform(0.05, 0.95, size=(nq, ns)), axis=1)[:, ::-1], 2).astype(np.float32)  # coarse: ties
+    prm = ref_search.resolve_params(og, member_top_m=5, alpha=alpha, delta=delta)
+    out = g.anchor_rerank(torch.from_numpy(sn).cuda(), torch.from_numpy(ss.copy()).cuda(), _params(engine, prm), top_k)
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    for q in range(nq):
+        want = ref_search.anchor_rerank(og, ref_search.seeds_from_topk([nodes[i] for i in sn[q]], ss[q]), top_k, prm)
+        got = [(nodes[out["nodes"][q, j]], float(out["semantic"][q, j]), float(out["score"][q, j])) for j in range(out["count"][q])]
+        assert got == [(r["node_id"], r["semantic"], r["score"]) for r in want["reranked"]], (alpha, delta, q)
