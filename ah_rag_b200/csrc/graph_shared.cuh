@@ -21,7 +21,9 @@ __device__ __forceinline__ bool expand_push(ExpandState &st, int32_t val, bool v
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   st.raw += __popc(vmask);
   // duplicates inside this batch of 32: the lowest lane carrying the value is the first occurrence
-  const unsigned peers = __match_any_sync(0xffffffffu, valid ? val : (int32_t)(-2 - lane));
+  // (MATCH.ANY costs ~2 cycles of an SM-wide unit per DISTINCT value, tools/ub/ub_match.cu: the lanes without a value share
+  // one sentinel instead of 32 different ones)
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? val : (int32_t)-2);
   const bool first_in_batch = (__ffs(peers & vmask) - 1) == lane;
   bool dup = false;
   if (valid)
