@@ -16,7 +16,7 @@ struct ExpandState {
 };
 
 // append values to the order-preserving unique list; returns true once the list is full
-// (limits up to 64: the list is scanned per candidate; larger limits take the edge-parallel kernel of graph.cu)
+// (limits up to 64: the list is scanned per candidate; larger limits take the hash-set kernel of graph.cu)
 __device__ __forceinline__ bool expand_push(ExpandState &st, int32_t val, bool valid, int lane) {
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   st.raw += __popc(vmask);

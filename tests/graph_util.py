@@ -4,7 +4,7 @@ import numpy as np
 
 def random_csr(rng, n_ent, n_sum, n_hyp, hub_deg):
     """CSR arrays built directly (dense ids: entities | summaries | hyperedges), with hub nodes whose lists are longer
-    than one round of the edge-parallel kernel (1024 / 2048 positions) and plenty of duplicates across segments."""
+    than many batches of the hash-set kernel and plenty of duplicates across segments."""
     n = n_ent + n_sum + n_hyp
     s0, h0 = n_ent, n_ent + n_sum
 

@@ -41,7 +41,7 @@ def case_graph():
     ops = torch.tensor([0, 1, 2] * 16, dtype=torch.int32).cuda()
     ids = torch.from_numpy(rng.integers(0, n, 96).astype(np.int32)).cuda()
     offs = torch.arange(0, 97, 2, dtype=torch.int32).cuda()
-    for limit in (10, 200):  # warp walker, edge-parallel kernel
+    for limit in (10, 200):  # warp walker, hash-set kernel
         oi, oc = g.expand(ops, ids, offs, limit)
         oi, oc, idh = oi.cpu().numpy(), oc.cpu().numpy(), ids.cpu().numpy()
         for e in range(48):
