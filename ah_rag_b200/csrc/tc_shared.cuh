@@ -32,7 +32,13 @@ struct TcParams {
   uint32_t *thr_shared;  // optional [n_slabs][q_rows]: what every slab has published for every query (see "shared bound")
   int32_t q_rows;        // row pitch of thr_shared (queries padded to whole tiles)
   int32_t bound_m;       // each slab publishes the bound_m-th best score of its list: n_slabs * bound_m >= k
+  int32_t list_filter;   // 1 (default): a full list is first filtered against its risen threshold; AHR_TC_LIST_FILTER=0: A/B knob
 };
+
+inline int tc_list_filter_default() {
+  static const int v = getenv("AHR_TC_LIST_FILTER") ? atoi(getenv("AHR_TC_LIST_FILTER")) : 1;
+  return v != 0;
+}
 
 // Optional knobs of a K1 launch (host side).
 struct TcExtra {
@@ -211,6 +217,31 @@ static __device__ __noinline__ float warp_list_compact(uint32_t list_addr, int c
   return cnt >= k ? orderable_float((uint32_t)(kth >> 32)) : -INFINITY;
 }
 
+// All 32 lanes call.  Drops from a FULL list every entry that no longer beats `thr` (the row's threshold has risen since
+// the entry was appended: a compaction, or the shared bound that arrives while an item's first tile is being scanned)
+// and closes the gaps, order preserved.  ~25 instructions against ~400 for the sort: when it frees enough slots the sort
+// is skipped.  Returns the number of entries left.
+template <int KLIST>
+static __device__ __noinline__ int warp_list_filter(uint32_t list_addr, float thr) {
+  constexpr int NPL = KLIST / 32;
+  const int lane = threadIdx.x & 31;
+  unsigned long long key[NPL];
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) key[r] = lds_u64(list_addr + (r * 32 + lane) * 8);
+  __syncwarp();  // every slot is in registers before any is overwritten
+  int base = 0;
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) {
+    const bool keep = orderable_float((uint32_t)(key[r] >> 32)) > thr;  // the admission rule of the append path
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) sts_u64(list_addr + (base + __popc(m & ((1u << lane) - 1u))) * 8, key[r]);
+    base += __popc(m);
+  }
+  __syncwarp();
+  return base;
+}
+
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -227,7 +258,7 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
 template <int KLIST>
 static __device__ __noinline__ void epilogue_overflow(uint32_t scratch_lane, unsigned pending, int k, int32_t id0,
                                                       uint32_t lists_warp, float &thr_ref, int &cnt_ref,
-                                                      uint32_t *bound_slot, int bound_m) {
+                                                      uint32_t *bound_slot, int bound_m, bool filter) {
   const int lane = threadIdx.x & 31;
   const uint32_t my_list = lists_warp + (uint32_t)lane * (KLIST * 8);
   float thr = thr_ref;
@@ -247,9 +278,16 @@ static __device__ __noinline__ void epilogue_overflow(uint32_t scratch_lane, uns
     while (full) {
       const int owner = __ffs(full) - 1;
       full &= full - 1;
-      const float kth = warp_list_compact<KLIST>(lists_warp + (uint32_t)owner * (KLIST * 8), KLIST, k);
+      // entries appended under an older, weaker threshold first: often most of the list (first tile of an item, once the
+      // other slabs have published), and then there is nothing to sort
+      const int left = filter ? warp_list_filter<KLIST>(lists_warp + (uint32_t)owner * (KLIST * 8), __shfl_sync(0xffffffffu, thr, owner)) : KLIST;
+      if (left <= KLIST - KLIST / 8) {
+        if (lane == owner) cnt = left;
+        continue;
+      }
+      const float kth = warp_list_compact<KLIST>(lists_warp + (uint32_t)owner * (KLIST * 8), left, k);
       if (lane == owner) {
-        cnt = k;
+        cnt = min(left, k);
         thr = fmaxf(thr, kth);  // never below a bound taken from thr_shared
         // the list is sorted now: its bound_m-th best score goes to the other slabs (single writer, only ever grows)
         if (bound_slot != nullptr) st_relaxed_u32(bound_slot, (uint32_t)(lds_u64(my_list + (bound_m - 1) * 8) >> 32));
@@ -327,9 +365,16 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bo
           st_relaxed_u32(bound_slot, float_orderable(cmax));
         }
       }
-      // a full list is compacted right away, even with nothing pending: its threshold is stale
-      if (__any_sync(0xffffffffu, cnt == KLIST))
-        epilogue_overflow<KLIST>(scratch_lane, pending, k, (int32_t)(col0 + c), lists_warp, thr, cnt, bound_slot, bound_m);
+      // a full list is compacted right away, even with nothing pending: its threshold is stale.  In the first tile of an
+      // item the lists fill before the first look at the shared bound (64 columns, all admitted): look now, so that the
+      // overflow path can drop what the bound excludes instead of sorting it
+      if (__any_sync(0xffffffffu, cnt == KLIST)) {
+        // (only where a list publishes its running maximum, bound_m == 1: with bound_m > 1 the value to publish is read
+        // from the SORTED list, and skipping sorts starved the other slabs of bounds -- Q = 512 / 1024 ran 3 % slower)
+        const bool filter = p.list_filter != 0 && bound_m == 1;
+        if (young && filter) thr = shared_bound_apply(shared_bound_peek(p, q_global, bound_slot != nullptr), thr);
+        epilogue_overflow<KLIST>(scratch_lane, pending, k, (int32_t)(col0 + c), lists_warp, thr, cnt, bound_slot, bound_m, filter);
+      }
     }
   };
 #pragma unroll 1

@@ -286,6 +286,7 @@ int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows
   p.thr_shared = n_slabs > 1 ? ex.thr_shared : nullptr;  // one slab: its own threshold is the bound
   p.q_rows = std::max(ex.q_rows, nq);
   p.bound_m = (k + n_slabs - 1) / n_slabs;
+  p.list_filter = tc_list_filter_default();
   p.nq = nq;
   p.dim = dim;
   p.n_qtiles = (nq + TC_BM - 1) / TC_BM;

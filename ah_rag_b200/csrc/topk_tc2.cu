@@ -338,6 +338,7 @@ int tc2_topk_partials(const CUtensorMap &map_x, const CUtensorMap *map_x_lo, con
   p.thr_shared = n_slabs > 1 ? ex.thr_shared : nullptr;  // one slab: its own threshold is the bound
   p.q_rows = std::max(ex.q_rows, nq);
   p.bound_m = (k + n_slabs - 1) / n_slabs;
+  p.list_filter = tc_list_filter_default();
   p.nq = nq;
   p.dim = dim;
   p.n_qtiles = (nq + 2 * T2_BM - 1) / (2 * T2_BM);
