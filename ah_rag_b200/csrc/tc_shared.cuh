@@ -37,7 +37,7 @@ struct TcParams {
 
 inline int tc_list_filter_default() {
   static const int v = getenv("AHR_TC_LIST_FILTER") ? atoi(getenv("AHR_TC_LIST_FILTER")) : 1;
-  return v != 0;
+  return v;
 }
 
 // Optional knobs of a K1 launch (host side).
@@ -371,7 +371,7 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bo
       if (__any_sync(0xffffffffu, cnt == KLIST)) {
         // (only where a list publishes its running maximum, bound_m == 1: with bound_m > 1 the value to publish is read
         // from the SORTED list, and skipping sorts starved the other slabs of bounds -- Q = 512 / 1024 ran 3 % slower)
-        const bool filter = p.list_filter != 0 && bound_m == 1;
+        const bool filter = p.list_filter != 0 && (bound_m == 1 || p.list_filter == 2);  // 2: experiment knob, every list
         if (young && filter) thr = shared_bound_apply(shared_bound_peek(p, q_global, bound_slot != nullptr), thr);
         epilogue_overflow<KLIST>(scratch_lane, pending, k, (int32_t)(col0 + c), lists_warp, thr, cnt, bound_slot, bound_m, filter);
       }
