@@ -594,23 +594,22 @@ class HierarchicalGraph:
             store = vector_store.VectorStore.open(db_path)
             rows = torch.from_numpy(np.ascontiguousarray(store.rows, dtype=np.float32))
             dev = dg["csr"].device
-            if self.index_dtype == "bf16":
-                rows_dev = rows.to(dev).to(torch.bfloat16).contiguous()
-            else:
-                rows_dev = rows.to(dev).contiguous()
             dense = dg["arrays"]["dense"]
             row_to_node = torch.tensor([dense.get(n, -1) for n in store.ids], dtype=torch.int32, device=dev)
             shard = getattr(self, "_shard", None)
-            if shard is not None and len(store.ids) >= 2 * self._world(shard):  # (a handful of rows stays replicated)
-                # this rank keeps rows [lo, hi) only; ids stay global (id_base), the merge restores the unsharded order
+            sharded = shard is not None and len(store.ids) >= 2 * self._world(shard)  # (a handful of rows stays replicated)
+            lo, hi = 0, len(store.ids)
+            if sharded:
+                # this rank uploads rows [lo, hi) only; ids stay global (id_base), the merge restores the unsharded order
                 from .. import dist as dist_mod
                 import torch.distributed as tdist
-                world, rank = self._world(shard), tdist.get_rank(shard["group"])
-                lo, hi = dist_mod.shard_bounds(len(store.ids), world, rank)
-                index = dist_mod.ShardedIndex.from_rows(rows_dev[lo:hi].clone().contiguous(), id_base=lo, group=shard["group"])
+                lo, hi = dist_mod.shard_bounds(len(store.ids), self._world(shard), tdist.get_rank(shard["group"]))
+            rows_dev = rows[lo:hi].to(dev)
+            rows_dev = (rows_dev.to(torch.bfloat16) if self.index_dtype == "bf16" else rows_dev).contiguous()
+            if sharded:
+                index = dist_mod.ShardedIndex.from_rows(rows_dev, id_base=lo, group=shard["group"])
                 if shard["peer"]:
                     index.enable_peer_exchange(4096, 128)
-                del rows_dev
             else:
                 index = engine.VectorIndex(rows_dev) if len(store.ids) else None
             cur = {"db_path": db_path, "stamp": stamp, "dtype": self.index_dtype, "store": store, "index": index,
