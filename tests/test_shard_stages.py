@@ -153,3 +153,25 @@ def test_staged_anchor_rerank_equals_whole_graph(world):
     got = shard_stages.anchor_merge(n, bounds, seeds, scores, top_k, 2, m, g1, g2)
     for q in range(nq):
         assert got[q] == array_graph.anchor_rerank(a, seeds[q], scores[q], top_k, m), (world, q)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_node_range_bounds_cover_and_balance(world):
+    """dist.node_range_bounds: contiguous node ranges that cover [0, n), identical from numpy and torch inputs, and -- with
+    balance="edges" -- of near-equal CSR volume on a graph whose adjacency sits in a narrow id range (the c5 shape)."""
+    import torch
+    from ah_rag_b200.dist import node_range_bounds
+    rng = np.random.default_rng(world)
+    a = random_csr(rng, n_ent=4000, n_sum=400, n_hyp=300, hub_deg=3000)
+    n = a["n_nodes"]
+    for balance in ("nodes", "edges"):
+        b = node_range_bounds(a, world, balance)
+        assert len(b) == world + 1 and b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+        at = {"n_nodes": n, "row_ptr": [torch.from_numpy(np.asarray(x)) for x in a["row_ptr"]]}
+        assert node_range_bounds(at, world, balance) == b
+    b = node_range_bounds(a, world, "edges")
+    vol = [sum(int(rp[b[r + 1]] - rp[b[r]]) for rp in a["row_ptr"]) + 10 * (b[r + 1] - b[r]) for r in range(world)]
+    hub = max(sum(int(rp[v + 1] - rp[v]) for rp in a["row_ptr"]) for v in (4000, 4001)) + 10  # one row cannot be split
+    assert max(vol) <= sum(vol) / world + hub
+    with pytest.raises(ValueError):
+        node_range_bounds(a, 2, "rows")
