@@ -117,9 +117,46 @@ class ShardedIndex:
             peer.close()
         return False
 
+    def topk_async(self, q: torch.Tensor, k: int, mode: str = "bf16") -> "PendingTopk":
+        """Pipelined form for back-to-back batches: the local top-k of this batch runs on the caller's stream, its exchange
+        (push to the peers, wait for theirs, merge) on a side stream -- so the NEXT batch's K1 starts without waiting for
+        the slowest peer of this one, and a step no longer costs the maximum over the ranks.  The two halves of the exchange
+        buffer bound the run-ahead to one batch: batch i + 2 waits for the merge of batch i.  Safe across ranks because
+        every rank's exchanges run in order on ONE stream: a peer pushes batch i + 2 into a half only after its merge of
+        i + 1, which needed this rank's push of i + 1, which follows this rank's merge of i.
+        ``.result()`` makes the caller's current stream wait and returns (scores, ids); collective like ``topk``."""
+        peer = getattr(self, "peer", None)
+        nq = int(q.shape[0])
+        if self.world == 1 or peer is None or (nq * k) % 4 != 0 or nq * k * 12 > peer.max_record_bytes:
+            return PendingTopk(*self.topk(q, k, mode), None)
+        st = self.__dict__.setdefault("_async", {"side": torch.cuda.Stream(device=q.device), "done": []})
+        main = torch.cuda.current_stream(q.device)
+        if len(st["done"]) >= 2:
+            main.wait_event(st["done"][-2])  # the half this batch writes was read by the merge two batches ago
+        ps, pi = peer.begin(nq, k)
+        self.index.topk_raw(q, k, mode, ps, pi)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(st["side"]):
+            st["side"].wait_event(ready)
+            scores, ids = peer.exchange_merge(nq, k)
+            done = torch.cuda.Event()
+            done.record(st["side"])
+        st["done"] = st["done"][-1:] + [done]
+        return PendingTopk(scores, ids, done)
+
+    def _drain_async(self, device) -> None:
+        st = self.__dict__.get("_async")
+        if st and st["done"]:
+            main = torch.cuda.current_stream(device)
+            for ev in st["done"]:
+                main.wait_event(ev)
+            st["done"] = []
+
     def topk(self, q: torch.Tensor, k: int, mode: str = "bf16") -> Tuple[torch.Tensor, torch.Tensor]:
         if self.world == 1:
             return self.local_topk(q, k, mode)
+        self._drain_async(q.device)  # exchanges still in flight on the side stream use the same buffer halves
         nq = int(q.shape[0])
         peer = getattr(self, "peer", None)
         if peer is not None and (nq * k) % 4 == 0 and nq * k * 12 <= peer.max_record_bytes:
@@ -144,6 +181,22 @@ class ShardedIndex:
         dist.all_gather_into_tensor(gathered, mine, group=self.group)  # the single exchange of the path
         all_s, all_i = unpack_candidates(gathered, self.world, nq, k)
         return self.merge(all_s, all_i)
+
+
+class PendingTopk:
+    """Result of ``ShardedIndex.topk_async``: tensors that become valid on the caller's stream after ``result()``."""
+
+    def __init__(self, scores: torch.Tensor, ids: torch.Tensor, done) -> None:
+        self.scores, self.ids, self.done = scores, ids, done
+
+    def result(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.done is not None:
+            cur = torch.cuda.current_stream(self.scores.device)
+            cur.wait_event(self.done)
+            self.scores.record_stream(cur)  # allocated on the side stream, consumed here
+            self.ids.record_stream(cur)
+            self.done = None
+        return self.scores, self.ids
 
 
 class ShardedGraph:

@@ -329,8 +329,22 @@ def main() -> int:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1, peer-memory exchange: back-to-back batches are pipelined -- batch i is exchanged and merged on a side stream
+    # while K1 of batch i + 1 runs (dist.ShardedIndex.topk_async; at most two batches in flight, results consumed in order).
+    # Without it every step costs the maximum over the ranks of that step's K1 (profiles/r2_scaling.md).
+    pipelined = (world > 1 and getattr(sharded, "peer", None) is not None and args.mode == "bf16"
+                 and os.environ.get("AHR_BENCH_PIPELINE", "1") != "0")
+    in_flight = []
+
     def step_device():
-        return sharded.topk(q_dev, TOP_K, mode=args.mode)
+        if not pipelined:
+            return sharded.topk(q_dev, TOP_K, mode=args.mode)
+        in_flight.append(sharded.topk_async(q_dev, TOP_K, mode=args.mode))
+        return in_flight.pop(0).result() if len(in_flight) > 2 else None
+
+    def drain():
+        while in_flight:
+            in_flight.pop(0).result()
 
     def step_e2e():
         if world == 1:
@@ -349,6 +363,7 @@ def main() -> int:
         e0.record()
         for _ in range(steps):
             fn()
+        drain()  # (pipelined device loop: the last two batches' merges; a no-op otherwise)
         e1.record()
         sync_all()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
@@ -361,6 +376,7 @@ def main() -> int:
         sampler.start()
     for _ in range(max(3, args.warmup)):
         step_device()
+    drain()
     step_e2e()
 
     sampler.window_begin()
@@ -414,7 +430,9 @@ def main() -> int:
             "config": {"workload": f"c3: synthetic {N_ROWS}x{DIM} bf16 corpus (seeded N(0,1), L2-normalised), "
                                    f"{N_QUERIES}-query batch, top-k={TOP_K}, mode={args.mode}",
                        "sharding": f"node-range, {world} shard(s) of {hi - lo} rows; queries replicated; "
-                                   + (exchange if world > 1 else "no collective"),
+                                   + (exchange if world > 1 else "no collective")
+                                   + ("; device loop pipelined: batch i exchanged and merged on a side stream while K1 of "
+                                      "batch i + 1 runs (AHR_BENCH_PIPELINE=0: one stream)" if pipelined else ""),
                        "l2": "inputs larger than L2 (corpus shard %.1f GB vs 126 MB)" % ((hi - lo) * DIM * 2 / 1e9),
                        "n_slabs": prof["n_slabs"]},
             "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": N_QUERIES * DIM * 2,

@@ -49,6 +49,23 @@ def _worker(rank, world, port, q):
             for j, ((s, i), (ws, wi)) in enumerate(zip(outs, wants)):
                 if not (torch.equal(i, wi) and torch.equal(s.view(torch.int32), ws.view(torch.int32))):
                     problems.append(f"peer={use_peer} case {j} differs")
+        # pipelined form: K1 of batch i + 1 on the main stream while batch i is exchanged and merged on the side stream
+        if getattr(sh, "peer", None) is not None:
+            os.environ["AHR_EXCHANGE_FUSED"] = "1"
+            qs = [torch.from_numpy(synth.unit_rows(nq, dim, 70 + it, clustered=8)).to(dev).to(torch.bfloat16).contiguous()
+                  for it, nq in enumerate((64, 300, 300, 8, 512, 128, 128, 128, 4, 256))]
+            for rep in range(2):
+                pend = [sh.topk_async(Q, k, "bf16") for Q in qs]           # ten batches in flight, no host synchronisation
+                tail = sh.topk(qs[1], k, "bf16")                           # the synchronous call drains them first
+                got = [p_.result() for p_ in pend]
+                torch.cuda.synchronize()
+                for j, (Q, (s, i)) in enumerate(zip(qs, got)):
+                    ws, wi = full.topk(Q, k, "bf16")
+                    if not (torch.equal(i, wi) and torch.equal(s.view(torch.int32), ws.view(torch.int32))):
+                        problems.append(f"topk_async rep {rep} batch {j} differs")
+                ws, wi = full.topk(qs[1], k, "bf16")
+                if not (torch.equal(tail[1], wi) and torch.equal(tail[0].view(torch.int32), ws.view(torch.int32))):
+                    problems.append(f"topk after topk_async differs (rep {rep})")
         # the knowledge-graph CSR sharded by node range: two NCCL all-gathers per expand call (csrc/graph_shard.cu)
         from ah_rag_b200.dist import ShardedGraph
         from tests.graph_util import random_csr
