@@ -33,7 +33,27 @@ struct TcParams {
   int32_t q_rows;        // row pitch of thr_shared (queries padded to whole tiles)
   int32_t bound_m;       // each slab publishes the bound_m-th best score of its list: n_slabs * bound_m >= k
   int32_t list_filter;   // 1 (default): a full list is first filtered against its risen threshold; AHR_TC_LIST_FILTER=0: A/B knob
+  int32_t qtile_major;   // item order of the pair kernel: 0 = slab-major, 1 = query-tile-major (see tc_item_decode)
 };
+
+// item -> (slab, query tile).  Slab-major (item = slab * n_qtiles + qtile) runs the query tiles of one slab side by side:
+// the corpus tile is read once from HBM for all of them.  Query-tile-major (item = qtile * n_slabs + slab) runs the S slabs
+// of one query tile side by side: their lists publish to the shared bound TOGETHER -- with slab-major order and more items
+// than CTA pairs (c3: 144 items on 74 pairs) a query's slabs are spread over two rounds, its bound stays at "not all slabs
+// have published" for the whole first round, and every list of that round learns its threshold alone (~500 appends and
+// ~35 sorts per row).  Measured on c3 (profiles/r2_k1_q256_wait_counters.md): 2.6 % fewer cycles (MMA wait for TMEM 3.9 M ->
+// 2.4 M, slow chunks 8324 -> 5010) but 3 % MORE time -- fewer query tiles share a slab position, the corpus is read twice,
+// and under the power cap the extra HBM traffic costs more clock than the saved cycles are worth.  Kept as an experiment
+// knob (AHR_TC_ITEM_ORDER=1), off by default.
+__device__ __forceinline__ void tc_item_decode(const TcParams &p, int item, int &slab, int &qt) {
+  if (p.qtile_major) {
+    qt = item / p.n_slabs;
+    slab = item - qt * p.n_slabs;
+  } else {
+    slab = item / p.n_qtiles;
+    qt = item - slab * p.n_qtiles;
+  }
+}
 
 inline int tc_list_filter_default() {
   static const int v = getenv("AHR_TC_LIST_FILTER") ? atoi(getenv("AHR_TC_LIST_FILTER")) : 1;

@@ -110,7 +110,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       auto open_item = [&](Cursor &c) {
         c.done = c.item >= n_items;
         if (c.done) return;
-        const int slab = c.item / p.n_qtiles, qt = c.item - slab * p.n_qtiles;
+        int slab, qt;
+        tc_item_decode(p, c.item, slab, qt);
         int64_t t0;
         slab_range(p, slab, t0, c.t1);
         c.ct = t0;
@@ -183,7 +184,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       unsigned long long w_full = 0, w_tempty = 0;
       const long long t_begin = clock64();
       for (int item = cluster_id; item < n_items; item += n_clusters) {
-        const int slab = item / p.n_qtiles;
+        int slab, qt_unused;
+        tc_item_decode(p, item, slab, qt_unused);
         int64_t t0, t1;
         slab_range(p, slab, t0, t1);
         for (int64_t ct = t0; ct < t1; ++ct) {
@@ -228,7 +230,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     unsigned long long w_tfull = 0, n_slow[4] = {0, 0, 0, 0};
     unsigned long long *acct = p.stats ? &w_tfull : nullptr;  // warp-uniform (tcgen05.wait::ld is .aligned); thread 64 reports
     for (int item = cluster_id; item < n_items; item += n_clusters) {
-      const int slab = item / p.n_qtiles, qt = item % p.n_qtiles;
+      int slab, qt;
+      tc_item_decode(p, item, slab, qt);
       int64_t t0, t1;
       slab_range(p, slab, t0, t1);
       const int64_t q_first = (int64_t)qt * (2 * T2_BM) + (int64_t)rank * T2_BM + quad * 32;
@@ -339,6 +342,11 @@ int tc2_topk_partials(const CUtensorMap &map_x, const CUtensorMap *map_x_lo, con
   p.q_rows = std::max(ex.q_rows, nq);
   p.bound_m = (k + n_slabs - 1) / n_slabs;
   p.list_filter = tc_list_filter_default();
+  {
+    // slab-major unless AHR_TC_ITEM_ORDER=1 (experiment knob, see tc_item_decode)
+    static const int order_env = getenv("AHR_TC_ITEM_ORDER") ? atoi(getenv("AHR_TC_ITEM_ORDER")) : -1;
+    p.qtile_major = order_env >= 0 ? (order_env != 0) : 0;
+  }
   p.nq = nq;
   p.dim = dim;
   p.n_qtiles = (nq + 2 * T2_BM - 1) / (2 * T2_BM);
