@@ -223,7 +223,7 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
   const size_t o_ps = carve(n_part * 4), o_pi = carve(n_part * 4), o_ss = carve(n_spart * 4), o_si = carve(n_spart * 4),
-               o_ts = carve((size_t)nq * k * 4), o_ti = carve((size_t)nq * k * 8), o_tb = carve((size_t)nq_pad * 4 * std::max(S, Ss));
+               o_ts = carve((size_t)nq * k * 4), o_ti = carve((size_t)nq * k * 8), o_tb = carve((size_t)nq_pad * 4 * std::max(S, Ss) * 2);  // full + partial bound
   int rc = idx->ws.reserve(off);
   if (rc != AHR_OK) return rc;
   uint8_t *w = reinterpret_cast<uint8_t *>(idx->ws.ptr);
@@ -255,7 +255,7 @@ static int tc_topk(ahr_index *idx, const void *dev_q, int32_t nq, int32_t k, flo
   if (idx->shared_bound && !dbg_scores) {
     // what every slab publishes for every query (tc_shared.cuh, "shared bound"): 0 = nothing published yet
     ex.thr_shared = reinterpret_cast<uint32_t *>(w + o_tb);
-    AHR_CUDA_CHECK(cudaMemsetAsync(ex.thr_shared, 0, (size_t)nq_pad * 4 * S, st));
+    AHR_CUDA_CHECK(cudaMemsetAsync(ex.thr_shared, 0, (size_t)nq_pad * 4 * S * 2, st));
   }
   if (stride > 1) {
     float *ss = reinterpret_cast<float *>(w + o_ss), *ts = reinterpret_cast<float *>(w + o_ts);

@@ -34,6 +34,8 @@ struct TcParams {
   int32_t bound_m;       // each slab publishes the bound_m-th best score of its list: n_slabs * bound_m >= k
   int32_t list_filter;   // 1 (default): a full list is first filtered against its risen threshold; AHR_TC_LIST_FILTER=0: A/B knob
   int32_t qtile_major;   // item order of the pair kernel: 0 = slab-major, 1 = query-tile-major (see tc_item_decode)
+  int32_t partial_m;     // > 0: every sorted list also publishes its partial_m-th best at thr_shared + n_slabs * q_rows
+                         // ("partial bound", see shared_bound_peek); 0 = off
 };
 
 // item -> (slab, query tile).  Slab-major (item = slab * n_qtiles + qtile) runs the query tiles of one slab side by side:
@@ -166,7 +168,16 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
 __device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// minimum over the slabs of what they published for query q (0 as soon as one slab has not published)
+// minimum over the slabs of what they published for query q (0 as soon as one slab has not published).
+//
+// Partial bound.  With more items than CTA pairs (c3: 9 slabs x 16 query tiles on 74 pairs) the slabs of a query run in
+// several rounds, and until the last round starts "every slab has published" is false: the lists of the earlier rounds
+// learn their thresholds alone (~500 appends, ~35 sorts per row).  The argument behind the bound does not need every slab:
+// if P published slabs each hold >= m' rows scoring >= b'_s and P * m' >= k, the corpus holds >= k rows scoring >=
+// min b'_s.  So a sorted list also publishes its m'-th best, m' = ceil(k / slabs that run entirely in the first round)
+// (c3: 4 slabs, m' = 13), in a second array, and while the full bound is missing the minimum over the slabs that HAVE
+// published counts as soon as there are enough of them.  Weaker than the full bound (13th instead of 6th best), which takes
+// over once it exists.
 __device__ __forceinline__ uint32_t shared_bound_peek(const TcParams &p, int64_t q, bool active) {
   if (!active) return 0;
   uint32_t b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu;
@@ -177,7 +188,16 @@ __device__ __forceinline__ uint32_t shared_bound_peek(const TcParams &p, int64_t
     b1 = min(b1, ld_relaxed_u32(src + (int64_t)(s + 1) * p.q_rows));
   }
   if (s < p.n_slabs) b0 = min(b0, ld_relaxed_u32(src + (int64_t)s * p.q_rows));
-  return min(b0, b1);
+  const uint32_t full = min(b0, b1);
+  if (full != 0 || p.partial_m <= 0) return full;
+  src += (int64_t)p.n_slabs * p.q_rows;
+  uint32_t b = 0xFFFFFFFFu;
+  int have = 0;
+  for (s = 0; s < p.n_slabs; ++s) {
+    const uint32_t v = ld_relaxed_u32(src + (int64_t)s * p.q_rows);
+    if (v != 0) { b = min(b, v); ++have; }
+  }
+  return have * p.partial_m >= p.k ? b : 0;
 }
 __device__ __forceinline__ float shared_bound_apply(uint32_t bits, float thr) {
   // 0x007FFFFF is the image of -inf: anything at or below it carries no information
@@ -278,7 +298,8 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
 template <int KLIST>
 static __device__ __noinline__ void epilogue_overflow(uint32_t scratch_lane, unsigned pending, int k, int32_t id0,
                                                       uint32_t lists_warp, float &thr_ref, int &cnt_ref,
-                                                      uint32_t *bound_slot, int bound_m, bool filter) {
+                                                      uint32_t *bound_slot, int bound_m, bool filter,
+                                                      int64_t partial_off, int partial_m) {
   const int lane = threadIdx.x & 31;
   const uint32_t my_list = lists_warp + (uint32_t)lane * (KLIST * 8);
   float thr = thr_ref;
@@ -310,7 +331,12 @@ static __device__ __noinline__ void epilogue_overflow(uint32_t scratch_lane, uns
         cnt = min(left, k);
         thr = fmaxf(thr, kth);  // never below a bound taken from thr_shared
         // the list is sorted now: its bound_m-th best score goes to the other slabs (single writer, only ever grows)
-        if (bound_slot != nullptr) st_relaxed_u32(bound_slot, (uint32_t)(lds_u64(my_list + (bound_m - 1) * 8) >> 32));
+        if (bound_slot != nullptr) {
+          st_relaxed_u32(bound_slot, (uint32_t)(lds_u64(my_list + (bound_m - 1) * 8) >> 32));
+          // (partial bound: cnt >= partial_m here -- the sort ran on more than KLIST - KLIST / 8 >= k >= partial_m entries)
+          if (partial_m > 0 && cnt >= partial_m)
+            st_relaxed_u32(bound_slot + partial_off, (uint32_t)(lds_u64(my_list + (partial_m - 1) * 8) >> 32));
+        }
       }
     }
   }
@@ -393,7 +419,8 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t t_acc, int ncols, bo
         // from the SORTED list, and skipping sorts starved the other slabs of bounds -- Q = 512 / 1024 ran 3 % slower)
         const bool filter = p.list_filter != 0 && (bound_m == 1 || p.list_filter == 2);  // 2: experiment knob, every list
         if (young && filter) thr = shared_bound_apply(shared_bound_peek(p, q_global, bound_slot != nullptr), thr);
-        epilogue_overflow<KLIST>(scratch_lane, pending, k, (int32_t)(col0 + c), lists_warp, thr, cnt, bound_slot, bound_m, filter);
+        epilogue_overflow<KLIST>(scratch_lane, pending, k, (int32_t)(col0 + c), lists_warp, thr, cnt, bound_slot, bound_m, filter,
+                                 (int64_t)p.n_slabs * p.q_rows, p.partial_m);
       }
     }
   };

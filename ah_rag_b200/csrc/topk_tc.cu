@@ -288,6 +288,7 @@ int tc_topk_partials(const CUtensorMap &map_x, const void *dev_q, int64_t n_rows
   p.bound_m = (k + n_slabs - 1) / n_slabs;
   p.list_filter = tc_list_filter_default();
   p.qtile_major = 0;
+  p.partial_m = 0;
   p.nq = nq;
   p.dim = dim;
   p.n_qtiles = (nq + TC_BM - 1) / TC_BM;

@@ -359,6 +359,16 @@ int tc2_topk_partials(const CUtensorMap &map_x, const CUtensorMap *map_x_lo, con
   const int items = p.n_slabs * p.n_qtiles;
   int n_clusters = n_pairs < items ? n_pairs : items;
   if (n_clusters < 1) n_clusters = 1;
+  {
+    // partial bound (tc_shared.cuh): only when a query's slabs run in several rounds and lists publish from sorts
+    static const int partial_env = getenv("AHR_TC_PARTIAL_BOUND") ? atoi(getenv("AHR_TC_PARTIAL_BOUND")) : 1;
+    const int first_round_slabs = n_clusters / p.n_qtiles;  // slabs whose items all start in the first round (slab-major)
+    p.partial_m = 0;
+    if (partial_env && p.thr_shared != nullptr && items > n_clusters && !p.qtile_major && p.bound_m > 1 && first_round_slabs >= 1) {
+      const int m2 = (k + first_round_slabs - 1) / first_round_slabs;
+      if (m2 > p.bound_m && m2 <= k) p.partial_m = m2;
+    }
+  }
   if (dbg_scores) {
     AHR_REQUIRE(k <= 56, "debug score dump supports k <= 56");
     return tc2_launch_t<64, 4, 4, true>(map_q, map_x, map_q_lo, mx_lo, p, n_clusters, stream);
