@@ -115,6 +115,42 @@ def test_single_cta_variant_matches(engine, monkeypatch):
     assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
 
 
+@pytest.mark.parametrize("order", ["random", "ascending", "descending"])
+def test_items_in_several_rounds_partial_bound_is_exact(engine, monkeypatch, order):
+    """16 query tiles x 9 slabs on 74 CTA pairs: a query's slabs run in two rounds, which is where the PARTIAL shared bound
+    (tc_shared.cuh: lists publish their ceil(k / first-round slabs)-th best, valid as soon as enough slabs have published)
+    decides what the first round admits.  Rows ordered by similarity to the query cluster make the slabs as unequal as they
+    can be (ascending: everything that matters sits in the last slabs, after the partial bound was taken from the worst
+    ones; descending: the reverse).  bf16 mode must keep recall >= 0.999 against the exact mode, the exact mode must be bit
+    for bit the host scan on sampled queries."""
+    monkeypatch.setenv("AHR_TC_SLABS", "9")
+    n, dim, nq, k = 400_000, 64, 4096, 50
+    g = torch.Generator(device="cuda").manual_seed(77)
+    X = torch.randn((n, dim), generator=g, device="cuda")
+    X /= X.norm(dim=1, keepdim=True)
+    c = torch.randn((dim,), generator=g, device="cuda")
+    c /= c.norm()
+    Q = c[None, :] + 0.35 * torch.randn((nq, dim), generator=g, device="cuda")
+    Q = (Q / Q.norm(dim=1, keepdim=True)).to(torch.bfloat16).contiguous()
+    if order != "random":
+        X = X[torch.argsort(X @ c, descending=(order == "descending"))]
+    X = X.to(torch.bfloat16).contiguous()
+    idx = engine.VectorIndex(X)
+    idx.set_profiling(True)
+    sb, ib = idx.topk(Q, k, mode="bf16")
+    assert idx.get_profile()["n_slabs"] == 9  # 144 items on 74 pairs: two rounds
+    idx.set_profiling(False)
+    sx, ix = idx.topk(Q, k, mode="exact")
+    hit = (ib[:, :, None] == ix[:, None, :]).any(dim=2).float().sum().item()
+    assert hit / (nq * k) >= 0.999, (order, hit / (nq * k))
+    assert torch.allclose(sb, sx, rtol=1e-2, atol=1e-4)
+    sel = list(range(0, nq, 97))
+    bits = lambda t: t.view(torch.int16).cpu().numpy().view(np.uint16)
+    rs, ri = exact.exact_topk(bits(X), bits(Q[sel]), k)
+    assert np.array_equal(ix[sel].cpu().numpy(), ri), order
+    assert np.array_equal(sx[sel].cpu().numpy().view(np.uint32), rs.view(np.uint32)), order
+
+
 @pytest.mark.parametrize("nq", [1, 100, 129, 300])
 def test_variant_dispatch_and_sample_seeded_thresholds(engine, monkeypatch, nq):
     """Batch-size dispatch (one CTA per tile up to 128 queries, CTA pairs above) and the sample pass that seeds the
